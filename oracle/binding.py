@@ -1,0 +1,272 @@
+"""ctypes binding of liboutfit_oracle.so (ORACLE: test infrastructure only; see oo.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_double_p = C.POINTER(C.c_double)
+D3 = C.c_double * 3
+D9 = C.c_double * 9
+
+
+def build():
+    """Compile the oracle with gcc (oracle/Makefile)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboutfit_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _declare(_LIB)
+    return _LIB
+
+
+class IodParams(C.Structure):
+    _fields_ = [
+        ("n_noise_realizations", C.c_uint64), ("noise_scale", C.c_double), ("extf", C.c_double),
+        ("dtmax", C.c_double), ("dt_min", C.c_double), ("dt_max_triplet", C.c_double),
+        ("optimal_interval_time", C.c_double), ("max_obs_for_triplets", C.c_uint64),
+        ("max_triplets", C.c_uint32), ("gap_max", C.c_double), ("max_ecc", C.c_double),
+        ("max_perihelion_au", C.c_double), ("min_rho2_au", C.c_double),
+        ("aberth_max_iter", C.c_uint32), ("aberth_eps", C.c_double), ("kepler_eps", C.c_double),
+        ("max_tested_solutions", C.c_uint64), ("r2_min_au", C.c_double), ("r2_max_au", C.c_double),
+        ("newton_eps", C.c_double), ("newton_max_it", C.c_uint64), ("root_imag_eps", C.c_double),
+    ]
+
+
+class KeplerParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("r0", C.c_double), ("sig0", C.c_double), ("mu", C.c_double),
+        ("alpha", C.c_double), ("e0", C.c_double), ("kind", C.c_int), ("convergency", C.c_double),
+        ("has_psi_guess", C.c_int), ("psi_guess", C.c_double),
+        ("max_iter_prelim_kepuni", C.c_uint64), ("parabolic_method", C.c_int),
+    ]
+
+
+class KeplerSolution(C.Structure):
+    _fields_ = [("psi", C.c_double), ("s0", C.c_double), ("s1", C.c_double), ("s2", C.c_double),
+                ("s3", C.c_double)]
+
+
+class Elements(C.Structure):
+    _fields_ = [("kind", C.c_int), ("epoch", C.c_double), ("e", C.c_double * 6)]
+
+
+class GaussObs(C.Structure):
+    _fields_ = [("idx", C.c_uint64 * 3), ("ra", D3), ("dec", D3), ("t", D3), ("obs_pos", D9)]
+
+
+class GaussResult(C.Structure):
+    _fields_ = [("corrected", C.c_int), ("orbit", Elements)]
+
+
+class WeightedTriplet(C.Structure):
+    _fields_ = [("weight", C.c_double), ("i", C.c_uint64), ("j", C.c_uint64), ("k", C.c_uint64)]
+
+
+class EphemTable(C.Structure):
+    _fields_ = [("cheb", c_double_p), ("n_blocks", C.c_size_t), ("block_stride", C.c_size_t),
+                ("jd_start", C.c_double), ("jd_end", C.c_double), ("block_days", C.c_double),
+                ("ipt", (C.c_uint32 * 3) * 3), ("emrat", C.c_double)]
+
+
+class TrajView(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("mjd_tt", c_double_p), ("ra", c_double_p), ("dec", c_double_p),
+                ("sigma_ra", c_double_p), ("sigma_dec", c_double_p), ("helio_equ", c_double_p),
+                ("geo_ecl", c_double_p), ("scorer_obs_equ", c_double_p)]
+
+
+class IodResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("cause", C.c_int32), ("cause_value", C.c_double),
+                ("attempts", C.c_uint64), ("span", C.c_double), ("corrected", C.c_int32),
+                ("element_kind", C.c_int32), ("epoch", C.c_double), ("elem", C.c_double * 6),
+                ("rms", C.c_double), ("triplet_idx", C.c_uint32 * 3), ("triplet_rank", C.c_uint32),
+                ("realization", C.c_uint32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "sfunct_calls", "sfunct_terms", "newton_steps", "prelim_calls", "prelim_steps",
+        "kepler_universal_solves", "brent_evals", "aberth_solves", "aberth_sweeps", "gauss_solves",
+        "roots_accepted", "fg_iterations", "ecc_controls", "orbits_built", "scorer_evals",
+        "scorer_newton", "earth_cheb_evals", "pvobs_evals", "propagate_universal_calls")]
+
+
+IOD_RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("cause", "<i4"), ("cause_value", "<f8"), ("attempts", "<u8"),
+    ("span", "<f8"), ("corrected", "<i4"), ("element_kind", "<i4"), ("epoch", "<f8"),
+    ("elem", "<f8", (6,)), ("rms", "<f8"), ("triplet_idx", "<u4", (3,)), ("triplet_rank", "<u4"),
+    ("realization", "<u4")], align=True)
+assert IOD_RESULT_DTYPE.itemsize == C.sizeof(IodResult), (IOD_RESULT_DTYPE.itemsize, C.sizeof(IodResult))
+
+
+def _declare(L):
+    L.oo_s_funct.argtypes = [C.c_double, C.c_double, C.c_double * 4]
+    L.oo_s_funct.restype = None
+    for n in ("oo_prelim_elliptic", "oo_prelim_hyperbolic", "oo_prelim_parabolic"):
+        getattr(L, n).argtypes = [C.POINTER(KeplerParams)]
+        getattr(L, n).restype = C.c_double
+    L.oo_prelim_kepuni.argtypes = [C.POINTER(KeplerParams), c_double_p]
+    L.oo_kepler_solve.argtypes = [C.POINTER(KeplerParams), C.POINTER(KeplerSolution)]
+    L.oo_kepler_params_default_solver.argtypes = [C.POINTER(KeplerParams)]
+    L.oo_kepler_params_default_solver.restype = None
+    L.oo_velocity_correction_with_guess.argtypes = [D3, D3, D3, C.c_double, C.c_double, C.c_double,
+                                                    C.c_int, C.c_double, C.c_double, D3, c_double_p,
+                                                    c_double_p, c_double_p]
+    L.oo_propagate_universal.argtypes = [D3, D3, C.c_double, C.c_double, C.c_int, C.c_double,
+                                         C.c_double * 11]
+    L.oo_propagate_universal_batch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+    L.oo_propagate_universal_batch.restype = None
+    L.oo_rotmt.argtypes = [C.c_double, C.c_int, D9]
+    L.oo_rotmt.restype = None
+    L.oo_eccentricity_control.argtypes = [D3, D3, C.c_double, C.c_double, C.POINTER(C.c_int),
+                                          c_double_p, c_double_p, c_double_p]
+    L.oo_ccek1.argtypes = [D3, D3, C.c_double, C.POINTER(Elements)]
+    L.oo_ccek1.restype = None
+    L.oo_to_equinoctial.argtypes = [C.POINTER(Elements), C.POINTER(Elements)]
+    L.oo_equinoctial_solve_kepler.argtypes = [C.POINTER(Elements), C.c_double, C.c_double, c_double_p]
+    L.oo_propagate_twobody.argtypes = [C.POINTER(Elements), C.c_double, C.c_double, D3, D3]
+    L.oo_gauss_prelim.argtypes = [C.POINTER(GaussObs), c_double_p, c_double_p, D9, D9, D3, D3]
+    L.oo_coeff_eight_poly.argtypes = [C.POINTER(GaussObs), D9, D9, D3, D3, D3]
+    L.oo_coeff_eight_poly.restype = None
+    L.oo_aberth8.argtypes = [C.c_double * 9, C.c_uint32, C.c_double, C.c_double * 8, C.c_double * 8,
+                             C.POINTER(C.c_uint32)]
+    L.oo_solve_8poly.argtypes = [C.c_double * 9, C.c_uint32, C.c_double, C.c_double, C.c_double * 8,
+                                 C.POINTER(C.c_int)]
+    L.oo_position_vector_and_reference_epoch.argtypes = [C.POINTER(GaussObs), C.POINTER(IodParams),
+                                                         D9, D9, D3, D9, c_double_p]
+    L.oo_gibbs_correction.argtypes = [D9, C.c_double, C.c_double, D3]
+    L.oo_gibbs_correction.restype = None
+    L.oo_pos_and_vel_correction.argtypes = [C.POINTER(GaussObs), C.POINTER(IodParams), D9, D3, D9, D9,
+                                            C.c_double, C.c_double, C.c_double, C.c_uint64, D9, D3,
+                                            c_double_p]
+    L.oo_prelim_orbit.argtypes = [C.POINTER(GaussObs), C.POINTER(IodParams), C.POINTER(GaussResult)]
+    L.oo_prelim_orbit_all.argtypes = [C.POINTER(GaussObs), C.POINTER(IodParams),
+                                      C.POINTER(GaussResult), C.c_int, C.POINTER(C.c_int)]
+    L.oo_iod_params_default.argtypes = [C.POINTER(IodParams)]
+    L.oo_iod_params_default.restype = None
+    L.oo_iod_params_validate.argtypes = [C.POINTER(IodParams)]
+    L.oo_downsample_uniform_with_edges.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.oo_downsample_uniform_with_edges.restype = C.c_size_t
+    L.oo_enumerate_triplets.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_size_t]
+    L.oo_enumerate_triplets.restype = C.c_size_t
+    L.oo_triplet_weight_with_inv.argtypes = [C.c_double] * 4
+    L.oo_triplet_weight_with_inv.restype = C.c_double
+    L.oo_best_k_triplets.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(IodParams),
+                                     C.POINTER(WeightedTriplet)]
+    L.oo_best_k_triplets.restype = C.c_size_t
+    L.oo_earth_ephemeris.argtypes = [C.POINTER(EphemTable), C.c_double, C.c_int, D3, D3]
+    L.oo_obleq.argtypes = [C.c_double]
+    L.oo_obleq.restype = C.c_double
+    L.oo_nutn80.argtypes = [C.c_double, c_double_p, c_double_p]
+    L.oo_nutn80.restype = None
+    L.oo_rnut80.argtypes = [C.c_double, D9]
+    L.oo_rnut80.restype = None
+    L.oo_equequ.argtypes = [C.c_double]
+    L.oo_equequ.restype = C.c_double
+    L.oo_prec.argtypes = [C.c_double, D9]
+    L.oo_prec.restype = None
+    L.oo_gmst.argtypes = [C.c_double]
+    L.oo_gmst.restype = C.c_double
+    L.oo_rotpn.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, D9]
+    L.oo_earth_fixed_position.argtypes = [C.c_double, C.c_double, C.c_double, D3, D3]
+    L.oo_earth_fixed_position.restype = None
+    L.oo_pvobs.argtypes = [C.c_double, C.c_double, D3, D3, D3, D3]
+    L.oo_pvobs.restype = None
+    L.oo_helio_position.argtypes = [C.POINTER(EphemTable), C.c_double, D3, D3]
+    L.oo_scorer_observer_position.argtypes = [C.POINTER(EphemTable), C.c_double, D3, D3]
+    L.oo_ephemeris_error.argtypes = [C.POINTER(TrajView), C.c_size_t, C.POINTER(EphemTable),
+                                     C.POINTER(Elements), c_double_p]
+    L.oo_compute_apparent_position.argtypes = [C.POINTER(TrajView), C.c_size_t, C.POINTER(EphemTable),
+                                               C.POINTER(Elements), c_double_p, c_double_p]
+    L.oo_estimate_best_orbit.argtypes = [C.POINTER(TrajView), C.POINTER(EphemTable),
+                                         C.POINTER(IodParams), C.c_void_p, C.POINTER(IodResult)]
+    L.oo_estimate_best_orbit.restype = None
+    L.oo_fit_full_iod.argtypes = [C.c_size_t] + [C.c_void_p] * 8 + [C.POINTER(EphemTable),
+                                  C.POINTER(IodParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int]
+    L.oo_fit_full_iod.restype = None
+    L.oo_counters_reset.restype = None
+    L.oo_counters_get.argtypes = [C.POINTER(Counters)]
+    L.oo_counters_get.restype = None
+
+
+# ---- small helpers ----------------------------------------------------------------------------
+def d3(v):
+    return D3(*[float(x) for x in v])
+
+
+def d9(v):
+    return D9(*[float(x) for x in v])
+
+
+def default_iod_params(**kw):
+    p = IodParams()
+    lib().oo_iod_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def make_ephem_table(cheb, jd_start, block_days, ipt, emrat):
+    """cheb: float64 array [n_blocks, block_stride]; ipt: 3x3 (0-based offset, n_coeff, n_sub)."""
+    cheb = np.ascontiguousarray(cheb, dtype=np.float64)
+    t = EphemTable()
+    t.cheb = cheb.ctypes.data_as(c_double_p)
+    t.n_blocks = cheb.shape[0]
+    t.block_stride = cheb.shape[1]
+    t.jd_start = jd_start
+    t.block_days = block_days
+    t.jd_end = jd_start + block_days * cheb.shape[0]
+    for b in range(3):
+        for j in range(3):
+            t.ipt[b][j] = int(ipt[b][j])
+    t.emrat = emrat
+    t._keep = cheb
+    return t
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fit_full_iod(batch, table, params, n_threads=0, dedup_earth=False):
+    """batch: dict of contiguous float64/uint64 numpy arrays (see outfit_b200.synth)."""
+    T = len(batch["traj_offset"]) - 1
+    out = np.zeros(T, dtype=IOD_RESULT_DTYPE)
+    nz = batch.get("noise_z")
+    no = batch.get("noise_offset")
+    lib().oo_fit_full_iod(T, ptr(batch["traj_offset"]), ptr(batch["mjd_tt"]), ptr(batch["ra"]),
+                          ptr(batch["dec"]), ptr(batch["sigma_ra"]), ptr(batch["sigma_dec"]),
+                          ptr(batch["helio_equ"]), ptr(batch["geo_ecl"]), C.byref(table),
+                          C.byref(params), ptr(nz) if nz is not None else None,
+                          ptr(no) if no is not None else None, ptr(out), n_threads,
+                          1 if dedup_earth else 0)
+    return out
+
+
+def propagate_universal_batch(rv, t0, t1, kind=2, convergency=100 * 2.220446049250313e-16, n_threads=0):
+    n = rv.shape[1]
+    out = np.empty((11, n), dtype=np.float64)
+    status = np.empty(n, dtype=np.int32)
+    lib().oo_propagate_universal_batch(n, ptr(rv), ptr(t0), ptr(t1), kind, convergency, ptr(out),
+                                       ptr(status), n_threads)
+    return out, status
+
+
+def counters():
+    c = Counters()
+    lib().oo_counters_get(C.byref(c))
+    return {n: getattr(c, n) for n, _ in Counters._fields_}
