@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C-ABI.
+
+Reference interface mirrored here (names, argument meaning, error behaviour):
+  IODParams / IODParamsBuilder::build   src/initial_orbit_determination/mod.rs:225-344, 544-624
+  FitIOD::fit_full_iod                  src/initial_orbit_determination/obs_dataset_api.rs:145-207
+  kepler::propagate_universal           src/kepler/propagation.rs:114-174
+  SolverType / SolverKind               src/kepler/params.rs:24-73
+Per-trajectory failures are values (status codes mirroring the OutfitError variant), never
+exceptions; argument / device failures raise OutfitError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+STATUS_NAMES = {
+    0: "Ok", 1: "SingularDirectionMatrix", 2: "GaussNoRootsFound", 3: "PolynomialRootFindingFailed",
+    4: "SpuriousRootDetected", 5: "VelocityCorrectionError", 6: "NewtonRaphsonKeplerConvergence",
+    7: "BrentDekkerKeplerConvergence", 8: "DegenerateState", 9: "InvalidConversion", 10: "InvalidOrbit",
+    11: "RootFindingError", 12: "NonFiniteScore", 13: "NoFeasibleTriplets", 14: "NoViableOrbit",
+    15: "ObservationNotFound", 17: "EphemerisOutOfRange",
+}
+
+
+class OutfitError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"outfit_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "liboutfit_b200.so")
+
+
+class IODParams(C.Structure):
+    """IODParams (mod.rs:225-266); defaults = IODParams::default() (mod.rs:308-344)."""
+    _fields_ = [
+        ("n_noise_realizations", C.c_uint64), ("noise_scale", C.c_double), ("extf", C.c_double),
+        ("dtmax", C.c_double), ("dt_min", C.c_double), ("dt_max_triplet", C.c_double),
+        ("optimal_interval_time", C.c_double), ("max_obs_for_triplets", C.c_uint64),
+        ("max_triplets", C.c_uint32), ("_pad0", C.c_uint32), ("gap_max", C.c_double),
+        ("max_ecc", C.c_double), ("max_perihelion_au", C.c_double), ("min_rho2_au", C.c_double),
+        ("aberth_max_iter", C.c_uint32), ("_pad1", C.c_uint32), ("aberth_eps", C.c_double),
+        ("kepler_eps", C.c_double), ("max_tested_solutions", C.c_uint64), ("r2_min_au", C.c_double),
+        ("r2_max_au", C.c_double), ("newton_eps", C.c_double), ("newton_max_it", C.c_uint64),
+        ("root_imag_eps", C.c_double),
+    ]
+
+    @classmethod
+    def builder(cls, **kw):
+        """IODParams::builder()...build(): validated like IODParamsBuilder::build."""
+        p = cls()
+        load_library().outfit_b200_iod_params_default(C.byref(p))
+        for k, v in kw.items():
+            if k.startswith("_") or not hasattr(p, k):
+                raise AttributeError(f"IODParams has no field {k!r}")
+            setattr(p, k, v)
+        rc = load_library().outfit_b200_iod_params_validate(C.byref(p))
+        if rc != 0:
+            raise OutfitError(rc, "InvalidIODParameter")
+        return p
+
+
+class SolverType(C.Structure):
+    """SolverType{kind, params} (kepler/params.rs:59-73); kind: 0 Newton, 1 BrentDecker, 2 Auto."""
+    _fields_ = [("kind", C.c_int32), ("parabolic_method", C.c_int32), ("convergency", C.c_double),
+                ("max_iter_prelim_kepuni", C.c_uint64)]
+
+    def __init__(self, kind=0, convergency=100.0 * 2.220446049250313e-16, max_iter_prelim_kepuni=20,
+                 parabolic_method=0):
+        super().__init__(kind, parabolic_method, convergency, max_iter_prelim_kepuni)
+
+
+class ObsBatch(C.Structure):
+    _fields_ = [("n_traj", C.c_uint64), ("n_obs", C.c_uint64), ("traj_offset", C.c_void_p),
+                ("mjd_tt", C.c_void_p), ("ra", C.c_void_p), ("dec", C.c_void_p),
+                ("sigma_ra", C.c_void_p), ("sigma_dec", C.c_void_p), ("obs_helio_equ", C.c_void_p),
+                ("obs_geo_ecl", C.c_void_p), ("observer_body_fixed", C.c_void_p),
+                ("mjd_ut1", C.c_void_p), ("noise_z", C.c_void_p)]
+
+
+class IodResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("cause", C.c_int32), ("cause_value", C.c_double),
+                ("attempts", C.c_uint64), ("span", C.c_double), ("corrected", C.c_int32),
+                ("element_kind", C.c_int32), ("epoch", C.c_double), ("elem", C.c_double * 6),
+                ("rms", C.c_double), ("triplet_idx", C.c_uint32 * 3), ("triplet_rank", C.c_uint32),
+                ("realization", C.c_uint32)]
+
+
+class IodCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "gauss_solves", "aberth_sweeps", "roots_accepted", "fg_iterations", "kepler_universal_solves",
+        "newton_steps", "sfunct_terms", "scorer_evals", "scorer_newton_steps", "candidates")]
+
+
+RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("cause", "<i4"), ("cause_value", "<f8"), ("attempts", "<u8"), ("span", "<f8"),
+    ("corrected", "<i4"), ("element_kind", "<i4"), ("epoch", "<f8"), ("elem", "<f8", (6,)),
+    ("rms", "<f8"), ("triplet_idx", "<u4", (3,)), ("triplet_rank", "<u4"), ("realization", "<u4")],
+    align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(IodResult)
+
+ABI_SYMBOLS = [
+    "outfit_b200_abi_version", "outfit_b200_strerror", "outfit_b200_last_error",
+    "outfit_b200_iod_params_default", "outfit_b200_iod_params_validate",
+    "outfit_b200_solver_type_default", "outfit_b200_init", "outfit_b200_destroy",
+    "outfit_b200_load_ephemeris", "outfit_b200_fit_full_iod", "outfit_b200_fit_full_iod_device",
+    "outfit_b200_observer_cache_device", "outfit_b200_propagate_universal",
+    "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters",
+    "outfit_b200_measure_fp64_peak",
+]
+
+
+def load_library():
+    """dlopen liboutfit_b200.so; raises (no fallback) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise OutfitError(-100, f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                                "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, cp = C.c_void_p, C.c_char_p
+    L.outfit_b200_abi_version.restype = C.c_int
+    L.outfit_b200_strerror.restype = cp
+    L.outfit_b200_strerror.argtypes = [C.c_int]
+    L.outfit_b200_last_error.restype = cp
+    L.outfit_b200_last_error.argtypes = [vp]
+    L.outfit_b200_iod_params_default.argtypes = [C.POINTER(IODParams)]
+    L.outfit_b200_iod_params_default.restype = None
+    L.outfit_b200_iod_params_validate.argtypes = [C.POINTER(IODParams)]
+    L.outfit_b200_solver_type_default.argtypes = [C.POINTER(SolverType)]
+    L.outfit_b200_solver_type_default.restype = None
+    L.outfit_b200_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.outfit_b200_destroy.argtypes = [vp]
+    L.outfit_b200_destroy.restype = None
+    L.outfit_b200_load_ephemeris.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, vp,
+                                             C.c_double]
+    L.outfit_b200_fit_full_iod.argtypes = [vp, C.POINTER(IODParams), C.POINTER(ObsBatch), vp]
+    L.outfit_b200_fit_full_iod_device.argtypes = [vp, C.POINTER(IODParams), C.POINTER(ObsBatch), vp, vp]
+    L.outfit_b200_observer_cache_device.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_propagate_universal.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(SolverType), vp, vp]
+    L.outfit_b200_propagate_universal_device.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(SolverType),
+                                                         vp, vp, vp]
+    L.outfit_b200_last_iod_counters.argtypes = [vp, C.POINTER(IodCounters)]
+    L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    _LIB = L
+    return L
+
+
+def _p(a):
+    """Host pointer of a C-contiguous numpy array, or device pointer of a torch tensor, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    return int(a)
+
+
+class OutfitB200:
+    """One context = one GPU (one process per GPU).  Mirrors the objects `fit_full_iod` borrows:
+    the ephemeris (`&JPLEphem`) is loaded once; params and the batch are passed per call."""
+
+    def __init__(self, device=-1):
+        L = load_library()
+        h = C.c_void_p()
+        rc = L.outfit_b200_init(device, C.byref(h))
+        if rc != 0:
+            raise OutfitError(rc, L.outfit_b200_strerror(rc).decode())
+        self._h = h
+        self._L = L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.outfit_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.outfit_b200_last_error(self._h).decode() or self._L.outfit_b200_strerror(rc).decode()
+            raise OutfitError(rc, msg)
+
+    # -- JPLEphem -----------------------------------------------------------------------------
+    def load_ephemeris(self, table):
+        cheb = np.ascontiguousarray(table["cheb"], dtype=np.float64)
+        ipt = np.ascontiguousarray(table["ipt"], dtype=np.uint32)
+        self._check(self._L.outfit_b200_load_ephemeris(self._h, cheb.ctypes.data, cheb.shape[0], cheb.shape[1],
+                                                       float(table["jd_start"]), float(table["block_days"]),
+                                                       ipt.ctypes.data, float(table["emrat"])))
+
+    # -- FitIOD::fit_full_iod -----------------------------------------------------------------
+    @staticmethod
+    def _batch_struct(batch, use_body_fixed=False):
+        b = ObsBatch()
+        b.n_traj = len(batch["traj_offset"]) - 1 if not hasattr(batch["traj_offset"], "data_ptr") else batch["traj_offset"].numel() - 1
+        mj = batch["mjd_tt"]
+        b.n_obs = mj.shape[0]
+        for k in ("traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec"):
+            setattr(b, k, _p(batch[k]))
+        if use_body_fixed:
+            b.observer_body_fixed = _p(batch["body_fixed"])
+            b.mjd_ut1 = _p(batch["mjd_ut1"])
+        else:
+            b.obs_helio_equ = _p(batch["helio_equ"])
+            b.obs_geo_ecl = _p(batch["geo_ecl"])
+        b.noise_z = _p(batch.get("noise_z"))
+        return b
+
+    def fit_full_iod(self, batch, params, use_body_fixed=False):
+        """HOST buffers in, numpy structured array (RESULT_DTYPE) out; H2D/D2H inside the call."""
+        b = self._batch_struct(batch, use_body_fixed)
+        if params.n_noise_realizations == 0:
+            b.noise_z = None
+        out = np.zeros(int(b.n_traj), dtype=RESULT_DTYPE)
+        self._check(self._L.outfit_b200_fit_full_iod(self._h, C.byref(params), C.byref(b), out.ctypes.data))
+        return out
+
+    def fit_full_iod_device(self, dev_batch, params, out_ptr, stream=0, use_body_fixed=False):
+        """DEVICE-resident buffers (torch tensors or raw pointers); enqueues, does not sync."""
+        b = self._batch_struct(dev_batch, use_body_fixed)
+        if params.n_noise_realizations == 0:
+            b.noise_z = None
+        self._check(self._L.outfit_b200_fit_full_iod_device(self._h, C.byref(params), C.byref(b), _p(out_ptr), stream))
+
+    def last_iod_counters(self):
+        c = IodCounters()
+        self._check(self._L.outfit_b200_last_iod_counters(self._h, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in IodCounters._fields_}
+
+    # -- OutfitCache::build ---------------------------------------------------------------------
+    def observer_cache_device(self, n, mjd_tt, mjd_ut1, body_fixed, geo_ecl, helio_equ, status=None, stream=0):
+        self._check(self._L.outfit_b200_observer_cache_device(self._h, n, _p(mjd_tt), _p(mjd_ut1), _p(body_fixed),
+                                                              _p(geo_ecl), _p(helio_equ), _p(status), stream))
+
+    # -- kepler::propagate_universal --------------------------------------------------------------
+    def propagate_universal(self, rv, t0, t1, solver=None, psi_guess=None):
+        """rv (6, n) plane-major, t0/t1 (n) host arrays -> out (11, n), status (n)."""
+        solver = solver or SolverType(kind=2)
+        n = rv.shape[1]
+        out = np.empty((11, n), dtype=np.float64)
+        status = np.empty(n, dtype=np.int32)
+        self._check(self._L.outfit_b200_propagate_universal(self._h, n, _p(rv), _p(t0), _p(t1), _p(psi_guess),
+                                                            C.byref(solver), out.ctypes.data, status.ctypes.data))
+        return out, status
+
+    def propagate_universal_device(self, n, rv, t0, t1, out, status, solver=None, psi_guess=None, stream=0):
+        solver = solver or SolverType(kind=2)
+        self._check(self._L.outfit_b200_propagate_universal_device(self._h, n, _p(rv), _p(t0), _p(t1), _p(psi_guess),
+                                                                   C.byref(solver), _p(out), _p(status), stream))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self._L.outfit_b200_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value

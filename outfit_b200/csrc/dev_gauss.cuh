@@ -1,0 +1,228 @@
+// dev_gauss.cuh -- device-side Gauss preliminary orbit for ONE observation triplet (one lane).
+//
+// Reference behaviour: /root/reference/src/initial_orbit_determination/gauss.rs
+//   gauss_prelim :532  coeff_eight_poly :585  visit_real_positive_roots/aberth :964
+//   accept_root :816   position_vector_and_reference_epoch :702  gibbs_correction :754
+//   pos_and_vel_correction :1284   prelim_orbit_all :1119   prelim_orbit :1238
+//
+// Aberth-Ehrlich root finder: the reference's root ORDER decides which orbit a triplet
+// contributes, and the order of the two roots that come from one conjugate pair of starting
+// points is decided by rounding-level symmetry breaking.  The sweep below therefore reproduces
+// the arithmetic of the aberth 0.4.1 crate exactly (explicit IEEE intrinsics, fused Horner steps,
+// textbook complex division, index-ordered sums) and takes the unit-circle starting directions
+// from the host libm (c_aberth_dir), so the 8 roots are bit-identical to the CPU path.
+#pragma once
+#include "dev_kepler.cuh"
+
+namespace ofb {
+
+struct IodDevParams {
+  double noise_scale, extf, dtmax, dt_min, dt_max_triplet, inv_optimal_interval;
+  double max_ecc, max_perihelion_au, min_rho2_au;
+  double aberth_eps, kepler_eps, r2_min_au, r2_max_au, newton_eps, root_imag_eps;
+  unsigned n_noise, max_triplets, max_obs_for_triplets, aberth_max_iter, max_tested_solutions,
+      newton_max_it;
+};
+
+// cos/sin of theta_k = (2 pi / 8) k + (pi / 2) / 8, k = 0..7, evaluated by the HOST libm.
+__constant__ double c_aberth_dir[16];
+
+struct Cx {
+  double re, im;
+};
+// exact (never contracted) complex helpers mirroring num-complex 0.4
+__device__ __forceinline__ Cx cx_sub(Cx a, Cx b) { return Cx{__dsub_rn(a.re, b.re), __dsub_rn(a.im, b.im)}; }
+__device__ __forceinline__ Cx cx_add(Cx a, Cx b) { return Cx{__dadd_rn(a.re, b.re), __dadd_rn(a.im, b.im)}; }
+__device__ __forceinline__ Cx cx_mul(Cx a, Cx b) {
+  return Cx{__dsub_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im)),
+            __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re))};
+}
+__device__ __forceinline__ Cx cx_div(Cx a, Cx b) {
+  const double n = __dadd_rn(__dmul_rn(b.re, b.re), __dmul_rn(b.im, b.im));
+  const double re = __dadd_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im));
+  const double im = __dsub_rn(__dmul_rn(a.im, b.re), __dmul_rn(a.re, b.im));
+  return Cx{__ddiv_rn(re, n), __ddiv_rn(im, n)};
+}
+__device__ __forceinline__ Cx cx_recip(Cx b) {  // (1 + 0i) / b
+  const double n = __dadd_rn(__dmul_rn(b.re, b.re), __dmul_rn(b.im, b.im));
+  return Cx{__ddiv_rn(b.re, n), __ddiv_rn(-b.im, n)};
+}
+// one Horner step r*x + c with the fused form of num-complex's MulAdd
+__device__ __forceinline__ Cx cx_horner_step(Cx r, Cx x, double c) {
+  Cx o;
+  o.re = __dsub_rn(__fma_rn(r.re, x.re, c), __dmul_rn(r.im, x.im));
+  o.im = __fma_rn(r.re, x.im, __fma_rn(r.im, x.re, 0.0));
+  return o;
+}
+
+// p(z) = z^8 + c6 z^6 + c3 z^3 + c0 and p'(z), dense Horner (zeros included: they round)
+__device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6, Cx &p, Cx &dp) {
+  Cx r = Cx{0.0, 0.0};
+  r = cx_horner_step(r, z, 1.0);
+  r = cx_horner_step(r, z, 0.0);
+  r = cx_horner_step(r, z, c6);
+  r = cx_horner_step(r, z, 0.0);
+  r = cx_horner_step(r, z, 0.0);
+  r = cx_horner_step(r, z, c3);
+  r = cx_horner_step(r, z, 0.0);
+  r = cx_horner_step(r, z, 0.0);
+  r = cx_horner_step(r, z, c0);
+  p = r;
+  Cx d = Cx{0.0, 0.0};
+  d = cx_horner_step(d, z, 8.0);
+  d = cx_horner_step(d, z, 0.0);
+  d = cx_horner_step(d, z, __dmul_rn(c6, 6.0));
+  d = cx_horner_step(d, z, 0.0);
+  d = cx_horner_step(d, z, 0.0);
+  d = cx_horner_step(d, z, __dmul_rn(c3, 3.0));
+  d = cx_horner_step(d, z, 0.0);
+  d = cx_horner_step(d, z, 0.0);
+  dp = d;
+}
+
+// returns 0 converged / 1 max-iter / 2 failed; roots in zr/zi (index order k)
+__device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned max_iter, double eps,
+                                    double (&zr)[8], double (&zi)[8], Work &w) {
+  // Cauchy-type start radius: smallest integer r0 with S(r0) > 0, S(w) = w^8 - |c6| w^6 - |c3| w^3 - |c0|
+  const double s0 = -fabs(c0), s3 = -fabs(c3), s6 = -fabs(c6);
+  double r0 = 1.0;
+  for (int guard = 0; guard < 100000; ++guard) {
+    double r = 0.0;
+    r = __dsub_rn(__fma_rn(r, r0, 1.0), 0.0);
+    r = __fma_rn(r, r0, -0.0);
+    r = __fma_rn(r, r0, s6);
+    r = __fma_rn(r, r0, -0.0);
+    r = __fma_rn(r, r0, -0.0);
+    r = __fma_rn(r, r0, s3);
+    r = __fma_rn(r, r0, -0.0);
+    r = __fma_rn(r, r0, -0.0);
+    r = __fma_rn(r, r0, s0);
+    if (r > 0.0) break;
+    r0 += 1.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    zr[k] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
+    zi[k] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
+  }
+  for (unsigned it = 0; it < max_iter; ++it) {
+    ++w.aberth_sweeps;
+    double nr[8], ni[8];
+    bool converged = true;
+    bool failed = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const Cx z = Cx{zr[i], zi[i]};
+      Cx p, dp;
+      poly8_eval(z, c0, c3, c6, p, dp);
+      Cx sum = Cx{0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k == i) continue;
+        sum = cx_add(sum, cx_recip(cx_sub(z, Cx{zr[k], zi[k]})));
+      }
+      const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, sum), dp)));
+      nr[i] = nz.re;
+      ni[i] = nz.im;
+      if (!(isfinite(nz.re) && isfinite(nz.im))) failed = true;
+      if (!(fabs(__dsub_rn(nz.re, z.re)) < eps && fabs(__dsub_rn(nz.im, z.im)) < eps)) converged = false;
+    }
+    if (failed) return 2;  // the caller maps it to PolynomialRootFindingFailed
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zr[i] = nr[i]; zi[i] = ni[i]; }
+    if (converged) return 0;
+  }
+  return 1;
+}
+
+struct Triplet {
+  double ra[3], dec[3], t[3];
+  V3 R[3];  // heliocentric observer positions at the 3 epochs (equatorial J2000), AU
+};
+struct Orbit {
+  int kind;        // 0 Keplerian, 2 Cometary
+  int corrected;   // 1 CorrectedOrbit / 0 PrelimOrbit
+  double epoch;
+  double e[6];
+};
+
+struct GaussGeom {
+  V3 S[3];      // unit line-of-sight vectors (columns of the unit matrix)
+  V3 SiR[3];    // ROWS of the inverse
+  double tau1, tau3;
+  double a0, a2, b0, b2;
+};
+
+// R*c with nalgebra's accumulation order, then rho, positions and light-time epoch (gauss.rs:702)
+__device__ __forceinline__ bool positions_from_c(const Triplet &g, const GaussGeom &gm, double c0,
+                                                 double c1, double c2, double min_rho2, V3 (&pos)[3],
+                                                 double &epoch) {
+  const V3 gc = V3{(g.R[0].x * c0 + g.R[1].x * c1) + g.R[2].x * c2,
+                   (g.R[0].y * c0 + g.R[1].y * c1) + g.R[2].y * c2,
+                   (g.R[0].z * c0 + g.R[1].z * c1) + g.R[2].z * c2};
+  const double rho0 = -(dot(gm.SiR[0], gc) / c0);
+  const double rho1 = -(dot(gm.SiR[1], gc) / c1);
+  const double rho2 = -(dot(gm.SiR[2], gc) / c2);
+  if (rho1 < min_rho2) return false;
+  pos[0] = g.R[0] + rho0 * gm.S[0];
+  pos[1] = g.R[1] + rho1 * gm.S[1];
+  pos[2] = g.R[2] + rho2 * gm.S[2];
+  epoch = g.t[1] - rho1 / kVlightAu;
+  return true;
+}
+
+__device__ __forceinline__ V3 gibbs_velocity(const V3 (&pos)[3], double tau1, double tau3) {
+  const double tau13 = tau3 - tau1;
+  const double n1 = norm(pos[0]), n2 = norm(pos[1]), n3 = norm(pos[2]);
+  const double r1m3 = 1.0 / ((n1 * n1) * n1), r2m3 = 1.0 / ((n2 * n2) * n2), r3m3 = 1.0 / ((n3 * n3) * n3);
+  const double d1 = tau3 * (r1m3 / 12.0 - 1.0 / (tau1 * tau13));
+  const double d2 = (tau1 + tau3) * (r2m3 / 12.0 - 1.0 / (tau1 * tau3));
+  const double d3 = -tau1 * (r3m3 / 12.0 + 1.0 / (tau3 * tau13));
+  const double e1 = -d1;
+  return V3{kGaussK * ((pos[0].x * e1 + pos[1].x * d2) + pos[2].x * d3),
+            kGaussK * ((pos[0].y * e1 + pos[1].y * d2) + pos[2].y * d3),
+            kGaussK * ((pos[0].z * e1 + pos[1].z * d2) + pos[2].z * d3)};
+}
+
+// Iterative two-sided Lagrange f-g refinement (gauss.rs:1284-1418).  Returns false <=> None.
+__device__ __forceinline__ bool pos_and_vel_correction(const Triplet &g, const GaussGeom &gm,
+                                                       const IodDevParams &P, V3 (&pos)[3], V3 &vel,
+                                                       double &epoch, Work &w) {
+  const double dt01 = g.t[0] - g.t[1], dt21 = g.t[2] - g.t[1];
+  double ep = 0.0;
+  if (fabs(dt01) <= kEps || fabs(dt21) <= kEps) return false;
+  bool has01 = false, has21 = false;
+  double chi01 = 0.0, chi21 = 0.0;
+  for (unsigned it = 0; it < P.newton_max_it; ++it) {
+    ++w.fg_iterations;
+    const VelCor L = velocity_correction(pos[0], pos[1], vel, dt01, P.max_perihelion_au, P.max_ecc,
+                                         has01, chi01, P.kepler_eps, w);
+    const VelCor Rr = velocity_correction(pos[2], pos[1], vel, dt21, P.max_perihelion_au, P.max_ecc,
+                                          has21, chi21, P.kepler_eps, w);
+    if (!(L.ok && Rr.ok)) continue;
+    has01 = true; chi01 = L.chi;
+    has21 = true; chi21 = Rr.chi;
+    if (!isfinite(L.g) || !isfinite(Rr.g)) continue;
+    const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
+    const double fl = L.f * Rr.g - Rr.f * L.g;
+    if (!isfinite(fl) || fabs(fl) < kEps) continue;
+    const double inv_f = 1.0 / fl;
+    V3 np[3];
+    double nep;
+    if (!positions_from_c(g, gm, Rr.g * inv_f, -1.0, -L.g * inv_f, P.min_rho2_au, np, nep)) continue;
+    const EccCtl ec = eccentricity_control(np[1], nv, P.max_perihelion_au, P.max_ecc);
+    if (!ec.defined || !ec.accepted) return false;
+    const double denom = sqrt((dot(np[0], np[0]) + dot(np[1], np[1])) + dot(np[2], np[2]));
+    if (!isfinite(denom) || denom <= kEps) continue;
+    const V3 d0 = np[0] - pos[0], d1 = np[1] - pos[1], d2 = np[2] - pos[2];
+    const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
+    pos[0] = np[0]; pos[1] = np[1]; pos[2] = np[2];
+    vel = nv;
+    ep = nep;
+    if (rel <= P.newton_eps) break;
+  }
+  epoch = ep;
+  return true;
+}
+
+}  // namespace ofb

@@ -1,0 +1,270 @@
+// dev_iod.cuh -- one warp per trajectory: triplet selection, one lane per (triplet, realization)
+// candidate, warp-level best-orbit selection.
+//
+// Reference behaviour:
+//   generate_triplets / best-K       triplet_generation/mod.rs:229-440, index_generator.rs:66-271
+//   estimate_best_orbit              trajectory.rs:429-545  (sequential loop with running-best
+//                                    pruning; reproduced here by an order-preserving warp fold)
+//   rms_orbit_error / interval       trajectory.rs:294-427
+//   prelim_orbit(_all)               gauss.rs:1119-1247
+#pragma once
+#include "dev_elements.cuh"
+
+namespace ofb {
+
+// ---- per-warp shared-memory view of one trajectory ------------------------------------------
+struct TrajSmem {
+  double *t, *ra, *dec, *sra, *sdec, *cosdec;
+  double *hx, *hy, *hz;  // OutfitCache helio position (equatorial J2000)
+  double *ox, *oy, *oz;  // scorer observer position (observation_ephemeris.rs:303-318)
+  unsigned short *trip;  // [max_triplets][4] : i, j, k, pad
+  double *heap_w;        // [max_triplets] best-K heap: weights
+  unsigned *heap_x;      // [max_triplets] best-K heap: packed (i<<20 | j<<10 | k)
+};
+constexpr int kObsPlanes = 12;
+
+__device__ __forceinline__ unsigned keep_index(unsigned i, unsigned n, unsigned max_keep) {
+  // downsample_uniform_with_edges (index_generator.rs:66-75)
+  if (max_keep >= n) return i;
+  if (max_keep <= 3) return i == 0 ? 0u : (i == 1 ? n / 2 : n - 1);
+  return (unsigned)(((unsigned long long)i * (n - 1)) / (max_keep - 1));
+}
+__device__ __forceinline__ double s_gap(double dt, double inv_dtw) {
+  const double r = dt * inv_dtw;
+  return r <= 1.0 ? 1.0 / r : 1.0 + r;
+}
+
+// Warp-cooperative best-K triplet selection that reproduces the reference's container semantics
+// exactly, because exact weight ties are systematic (for gaps longer than the optimal interval the
+// weight is 2 + (t_k - t_i)/dtw whatever the middle index): candidates are produced in the
+// generator's lexicographic (i<j<k) order, lanes compute 32 weights at a time, and the survivors are
+// fed IN ORDER to a std::collections::BinaryHeap replica (push = sift_up; pop = swap-last +
+// sift_down_to_bottom + sift_up; replacement only on strict `<`, mod.rs:386-401), followed by the
+// stable insertion sort `sort_unstable_by` performs on short slices (mod.rs:405-407).
+// Returns the number found (warp-uniform); writes them (ascending) to sm.trip.
+__device__ __forceinline__ bool heap_le(double wa, double wb) { return !(wa > wb); }  // a <= b by weight
+__device__ __forceinline__ void heap_sift_up(double *hw, unsigned *hx, unsigned pos) {
+  const double w = hw[pos];
+  const unsigned x = hx[pos];
+  while (pos > 0) {
+    const unsigned parent = (pos - 1) >> 1;
+    if (heap_le(w, hw[parent])) break;
+    hw[pos] = hw[parent]; hx[pos] = hx[parent];
+    pos = parent;
+  }
+  hw[pos] = w; hx[pos] = x;
+}
+__device__ __forceinline__ void heap_sift_down_to_bottom(double *hw, unsigned *hx, unsigned end) {
+  const double w = hw[0];
+  const unsigned x = hx[0];
+  unsigned pos = 0, child = 1;
+  while (end >= 2 && child <= end - 2) {
+    if (heap_le(hw[child], hw[child + 1])) child += 1;
+    hw[pos] = hw[child]; hx[pos] = hx[child];
+    pos = child;
+    child = 2 * pos + 1;
+  }
+  if (end >= 1 && child == end - 1) {
+    hw[pos] = hw[child]; hx[pos] = hx[child];
+    pos = child;
+  }
+  hw[pos] = w; hx[pos] = x;
+  heap_sift_up(hw, hx, pos);
+}
+
+__device__ __forceinline__ unsigned select_triplets(const TrajSmem &sm, unsigned n_obs,
+                                                    const IodDevParams &P, unsigned lane) {
+  if (P.max_triplets == 0 || n_obs < 3) return 0;
+  const unsigned nr = P.max_obs_for_triplets >= n_obs ? n_obs : (P.max_obs_for_triplets <= 3 ? 3u : P.max_obs_for_triplets);
+  const unsigned K = P.max_triplets;
+  double *hw = sm.heap_w;
+  unsigned *hx = sm.heap_x;
+  unsigned heap_len = 0;   // warp-uniform
+  double worst = INFINITY; // weight at the heap root once the heap is full (warp-uniform)
+  // odometer over (i, j, k): this lane visits lexicographic indices lane, lane + 32, ...
+  unsigned i = 0, j = 1, o = lane;
+  bool done = false;
+  for (;;) {
+    while (!done && o >= nr - 1 - j) {
+      o -= nr - 1 - j;
+      ++j;
+      if (j + 1 >= nr) { ++i; j = i + 1; if (i + 2 >= nr) done = true; }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+    double wgt = INFINITY;
+    unsigned packed = 0;
+    bool cand = false;
+    if (!done) {
+      const unsigned k = j + 1 + o;
+      const double ti = sm.t[keep_index(i, n_obs, P.max_obs_for_triplets)];
+      const double tj = sm.t[keep_index(j, n_obs, P.max_obs_for_triplets)];
+      const double tk = sm.t[keep_index(k, n_obs, P.max_obs_for_triplets)];
+      const double span = tk - ti;
+      if (span >= P.dt_min && span <= P.dt_max_triplet) {
+        wgt = s_gap(tj - ti, P.inv_optimal_interval) + s_gap(tk - tj, P.inv_optimal_interval);
+        cand = isfinite(wgt);
+        packed = (i << 20) | (j << 10) | k;
+      }
+      o += 32;
+    }
+    // feed this chunk's survivors to the heap in enumeration (= lane) order
+    unsigned mask = __ballot_sync(0xffffffffu, cand && (heap_len < K || wgt < worst));
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double ws = __shfl_sync(0xffffffffu, wgt, src);
+      const unsigned xs = __shfl_sync(0xffffffffu, packed, src);
+      if (lane == 0) {
+        if (heap_len < K) {
+          hw[heap_len] = ws; hx[heap_len] = xs;
+          heap_sift_up(hw, hx, heap_len);
+          ++heap_len;
+        } else if (ws < hw[0]) {
+          // BinaryHeap::pop then push
+          --heap_len;
+          if (heap_len > 0) {
+            hw[0] = hw[heap_len]; hx[0] = hx[heap_len];
+            heap_sift_down_to_bottom(hw, hx, heap_len);
+          }
+          hw[heap_len] = ws; hx[heap_len] = xs;
+          heap_sift_up(hw, hx, heap_len);
+          ++heap_len;
+        }
+        worst = heap_len >= K ? hw[0] : INFINITY;
+      }
+      heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
+      worst = __shfl_sync(0xffffffffu, worst, 0);
+      mask &= __ballot_sync(0xffffffffu, cand && (heap_len < K || wgt < worst));
+    }
+  }
+  if (lane == 0) {
+    // heap.into_vec() then insertion sort by weight (stable)
+    for (unsigned a = 1; a < heap_len; ++a) {
+      const double w = hw[a];
+      const unsigned x = hx[a];
+      unsigned b = a;
+      while (b > 0 && w < hw[b - 1]) { hw[b] = hw[b - 1]; hx[b] = hx[b - 1]; --b; }
+      hw[b] = w; hx[b] = x;
+    }
+    for (unsigned a = 0; a < heap_len; ++a) {
+      sm.trip[4 * a + 0] = (unsigned short)(hx[a] >> 20);
+      sm.trip[4 * a + 1] = (unsigned short)((hx[a] >> 10) & 1023u);
+      sm.trip[4 * a + 2] = (unsigned short)(hx[a] & 1023u);
+    }
+  }
+  __syncwarp();
+  return heap_len;
+}
+
+// ---- one candidate: Gauss solve -> orbit (prelim_orbit, gauss.rs:1238) ------------------------
+// returns 0 or an OUTFIT_ST_* error code
+__device__ __forceinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i0, unsigned i1, unsigned i2,
+                                                  const double (&ra)[3], const double (&dec)[3],
+                                                  const IodDevParams &P, Orbit &out, Work &w) {
+  ++w.gauss_solves;
+  Triplet g;
+  g.t[0] = sm.t[i0]; g.t[1] = sm.t[i1]; g.t[2] = sm.t[i2];
+  g.R[0] = V3{sm.hx[i0], sm.hy[i0], sm.hz[i0]};
+  g.R[1] = V3{sm.hx[i1], sm.hy[i1], sm.hz[i1]};
+  g.R[2] = V3{sm.hx[i2], sm.hy[i2], sm.hz[i2]};
+  GaussGeom gm;
+  // gauss_prelim (gauss.rs:532-549)
+  gm.tau1 = kGaussK * (g.t[0] - g.t[1]);
+  gm.tau3 = kGaussK * (g.t[2] - g.t[1]);
+  const double tau13 = gm.tau3 - gm.tau1;
+  gm.a0 = gm.tau3 / tau13;
+  gm.a2 = -(gm.tau1 / tau13);
+  gm.b0 = gm.a0 * (tau13 * tau13 - gm.tau3 * gm.tau3) / 6.0;
+  gm.b2 = gm.a2 * (tau13 * tau13 - gm.tau1 * gm.tau1) / 6.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double sr, cr, sd, cd;
+    sincos(ra[c], &sr, &cr);
+    sincos(dec[c], &sd, &cd);
+    gm.S[c] = V3{cr * cd, sr * cd, sd};
+  }
+  {  // cofactor inverse (nalgebra try_inverse, dim 3); rows of the inverse
+    const double m11 = gm.S[0].x, m12 = gm.S[1].x, m13 = gm.S[2].x;
+    const double m21 = gm.S[0].y, m22 = gm.S[1].y, m23 = gm.S[2].y;
+    const double m31 = gm.S[0].z, m32 = gm.S[1].z, m33 = gm.S[2].z;
+    const double mi1 = m22 * m33 - m32 * m23;
+    const double mi2 = m21 * m33 - m31 * m23;
+    const double mi3 = m21 * m32 - m31 * m22;
+    const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;
+    if (det == 0.0) return 1;
+    gm.SiR[0] = V3{mi1 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det};
+    gm.SiR[1] = V3{-mi2 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det};
+    gm.SiR[2] = V3{mi3 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det};
+  }
+  // coeff_eight_poly (gauss.rs:585-614)
+  double c6, c3, c0;
+  {
+    const V3 ra_v = V3{(g.R[0].x * gm.a0 + g.R[1].x * -1.0) + g.R[2].x * gm.a2,
+                       (g.R[0].y * gm.a0 + g.R[1].y * -1.0) + g.R[2].y * gm.a2,
+                       (g.R[0].z * gm.a0 + g.R[1].z * -1.0) + g.R[2].z * gm.a2};
+    const V3 rb_v = V3{(g.R[0].x * gm.b0 + g.R[1].x * 0.0) + g.R[2].x * gm.b2,
+                       (g.R[0].y * gm.b0 + g.R[1].y * 0.0) + g.R[2].y * gm.b2,
+                       (g.R[0].z * gm.b0 + g.R[1].z * 0.0) + g.R[2].z * gm.b2};
+    const double a2s = dot(gm.SiR[1], ra_v);
+    const double b2s = dot(gm.SiR[1], rb_v);
+    const double r22 = dot(g.R[1], g.R[1]);
+    const double s2r2 = dot(gm.S[1], g.R[1]);
+    c6 = -(a2s * a2s) - r22 - (2.0 * a2s * s2r2);
+    c3 = -(2.0 * b2s * (a2s + s2r2));
+    c0 = -(b2s * b2s);
+  }
+  {  // Descartes prefilter (gauss.rs:214-240): no sign change <=> no positive real root
+    int last = 1, count = 0;
+    const double cs[3] = {c6, c3, c0};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int cur = cs[q] == 0.0 ? 0 : (signbit(cs[q]) ? -1 : 1);
+      if (cur == 0) continue;
+      if (cur != last) ++count;
+      last = cur;
+    }
+    if (count == 0) return 2;
+  }
+  double zr[8], zi[8];
+  if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) return 3;
+
+  // roots in solver order -> accept -> correct -> first Corrected, else first pushed
+  bool have_first = false;
+  unsigned n_solutions = 0;
+#pragma unroll 1
+  for (int kroot = 0; kroot < 8; ++kroot) {
+    const double r2 = zr[kroot];
+    if (!(r2 > 0.0 && fabs(zi[kroot]) < P.root_imag_eps)) continue;
+    if (!(r2 >= P.r2_min_au && r2 <= P.r2_max_au)) continue;
+    // accept_root (gauss.rs:816-870)
+    const double r2m3 = 1.0 / ((r2 * r2) * r2);
+    V3 pos[3];
+    double epoch;
+    if (!positions_from_c(g, gm, gm.a0 + gm.b0 * r2m3, -1.0, gm.a2 + gm.b2 * r2m3, P.min_rho2_au, pos, epoch))
+      continue;
+    V3 vel = gibbs_velocity(pos, gm.tau1, gm.tau3);
+    {
+      const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
+      if (!ec.defined || !ec.accepted) continue;
+    }
+    ++w.roots_accepted;
+    V3 cpos[3] = {pos[0], pos[1], pos[2]};
+    V3 cvel = vel;
+    double cepoch;
+    const bool corrected = pos_and_vel_correction(g, gm, P, cpos, cvel, cepoch, w);
+    ++n_solutions;
+    if (corrected || !have_first) {
+      // build_result (gauss.rs:1063): rotate to ecliptic J2000, state -> elements
+      const V3 rr = corrected ? cpos[1] : pos[1];
+      const V3 vv = corrected ? cvel : vel;
+      ccek1(equ_to_ecl(rr), equ_to_ecl(vv), corrected ? cepoch : epoch, out);
+      out.corrected = corrected ? 1 : 0;
+      have_first = true;
+      if (corrected) return 0;  // first CorrectedOrbit in discovery order wins (gauss.rs:1240-1245)
+    }
+    if (n_solutions >= P.max_tested_solutions) break;
+  }
+  return have_first ? 0 : 2;
+}
+
+}  // namespace ofb

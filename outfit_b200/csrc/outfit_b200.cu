@@ -1,0 +1,762 @@
+// outfit_b200.cu -- kernels + C-ABI (include/outfit_b200.h) of the B200-native batched IOD path.
+//
+// Kernels (all scalar FP64, sm_100a):
+//   iod_kernel                 one warp per trajectory, one lane per (triplet, realization)
+//   scorer_observer_kernel     per observation: DE-style Chebyshev Earth position + frame rotations
+//   propagate_universal_kernel one thread per two-body propagation
+//   fp64_peak_kernel           DFMA issue-rate probe (roofline denominator)
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/outfit_b200.h"
+#include "dev_iod.cuh"
+#include "dev_geometry.cuh"
+
+using namespace ofb;
+
+// =================================================================================================
+// full-IOD kernel
+// =================================================================================================
+struct IodBatchDev {
+  unsigned long long n_traj;
+  unsigned long long n_obs;
+  const unsigned long long *traj_offset;
+  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
+  const double *helio;   // [3][n_obs]
+  const double *scorer;  // [3][n_obs]
+  const double *noise_z; // [n_traj][max_triplets][n_noise][6] or null
+};
+
+struct CandScore {
+  int kind;     // 0 = gauss error (code), 1 = abort trajectory (code), 2 = score break, 3 = score sum
+  int code;
+  double sum;
+  unsigned n_arc;
+};
+
+constexpr int kWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+iod_kernel(IodBatchDev B, IodDevParams P, OutfitIodResult *__restrict__ out, unsigned n_obs_cap,
+           unsigned long long *__restrict__ traj_counter, unsigned long long *__restrict__ work_counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const size_t per_warp = (size_t)kObsPlanes * n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8);
+  const size_t per_warp_al = (per_warp + 15) & ~(size_t)15;
+  unsigned char *base = smem_raw + warp * per_warp_al;
+  TrajSmem sm;
+  {
+    double *d = reinterpret_cast<double *>(base);
+    sm.t = d; sm.ra = d + n_obs_cap; sm.dec = d + 2 * n_obs_cap; sm.sra = d + 3 * n_obs_cap;
+    sm.sdec = d + 4 * n_obs_cap; sm.cosdec = d + 5 * n_obs_cap;
+    sm.hx = d + 6 * n_obs_cap; sm.hy = d + 7 * n_obs_cap; sm.hz = d + 8 * n_obs_cap;
+    sm.ox = d + 9 * n_obs_cap; sm.oy = d + 10 * n_obs_cap; sm.oz = d + 11 * n_obs_cap;
+    sm.heap_w = d + (size_t)kObsPlanes * n_obs_cap;
+    sm.heap_x = reinterpret_cast<unsigned *>(sm.heap_w + P.max_triplets);
+    sm.trip = reinterpret_cast<unsigned short *>(sm.heap_x + P.max_triplets);
+  }
+  Work w;
+  memset(&w, 0, sizeof w);
+  const unsigned M = P.n_noise + 1;
+
+  for (;;) {
+    // dynamic trajectory fetch: one atomic per warp (trajectories differ in n_obs and work)
+    unsigned long long tr = 0;
+    if (lane == 0) tr = atomicAdd(traj_counter, 1ull);
+    tr = __shfl_sync(0xffffffffu, tr, 0);
+    if (tr >= B.n_traj) break;
+    const unsigned long long o0 = B.traj_offset[tr];
+    const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+    __syncwarp();
+    // stage the trajectory's observation stream: coalesced 8-byte lanes per plane
+    for (unsigned i = lane; i < n_obs; i += 32) {
+      const unsigned long long gI = o0 + i;
+      sm.t[i] = B.mjd_tt[gI];
+      sm.ra[i] = B.ra[gI];
+      const double d = B.dec[gI];
+      sm.dec[i] = d;
+      sm.cosdec[i] = cos(d);
+      sm.sra[i] = B.sigma_ra[gI];
+      sm.sdec[i] = B.sigma_dec[gI];
+      sm.hx[i] = B.helio[gI]; sm.hy[i] = B.helio[B.n_obs + gI]; sm.hz[i] = B.helio[2 * B.n_obs + gI];
+      sm.ox[i] = B.scorer[gI]; sm.oy[i] = B.scorer[B.n_obs + gI]; sm.oz[i] = B.scorer[2 * B.n_obs + gI];
+    }
+    __syncwarp();
+
+    OutfitIodResult res;
+    memset(&res, 0, sizeof res);
+    res.rms = NAN;
+    const unsigned K = select_triplets(sm, n_obs, P, lane);
+    if (K == 0) {
+      if (lane == 0) {
+        res.status = OUTFIT_ST_NO_FEASIBLE_TRIPLETS;
+        res.span = n_obs == 0 ? 0.0 : sm.t[n_obs - 1] - sm.t[0];
+        out[tr] = res;
+      }
+      continue;
+    }
+    const unsigned n_cand = K * M;
+    // warp-uniform fold state (identical in every lane)
+    double best_rms = INFINITY;
+    unsigned best_c = 0xffffffffu;
+    int abort_code = 0;
+    unsigned abort_c = 0xffffffffu;
+    // warp-uniform copy of the currently selected orbit (broadcast from the owning lane)
+    int bo_kind = 0, bo_corrected = 0;
+    double bo_epoch = 0.0, bo_e0 = 0.0, bo_e1 = 0.0, bo_e2 = 0.0, bo_e3 = 0.0, bo_e4 = 0.0, bo_e5 = 0.0;
+    int last_kind = 0, last_code = 0;
+    double last_val = 0.0;
+
+    for (unsigned cbase = 0; cbase < n_cand; cbase += 32) {
+      const unsigned c = cbase + lane;
+      CandScore cs;
+      cs.kind = -1; cs.code = 0; cs.sum = 0.0; cs.n_arc = 0;
+      Orbit orb;
+      orb.kind = 0; orb.corrected = 0; orb.epoch = 0.0;
+      if (c < n_cand) {
+        ++w.candidates;
+        const unsigned r = c / M, m = c - r * M;
+        const unsigned i0 = sm.trip[4 * r], i1 = sm.trip[4 * r + 1], i2 = sm.trip[4 * r + 2];
+        double ra[3] = {sm.ra[i0], sm.ra[i1], sm.ra[i2]};
+        double dec[3] = {sm.dec[i0], sm.dec[i1], sm.dec[i2]};
+        if (m > 0) {
+          // realizations_iter (gauss.rs:323-387): z order ra0,ra1,ra2,dec0,dec1,dec2
+          const double *z = B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6;
+          const double2 z01 = __ldg(reinterpret_cast<const double2 *>(z));
+          const double2 z23 = __ldg(reinterpret_cast<const double2 *>(z) + 1);
+          const double2 z45 = __ldg(reinterpret_cast<const double2 *>(z) + 2);
+          ra[0] = ra[0] + z01.x * (sm.sra[i0] * P.noise_scale);
+          ra[1] = ra[1] + z01.y * (sm.sra[i1] * P.noise_scale);
+          ra[2] = ra[2] + z23.x * (sm.sra[i2] * P.noise_scale);
+          dec[0] = dec[0] + z23.y * (sm.sdec[i0] * P.noise_scale);
+          dec[1] = dec[1] + z45.x * (sm.sdec[i1] * P.noise_scale);
+          dec[2] = dec[2] + z45.y * (sm.sdec[i2] * P.noise_scale);
+        }
+        const int rc = gauss_prelim_orbit(sm, i0, i1, i2, ra, dec, P, orb, w);
+        if (rc != 0) {
+          cs.kind = 0; cs.code = rc;
+        } else {
+          Equinoctial eq;
+          const int rq = to_equinoctial(orb, eq);
+          if (rq != 0) {
+            cs.kind = 1; cs.code = rq;
+          } else {
+            // select_rms_interval (trajectory.rs:294-350)
+            const double t1 = sm.t[i0], t3 = sm.t[i2];
+            double dtw = P.extf >= 0.0 ? (t3 - t1) * P.extf : 10.0 * (sm.t[n_obs - 1] - sm.t[0]);
+            if (P.dtmax >= 0.0) dtw = fmax(dtw, P.dtmax);
+            unsigned is = 0, ie = n_obs - 1;
+            for (int ii = (int)i0; ii >= 0; --ii) {
+              if (t1 - sm.t[ii] > dtw) break;
+              is = (unsigned)ii;
+            }
+            for (unsigned ii = i2; ii < n_obs; ++ii) {
+              if (sm.t[ii] - t3 > dtw) break;
+              ie = ii;
+            }
+            cs.n_arc = ie - is + 1;
+            const ScoreOrbit so = make_score_orbit(eq);
+            cs.kind = 3;
+            double sum = 0.0;
+            if (!so.elliptic) {
+              cs.kind = 2;
+            } else {
+              for (unsigned ii = is; ii <= ie; ++ii) {
+                double v;
+                if (!ephemeris_error(so, sm.t[ii], sm.ra[ii], sm.dec[ii], sm.cosdec[ii], sm.sra[ii],
+                                     sm.sdec[ii], V3{sm.ox[ii], sm.oy[ii], sm.oz[ii]}, v, w)) {
+                  cs.kind = 2;
+                  break;
+                }
+                const double ns = sum + v;
+                if (ns >= INFINITY) { cs.kind = 2; break; }
+                sum = ns;
+              }
+            }
+            cs.sum = sum;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- order-preserving fold of this chunk (trajectory.rs:465-528) ------------------------
+      // (a) the first candidate whose conversion to equinoctial fails aborts the trajectory
+      {
+        const unsigned ab = __ballot_sync(0xffffffffu, cs.kind == 1);
+        if (ab != 0 && abort_c == 0xffffffffu) {
+          const int src = __ffs(ab) - 1;
+          abort_c = cbase + src;
+          abort_code = __shfl_sync(0xffffffffu, cs.code, src);
+        }
+      }
+      // (b) running-best selection with the reference's pruning rule: a candidate replaces the
+      //     best iff its full sum stays below best^2 * 2N (never pruned) and sqrt(sum/2N) < best
+      {
+        const double denom = 2.0 * (double)cs.n_arc;
+        const double rms_c = sqrt(cs.sum / denom);
+        unsigned from = 0;
+        for (;;) {
+          const double cutoff = isfinite(best_rms) ? best_rms * best_rms * denom : INFINITY;
+          const bool acc = cs.kind == 3 && lane >= from && !(cs.sum >= cutoff) && isfinite(rms_c) && rms_c < best_rms;
+          const unsigned bal = __ballot_sync(0xffffffffu, acc);
+          if (bal == 0) break;
+          const int src = __ffs(bal) - 1;
+          best_rms = __shfl_sync(0xffffffffu, rms_c, src);
+          best_c = cbase + src;
+          bo_kind = __shfl_sync(0xffffffffu, orb.kind, src);
+          bo_corrected = __shfl_sync(0xffffffffu, orb.corrected, src);
+          bo_epoch = __shfl_sync(0xffffffffu, orb.epoch, src);
+          bo_e0 = __shfl_sync(0xffffffffu, orb.e[0], src);
+          bo_e1 = __shfl_sync(0xffffffffu, orb.e[1], src);
+          bo_e2 = __shfl_sync(0xffffffffu, orb.e[2], src);
+          bo_e3 = __shfl_sync(0xffffffffu, orb.e[3], src);
+          bo_e4 = __shfl_sync(0xffffffffu, orb.e[4], src);
+          bo_e5 = __shfl_sync(0xffffffffu, orb.e[5], src);
+          from = src + 1;
+          if (from >= 32) break;
+        }
+      }
+      // (c) error of the LAST candidate in evaluation order (only used when nothing succeeds,
+      //     in which case best_rms stayed +inf for every candidate)
+      if (c == n_cand - 1) {
+        if (cs.kind == 0) { last_kind = 0; last_code = cs.code; last_val = 0.0; }
+        else if (cs.kind == 2) { last_kind = 1; last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = INFINITY; }
+        else if (cs.kind == 3) {
+          last_kind = 1; last_code = OUTFIT_ST_NON_FINITE_SCORE;
+          last_val = sqrt(cs.sum / (2.0 * (double)cs.n_arc));
+        }
+      }
+    }
+
+    // ---- result ---------------------------------------------------------------------------
+    const unsigned last_lane = (n_cand - 1) & 31u;
+    const int l_code = __shfl_sync(0xffffffffu, last_code, last_lane);
+    const double l_val = __shfl_sync(0xffffffffu, last_val, last_lane);
+    (void)last_kind;
+    if (abort_c != 0xffffffffu) {
+      // `?` in trajectory.rs:491-497 returns the conversion error for the whole trajectory
+      if (lane == 0) {
+        res.status = abort_code;
+        res.attempts = abort_c + 1;
+        out[tr] = res;
+      }
+    } else if (best_c != 0xffffffffu) {
+      if (lane == 0) {
+        const unsigned r = best_c / M;
+        res.status = OUTFIT_ST_OK;
+        res.attempts = n_cand;
+        res.corrected = bo_corrected;
+        res.element_kind = bo_kind;
+        res.epoch = bo_epoch;
+        res.elem[0] = bo_e0; res.elem[1] = bo_e1; res.elem[2] = bo_e2;
+        res.elem[3] = bo_e3; res.elem[4] = bo_e4; res.elem[5] = bo_e5;
+        res.rms = best_rms;
+        res.triplet_idx[0] = sm.trip[4 * r];
+        res.triplet_idx[1] = sm.trip[4 * r + 1];
+        res.triplet_idx[2] = sm.trip[4 * r + 2];
+        res.triplet_rank = r;
+        res.realization = best_c - r * M;
+        out[tr] = res;
+      }
+    } else if (lane == 0) {
+      res.status = OUTFIT_ST_NO_VIABLE_ORBIT;
+      res.cause = l_code;
+      res.cause_value = l_val;
+      res.attempts = n_cand;
+      out[tr] = res;
+    }
+    __syncwarp();
+  }
+
+  // work counters: warp reduce, one atomic per counter per warp
+  unsigned *wp = reinterpret_cast<unsigned *>(&w);
+#pragma unroll
+  for (int q = 0; q < (int)(sizeof(Work) / sizeof(unsigned)); ++q) {
+    unsigned long long v = wp[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0 && work_counters) atomicAdd(&work_counters[q], v);
+  }
+}
+
+// =================================================================================================
+// bulk propagate_universal (kepler/propagation.rs:114-207)
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double *__restrict__ t0,
+                           const double *__restrict__ t1, const double *__restrict__ psi_guess,
+                           OutfitSolverType st, double *__restrict__ out, int *__restrict__ status) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Work w;
+  memset(&w, 0, sizeof w);
+  const V3 r = V3{rv[i], rv[n + i], rv[2 * n + i]};
+  const V3 v = V3{rv[3 * n + i], rv[4 * n + i], rv[5 * n + i]};
+  double o[11];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) o[q] = NAN;
+  int stt = OUTFIT_ST_OK;
+  const double r0 = norm(r);
+  if (r0 < kEps) {
+    stt = OUTFIT_ST_DEGENERATE_STATE;
+  } else {
+    const double v2 = dot(v, v);
+    const double sig0 = dot(r, v) / kGaussK;
+    const double alpha = (v2 - 2.0 * kMu / r0) / kMu;
+    const V3 h = cross(r, v);
+    double e0 = sqrt(1.0 + alpha * dot(h, h) / kMu);
+    e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
+    KepIn kp;
+    kp.dt = t1[i] - t0[i]; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
+    kp.convergency = st.convergency;
+    kp.max_iter_prelim = (unsigned)st.max_iter_prelim_kepuni;
+    kp.parabolic_newton = st.parabolic_method;
+    const double psi0 = psi_guess ? psi_guess[i] : prelim_kepuni(kp);
+    KepSol sol;
+    sol.ok = false;
+    if (st.kind == OUTFIT_SOLVER_NEWTON || st.kind == OUTFIT_SOLVER_AUTO) sol = solve_kepuni_newton(kp, psi0, w);
+    if (!sol.ok && st.kind != OUTFIT_SOLVER_NEWTON) sol = solve_kepuni_brent(kp, psi0, w);
+    if (!sol.ok) {
+      stt = st.kind == OUTFIT_SOLVER_NEWTON ? OUTFIT_ST_NEWTON_KEPLER : OUTFIT_ST_BRENT_KEPLER;
+    } else {
+      const double r1 = r0 * sol.s.s0 + sig0 * sol.s.s1 + sol.s.s2;
+      if (r1 < kEps) {
+        stt = OUTFIT_ST_DEGENERATE_STATE;
+      } else {
+        const double fl = 1.0 - sol.s.s2 / r0;
+        const double gl = (r0 * sol.s.s1 + sig0 * sol.s.s2) / kGaussK;
+        const double fd = -(kGaussK / (r0 * r1)) * sol.s.s1;
+        const double gd = 1.0 - sol.s.s2 / r1;
+        o[0] = fl * r.x + gl * v.x; o[1] = fl * r.y + gl * v.y; o[2] = fl * r.z + gl * v.z;
+        o[3] = fd * r.x + gd * v.x; o[4] = fd * r.y + gd * v.y; o[5] = fd * r.z + gd * v.z;
+        o[6] = fl; o[7] = gl; o[8] = fd; o[9] = gd; o[10] = sol.psi;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 11; ++q) out[(size_t)q * n + i] = o[q];
+  status[i] = stt;
+}
+
+// =================================================================================================
+// FP64 pipe probe
+// =================================================================================================
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters) {
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) sink[0] = s;
+}
+
+// =================================================================================================
+// context + C-ABI
+// =================================================================================================
+struct OutfitCtx {
+  int device = 0;
+  int sm_count = 0;
+  std::string last_error;
+  EphemDev eph{};
+  double *d_cheb = nullptr;
+  bool have_eph = false;
+  unsigned long long *d_counters = nullptr;  // [0] trajectory fetch counter, [1..] work counters
+  // scratch owned by the context (grown on demand)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void *h_scratch = nullptr;
+};
+
+static int fail(OutfitCtx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    ctx->last_error = what;
+    if (e != cudaSuccess) { ctx->last_error += ": "; ctx->last_error += cudaGetErrorString(e); }
+  }
+  return code;
+}
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, #call, e__); \
+  } while (0)
+
+extern "C" int outfit_b200_abi_version(void) { return OUTFIT_B200_ABI_VERSION; }
+
+extern "C" const char *outfit_b200_strerror(int code) {
+  switch (code) {
+    case OUTFIT_OK: return "ok";
+    case OUTFIT_E_INVALID_ARGUMENT: return "invalid argument";
+    case OUTFIT_E_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case OUTFIT_E_CUDA: return "CUDA runtime error";
+    case OUTFIT_E_ALLOC: return "allocation failed";
+    case OUTFIT_E_INVALID_IOD_PARAMETER: return "invalid IOD parameter";
+    case OUTFIT_E_NO_EPHEMERIS: return "ephemeris table not loaded";
+    case OUTFIT_E_UNSUPPORTED: return "size exceeds a kernel limit";
+    default: return "unknown error";
+  }
+}
+extern "C" const char *outfit_b200_last_error(OutfitCtx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+extern "C" void outfit_b200_iod_params_default(OutfitIodParams *p) {
+  memset(p, 0, sizeof *p);
+  p->n_noise_realizations = 20; p->noise_scale = 1.0; p->extf = -1.0; p->dtmax = 30.0;
+  p->dt_min = 0.03; p->dt_max_triplet = 150.0; p->optimal_interval_time = 20.0;
+  p->max_obs_for_triplets = 100; p->max_triplets = 10; p->gap_max = 8.0 / 24.0;
+  p->max_ecc = 5.0; p->max_perihelion_au = 1.0e3; p->min_rho2_au = 0.01;
+  p->aberth_max_iter = 50; p->aberth_eps = 1.0e-6; p->kepler_eps = 1e3 * 2.220446049250313e-16;
+  p->max_tested_solutions = 3; p->r2_min_au = 0.05; p->r2_max_au = 200.0;
+  p->newton_eps = 1.0e-10; p->newton_max_it = 50; p->root_imag_eps = 1.0e-6;
+}
+extern "C" int outfit_b200_iod_params_validate(const OutfitIodParams *p) {
+  if (!p) return OUTFIT_E_INVALID_ARGUMENT;
+  const bool ok = p->noise_scale >= 0.0 && p->dt_min >= 0.0 && p->dt_max_triplet >= 0.0 && p->dtmax >= 0.0 &&
+                  p->max_ecc >= 0.0 && p->root_imag_eps >= 0.0 && p->max_perihelion_au > 0.0 &&
+                  p->min_rho2_au > 0.0 && p->aberth_eps > 0.0 && p->kepler_eps > 0.0 && p->newton_eps > 0.0 &&
+                  p->newton_max_it != 0 && p->aberth_max_iter != 0 && p->max_tested_solutions >= 1 &&
+                  p->r2_min_au > 0.0 && p->r2_max_au > 0.0 && p->r2_min_au <= p->r2_max_au;
+  return ok ? OUTFIT_OK : OUTFIT_E_INVALID_IOD_PARAMETER;
+}
+extern "C" void outfit_b200_solver_type_default(OutfitSolverType *s) {
+  s->kind = OUTFIT_SOLVER_NEWTON; s->parabolic_method = 0;
+  s->convergency = 100.0 * 2.220446049250313e-16; s->max_iter_prelim_kepuni = 20;
+}
+
+extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
+  if (!out) return OUTFIT_E_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return OUTFIT_E_NO_DEVICE;
+  OutfitCtx *ctx = new (std::nothrow) OutfitCtx();
+  if (!ctx) return OUTFIT_E_ALLOC;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) { delete ctx; return OUTFIT_E_CUDA; }
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return OUTFIT_E_CUDA; }
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return OUTFIT_E_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)) != cudaSuccess) { delete ctx; return OUTFIT_E_ALLOC; }
+  cudaMemset(ctx->d_counters, 0, 32 * sizeof(unsigned long long));
+  // Aberth starting directions from the HOST libm (see dev_gauss.cuh)
+  double dir[16];
+  for (int k = 0; k < 8; ++k) {
+    const double theta = (6.283185307179586476925286766559 / 8.0) * (double)k + (3.14159265358979323846 / 2.0) / 8.0;
+    dir[2 * k] = cos(theta);
+    dir[2 * k + 1] = sin(theta);
+  }
+  if (cudaMemcpyToSymbol(c_aberth_dir, dir, sizeof dir) != cudaSuccess) { cudaFree(ctx->d_counters); delete ctx; return OUTFIT_E_CUDA; }
+  *out = ctx;
+  return OUTFIT_OK;
+}
+
+extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_cheb) cudaFree(ctx->d_cheb);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  delete ctx;
+}
+
+extern "C" int outfit_b200_load_ephemeris(OutfitCtx *ctx, const double *cheb, size_t n_blocks,
+                                          size_t block_stride, double jd_start, double block_days,
+                                          const uint32_t ipt[3][3], double emrat) {
+  if (!ctx || !cheb || n_blocks == 0 || block_stride == 0 || !(block_days > 0.0)) return OUTFIT_E_INVALID_ARGUMENT;
+  for (int b = 0; b < 3; ++b) {
+    if (ipt[b][1] < 3 || ipt[b][1] > kMaxCheb || ipt[b][2] == 0) return fail(ctx, OUTFIT_E_UNSUPPORTED, "ipt: n_coeff must be in [3, 18]");
+    if ((size_t)ipt[b][0] + (size_t)ipt[b][1] * ipt[b][2] * 3 > block_stride) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "ipt exceeds block_stride");
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_cheb) { cudaFree(ctx->d_cheb); ctx->d_cheb = nullptr; }
+  CK(cudaMalloc(&ctx->d_cheb, n_blocks * block_stride * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_cheb, cheb, n_blocks * block_stride * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->eph.cheb = ctx->d_cheb;
+  ctx->eph.n_blocks = n_blocks;
+  ctx->eph.block_stride = block_stride;
+  ctx->eph.jd_start = jd_start;
+  ctx->eph.jd_end = jd_start + block_days * (double)n_blocks;
+  ctx->eph.block_days = block_days;
+  for (int b = 0; b < 3; ++b)
+    for (int j = 0; j < 3; ++j) ctx->eph.ipt[b][j] = ipt[b][j];
+  ctx->eph.emrat = emrat;
+  ctx->have_eph = true;
+  return OUTFIT_OK;
+}
+
+static int ensure_scratch(OutfitCtx *ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return OUTFIT_OK;
+  if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+  if (cudaMalloc(&ctx->scratch, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(scratch)");
+  ctx->scratch_bytes = bytes;
+  return OUTFIT_OK;
+}
+
+static IodDevParams to_dev_params(const OutfitIodParams &p) {
+  IodDevParams d;
+  d.noise_scale = p.noise_scale; d.extf = p.extf; d.dtmax = p.dtmax; d.dt_min = p.dt_min;
+  d.dt_max_triplet = p.dt_max_triplet; d.inv_optimal_interval = 1.0 / p.optimal_interval_time;
+  d.max_ecc = p.max_ecc; d.max_perihelion_au = p.max_perihelion_au; d.min_rho2_au = p.min_rho2_au;
+  d.aberth_eps = p.aberth_eps; d.kepler_eps = p.kepler_eps; d.r2_min_au = p.r2_min_au; d.r2_max_au = p.r2_max_au;
+  d.newton_eps = p.newton_eps; d.root_imag_eps = p.root_imag_eps;
+  d.n_noise = (unsigned)p.n_noise_realizations; d.max_triplets = p.max_triplets;
+  d.max_obs_for_triplets = p.max_obs_for_triplets > 0xffffffffull ? 0xffffffffu : (unsigned)p.max_obs_for_triplets;
+  d.aberth_max_iter = p.aberth_max_iter;
+  d.max_tested_solutions = p.max_tested_solutions > 0xffffffffull ? 0xffffffffu : (unsigned)p.max_tested_solutions;
+  d.newton_max_it = p.newton_max_it > 0xffffffffull ? 0xffffffffu : (unsigned)p.newton_max_it;
+  return d;
+}
+
+// max observations per trajectory the shared-memory staging supports (per-warp planes)
+constexpr unsigned kMaxObsPerTraj = 448;
+constexpr unsigned kMaxTriplets = 1024;
+
+// Launch the device pipeline on device-resident buffers.  `max_obs` = longest trajectory.
+static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *b,
+                      OutfitIodResult *d_out, unsigned max_obs, cudaStream_t stream) {
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  if (max_obs > kMaxObsPerTraj) return fail(ctx, OUTFIT_E_UNSUPPORTED, "trajectory longer than 448 observations");
+  if (params->max_triplets > kMaxTriplets) return fail(ctx, OUTFIT_E_UNSUPPORTED, "max_triplets > 1024");
+  if (params->n_noise_realizations > 0 && !b->noise_z) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "noise_z is NULL but n_noise_realizations > 0");
+  if (params->n_noise_realizations > 65535) return fail(ctx, OUTFIT_E_UNSUPPORTED, "n_noise_realizations > 65535");
+  const size_t n = b->n_obs;
+  const bool have_cache = b->obs_helio_equ && b->obs_geo_ecl;
+  const bool have_bf = b->observer_body_fixed && b->mjd_ut1;
+  if (!have_cache && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_helio_equ+obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  // scratch: scorer[3][n] (+ geo[3][n] + helio[3][n] when computed on device) + status[n]
+  const size_t planes = have_cache ? 3 : 9;
+  int rc = ensure_scratch(ctx, planes * n * sizeof(double) + n * sizeof(int) + 256);
+  if (rc) return rc;
+  double *d_scorer = reinterpret_cast<double *>(ctx->scratch);
+  const double *d_geo = b->obs_geo_ecl;
+  const double *d_helio = b->obs_helio_equ;
+  int *d_status = reinterpret_cast<int *>(d_scorer + planes * n);
+  const int tpb = 128;
+  const unsigned gblocks = (unsigned)((n + tpb - 1) / tpb);
+  if (!have_cache) {
+    double *geo = d_scorer + 3 * n, *helio = d_scorer + 6 * n;
+    if (n) observer_cache_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, b->mjd_ut1, b->observer_body_fixed, geo, helio, d_status);
+    d_geo = geo;
+    d_helio = helio;
+  }
+  if (n) scorer_observer_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, d_geo, d_scorer, d_status);
+
+  IodBatchDev B;
+  B.n_traj = b->n_traj; B.n_obs = n; B.traj_offset = reinterpret_cast<const unsigned long long *>(b->traj_offset);
+  B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
+  B.helio = d_helio; B.scorer = d_scorer; B.noise_z = b->noise_z;
+  const IodDevParams P = to_dev_params(*params);
+  const unsigned cap = max_obs < 3 ? 4 : ((max_obs + 1) & ~1u);
+  size_t per_warp = (size_t)kObsPlanes * cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8);
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  const size_t smem = per_warp * kWarpsPerBlock;
+  if (smem > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");
+  CK(cudaFuncSetAttribute(iod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iod_kernel, kWarpsPerBlock * 32, smem));
+  if (occ < 1) occ = 1;
+  unsigned long long want = (b->n_traj + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  unsigned grid = (unsigned)ctx->sm_count * (unsigned)occ;  // persistent: a multiple of the SM count
+  if (want < grid) grid = (unsigned)(want ? want : 1);
+  CK(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), stream));
+  if (b->n_traj) iod_kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(B, P, d_out, cap, ctx->d_counters, ctx->d_counters + 1);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodParams *params,
+                                               const OutfitObsBatch *batch, OutfitIodResult *out,
+                                               void *cuda_stream) {
+  if (!ctx || !params || !batch || (!out && batch->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  int rc = outfit_b200_iod_params_validate(params);
+  if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  // longest trajectory: read the offsets back once (T+1 words); callers that know it can avoid
+  // this by using the host entry point, which computes it from the host copy.
+  unsigned max_obs = 0;
+  if (batch->n_traj) {
+    std::string keep;
+    unsigned long long *h = (unsigned long long *)malloc((batch->n_traj + 1) * sizeof(unsigned long long));
+    if (!h) return fail(ctx, OUTFIT_E_ALLOC, "malloc(offsets)");
+    cudaError_t e = cudaMemcpyAsync(h, batch->traj_offset, (batch->n_traj + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { free(h); return fail(ctx, OUTFIT_E_CUDA, "read traj_offset", e); }
+    for (unsigned long long t = 0; t < batch->n_traj; ++t) {
+      const unsigned long long c = h[t + 1] - h[t];
+      if (c > max_obs) max_obs = c > 0xffffffffull ? 0xffffffffu : (unsigned)c;
+    }
+    free(h);
+  }
+  return launch_iod(ctx, params, batch, out, max_obs, stream);
+}
+
+extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *params,
+                                        const OutfitObsBatch *hb, OutfitIodResult *out) {
+  if (!ctx || !params || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  int rc = outfit_b200_iod_params_validate(params);
+  if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
+  if (hb->n_traj && (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec))
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  CK(cudaSetDevice(ctx->device));
+  const size_t T = hb->n_traj, n = hb->n_obs;
+  if (T == 0) return OUTFIT_OK;
+  unsigned max_obs = 0;
+  for (size_t t = 0; t < T; ++t) {
+    if (hb->traj_offset[t + 1] < hb->traj_offset[t] || hb->traj_offset[t + 1] > n)
+      return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "traj_offset is not monotone within n_obs");
+    const unsigned long long c = hb->traj_offset[t + 1] - hb->traj_offset[t];
+    if (c > max_obs) max_obs = c > 0xffffffffull ? 0xffffffffu : (unsigned)c;
+  }
+  const bool have_cache = hb->obs_helio_equ && hb->obs_geo_ecl;
+  const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
+  if (!have_cache && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_helio_equ+obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  const size_t n_noise_doubles = hb->noise_z ? T * (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
+  // one device arena for the inputs and the results (every sub-buffer 256-B aligned)
+  const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 +
+                       T * sizeof(OutfitIodResult) + 16 * 256;
+  unsigned char *arena = nullptr;
+  if (cudaMalloc(&arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(batch arena)");
+  cudaStream_t stream = 0;
+  size_t off = 0;
+  auto put = [&](const void *src, size_t nbytes) -> void * {
+    void *dst = arena + off;
+    off += (nbytes + 255) & ~(size_t)255;
+    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream);
+    return dst;
+  };
+  OutfitObsBatch db = *hb;
+  db.traj_offset = (const uint64_t *)put(hb->traj_offset, (T + 1) * 8);
+  db.mjd_tt = (const double *)put(hb->mjd_tt, n * 8);
+  db.ra = (const double *)put(hb->ra, n * 8);
+  db.dec = (const double *)put(hb->dec, n * 8);
+  db.sigma_ra = (const double *)put(hb->sigma_ra, n * 8);
+  db.sigma_dec = (const double *)put(hb->sigma_dec, n * 8);
+  if (have_cache) {
+    db.obs_helio_equ = (const double *)put(hb->obs_helio_equ, 3 * n * 8);
+    db.obs_geo_ecl = (const double *)put(hb->obs_geo_ecl, 3 * n * 8);
+    db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
+  } else {
+    db.observer_body_fixed = (const double *)put(hb->observer_body_fixed, 3 * n * 8);
+    db.mjd_ut1 = (const double *)put(hb->mjd_ut1, n * 8);
+    db.obs_helio_equ = nullptr; db.obs_geo_ecl = nullptr;
+  }
+  db.noise_z = n_noise_doubles ? (const double *)put(hb->noise_z, n_noise_doubles * 8) : nullptr;
+  OutfitIodResult *d_out = (OutfitIodResult *)put(nullptr, T * sizeof(OutfitIodResult));
+  rc = launch_iod(ctx, params, &db, d_out, max_obs, stream);
+  if (rc == OUTFIT_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitIodResult), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "fit_full_iod: copy back / kernel", e);
+  }
+  cudaFree(arena);
+  return rc;
+}
+
+extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *out) {
+  if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long h[32];
+  CK(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+  // order of struct Work (dev_kepler.cuh)
+  out->gauss_solves = h[1]; out->aberth_sweeps = h[2]; out->roots_accepted = h[3]; out->fg_iterations = h[4];
+  out->kepler_universal_solves = h[5]; out->newton_steps = h[6]; out->sfunct_terms = h[7];
+  out->scorer_evals = h[8]; out->scorer_newton_steps = h[9]; out->candidates = h[10];
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_observer_cache_device(OutfitCtx *ctx, size_t n, const double *mjd_tt,
+                                                 const double *mjd_ut1, const double *bf, double *geo_ecl,
+                                                 double *helio_equ, int32_t *status, void *cuda_stream) {
+  if (!ctx || (n && (!mjd_tt || !mjd_ut1 || !bf || !geo_ecl || !helio_equ))) return OUTFIT_E_INVALID_ARGUMENT;
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return OUTFIT_OK;
+  const int tpb = 128;
+  observer_cache_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      ctx->eph, n, mjd_tt, mjd_ut1, bf, geo_ecl, helio_equ, status);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_propagate_universal_device(OutfitCtx *ctx, size_t n, const double *rv, const double *t0,
+                                                      const double *t1, const double *psi_guess,
+                                                      const OutfitSolverType *solver, double *out, int32_t *status,
+                                                      void *cuda_stream) {
+  if (!ctx || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return OUTFIT_OK;
+  const int tpb = 128;
+  propagate_universal_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      n, rv, t0, t1, psi_guess, *solver, out, status);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_propagate_universal(OutfitCtx *ctx, size_t n, const double *rv, const double *t0,
+                                               const double *t1, const double *psi_guess,
+                                               const OutfitSolverType *solver, double *out, int32_t *status) {
+  if (!ctx || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return OUTFIT_OK;
+  const size_t in_d = (8 + (psi_guess ? 1 : 0)) * n, out_d = 11 * n;
+  double *d = nullptr;
+  if (cudaMalloc(&d, (in_d + out_d) * 8 + n * sizeof(int)) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(propagation)");
+  double *d_rv = d, *d_t0 = d + 6 * n, *d_t1 = d + 7 * n, *d_pg = psi_guess ? d + 8 * n : nullptr, *d_out = d + in_d;
+  int *d_st = reinterpret_cast<int *>(d_out + out_d);
+  int rc = OUTFIT_OK;
+  cudaError_t e = cudaMemcpyAsync(d_rv, rv, 6 * n * 8, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t0, t0, n * 8, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t1, t1, n * 8, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess && psi_guess) e = cudaMemcpyAsync(d_pg, psi_guess, n * 8, cudaMemcpyHostToDevice, 0);
+  if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_universal: H2D", e);
+  if (rc == OUTFIT_OK) rc = outfit_b200_propagate_universal_device(ctx, n, d_rv, d_t0, d_t1, d_pg, solver, d_out, d_st, nullptr);
+  if (rc == OUTFIT_OK) {
+    e = cudaMemcpyAsync(out, d_out, out_d * 8, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n * sizeof(int), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_universal: D2H / kernel", e);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+extern "C" int outfit_b200_measure_fp64_peak(OutfitCtx *ctx, double *flops_per_s) {
+  if (!ctx || !flops_per_s) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  double *sink = nullptr;
+  CK(cudaMalloc(&sink, 8));
+  const int iters = 1 << 15, threads = 256;
+  const int blocks = ctx->sm_count * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  fp64_peak_kernel<<<blocks, threads>>>(sink, iters);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(sink, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks / (ms * 1e-3);
+    if (fl > best) best = fl;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  CK(cudaGetLastError());
+  *flops_per_s = best;
+  return OUTFIT_OK;
+}
