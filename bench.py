@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- full-IOD trajectories/s (+ Kepler propagations/s) on N B200s vs the CPU path.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it
+is launched under torch.distributed.run, one rank per GPU.  Rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[2], the single-GPU full-IOD case): per GPU 100 000 synthetic
+trajectories x 12 observations, IODParams of the reference's examples/run_full_iod*.rs
+(n_noise_realizations=10, noise_scale=1.1, max_triplets=30), synthetic DE440-shaped ephemeris.
+A "step" is one fit_full_iod pass over the batch.  Weak scaling: every rank owns its own 100 k
+trajectories (trajectory-index sharding, no data-path collective); the only cross-GPU step is the
+gather of the per-trajectory results, inside the timed region.
+
+  value     device-resident inputs, CUDA events on the launching stream, max over ranks
+  e2e       same metric through the host-buffer C-ABI entry (pinned host inputs -> H2D ->
+            kernels -> D2H of the results), wall clock bracketed by synchronize, max over ranks
+  roofline  FP64: algorithmic flop of the step (device event counters x the static weights of
+            SURVEY 8d) / CUDA-event duration, against the DFMA peak measured live on this GPU
+            (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline  the C oracle (kind "port": the reference is Rust and cannot be built here) on all
+            host cores over a bounded sample of the same workload (rank 0, N = 1 only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (trajectories per GPU, n_obs, max_triplets, n_noise, noise_scale)
+    "c3_100k_x12": (100_000, 12, 30, 10, 1.1),
+    "c4_ragged_8_30": (100_000, (8, 30), 30, 10, 1.1),
+    "small": (4_000, 12, 30, 10, 1.1),
+}
+# static flop weights per counted event; libm calls are reported separately
+W_FLOP = dict(sfunct_terms=12.0, newton_steps=15.0 + 9.0, fg_iterations=2 * 60.0 + 150.0,
+              aberth_sweeps=1850.0, gauss_solves=120.0, roots_accepted=260.0, candidates=180.0,
+              scorer_evals=127.0, scorer_newton_steps=10.0)
+W_LIBM = dict(gauss_solves=12.0, candidates=15.0, scorer_evals=4.0, scorer_newton_steps=2.0)
+
+
+def algorithmic_flops(counters):
+    return sum(W_FLOP[k] * counters[k] for k in W_FLOP)
+
+
+def libm_calls(counters):
+    return sum(W_LIBM[k] * counters[k] for k in W_LIBM)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(batch, table, kw, target_s=15.0, n_threads=0):
+    """Oracle (C restatement of the reference's Rayon path) on a bounded sample: (traj/s, n, secs)."""
+    from oracle import binding as O
+    from outfit_b200 import shard, synth
+    et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    p = O.default_iod_params(**kw)
+    T = len(batch["traj_offset"]) - 1
+    n0 = min(T, 256)
+    t0 = time.perf_counter()
+    O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, n0)), et, p, n_threads=n_threads)
+    rate0 = n0 / max(time.perf_counter() - t0, 1e-9)
+    n = int(min(T, max(n0, rate0 * target_s)))
+    ob = O.from_soa_batch(shard.slice_batch(batch, 0, n))
+    O.lib().oo_counters_reset()
+    t0 = time.perf_counter()
+    O.fit_full_iod(ob, et, p, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, O.counters()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3_100k_x12", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-kepler", action="store_true", help="skip the 10M propagate_universal leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    T, n_obs, K, nn, nscale = WORKLOADS[args.workload]
+    kw = dict(n_noise_realizations=nn, noise_scale=nscale, max_triplets=K, max_obs_for_triplets=100)
+    cores = os.cpu_count() or 1
+    config = {"workload": f"synthetic {T} trajectories x {n_obs} obs per GPU, full Gauss IOD with arc RMS "
+                          f"(IODParams of examples/run_full_iod: max_triplets={K}, n_noise_realizations={nn}, "
+                          f"noise_scale={nscale}); synthetic DE440-shaped ephemeris",
+              "trajectories_per_gpu": T, "n_obs": n_obs, "max_triplets": K, "n_noise_realizations": nn,
+              "candidates_per_trajectory": K * (nn + 1), "sharding": f"trajectory-index x{world}",
+              "l2": "inputs (>1 GB noise + observation stream per step) exceed the 126 MB L2"}
+
+    from outfit_b200 import synth
+    table = synth.make_ephemeris_table()
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_T = 3000
+        batch = synth.make_trajectories(sample_T, n_obs, seed=20261018, table=table, max_triplets=K, n_noise=nn)
+        from oracle import binding as O
+        from outfit_b200 import shard
+        et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+        p = O.default_iod_params(**kw)
+        ob = O.from_soa_batch(batch)
+        # size each step so that warmup + steps stay within a few minutes
+        t0 = time.perf_counter()
+        O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, 128)), et, p, n_threads=0)
+        rate0 = 128 / (time.perf_counter() - t0)
+        per_step = int(min(sample_T, max(128, rate0 * 120.0 / max(1, args.steps + args.warmup))))
+        ob = O.from_soa_batch(shard.slice_batch(batch, 0, per_step))
+        for _ in range(args.warmup):
+            O.fit_full_iod(ob, et, p, n_threads=0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.fit_full_iod(ob, et, p, n_threads=0)
+        dt = (time.perf_counter() - t0) / max(1, args.steps)
+        v = per_step / dt
+        sample = f"{per_step} trajectories of the same workload per step, all {cores} host threads (pthread pool, one task per trajectory)"
+        print(json.dumps({
+            "impl": "reference", "metric": "full_iod_trajectories_per_s", "value": v, "unit": "trajectories/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference's Rayon path (oracle/); the Rust reference cannot be built in this image"},
+            "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from outfit_b200 import IODParams, OutfitB200, RESULT_DTYPE, SolverType
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: outfit_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch = synth.make_trajectories(T, n_obs, seed=20261018 + rank, table=table, max_triplets=K, n_noise=nn)
+    ctx = OutfitB200(local_rank)
+    ctx.load_ephemeris(table)
+    params = IODParams.builder(**kw)
+    fp64_peak = ctx.measure_fp64_peak()
+
+    keys = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "noise_z"]
+    # pinned host copies (the e2e leg copies from these) and device-resident copies (the `value` leg)
+    pinned, devb = {}, {}
+    for k in keys:
+        a = batch[k]
+        t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a)
+        pinned[k] = t.pin_memory()
+        devb[k] = pinned[k].to(dev, non_blocking=True)
+    host_batch = {k: (pinned[k].numpy().view(np.uint64) if k == "traj_offset" else pinned[k].numpy()) for k in keys}
+    h2d_bytes = int(sum(pinned[k].numel() * pinned[k].element_size() for k in keys))
+    d_out = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d2h_bytes = int(d_out.numel())
+    gather_bufs = [torch.zeros_like(d_out) for _ in range(world)] if world > 1 else None
+    devb["max_obs_per_traj"] = int(np.diff(batch["traj_offset"].astype(np.int64)).max())
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
+        if world > 1:
+            dist.all_gather(gather_bufs, d_out)  # the only cross-GPU step: gather of per-trajectory results
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / max(1, args.steps)
+    counters = ctx.last_iod_counters()
+    launches = args.steps * 2  # scorer_observer_kernel + iod_kernel per step (memset is not ours)
+
+    # kernel-only timing of the dominant kernel path (no gather), for the roofline
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1)
+    launches += 2
+
+    # e2e: host-buffer C-ABI entry (H2D of the pinned inputs + kernels + D2H of the results)
+    ctx.fit_full_iod(host_batch, params)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        res_host = ctx.fit_full_iod(host_batch, params)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    launches += 2 * (e2e_steps + 1)
+    clocks = sampler.stop()
+
+    # Kepler leg: 10 M propagate_universal (BASELINE configs[1]), device-resident
+    kep = None
+    if not args.no_kepler:
+        n_prop = 10_000_000
+        rv, t0a, t1a = synth.make_propagation_states(n_prop, seed=20261018 + rank)
+        d_rv, d_t0, d_t1 = (torch.from_numpy(x).to(dev) for x in (rv, t0a, t1a))
+        d_o = torch.empty(11 * n_prop, dtype=torch.float64, device=dev)
+        d_s = torch.empty(n_prop, dtype=torch.int32, device=dev)
+        st = SolverType(kind=2)
+        for _ in range(3):
+            ctx.propagate_universal_device(n_prop, d_rv, d_t0, d_t1, d_o, d_s, st, stream=stream)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            ctx.propagate_universal_device(n_prop, d_rv, d_t0, d_t1, d_o, d_s, st, stream=stream)
+        p1.record()
+        torch.cuda.synchronize()
+        pms = p0.elapsed_time(p1) / 5
+        launches += 8
+        kep = {"propagate_universal_per_s": n_prop / (pms * 1e-3), "n": n_prop, "ms": pms,
+               "hbm_gbs": 156.0 * n_prop / (pms * 1e-3) / 1e9, "ok_fraction": float((d_s == 0).float().mean().item()),
+               "workload": "10M random elliptic/hyperbolic heliocentric states, SolverKind::Auto, convergency 100 eps"}
+        del d_rv, d_t0, d_t1, d_o, d_s
+
+    # max over ranks
+    tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        if kep is not None:
+            kr = torch.tensor([kep["propagate_universal_per_s"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(kr, op=dist.ReduceOp.SUM)
+            kep["propagate_universal_per_s"] = float(kr.item())
+    ms, e2e_ms, kernel_ms_max = (float(x) for x in tm.tolist())
+
+    if rank == 0:
+        flops = algorithmic_flops(counters)
+        achieved = flops / (kernel_ms * 1e-3)
+        n_total_obs = int(batch["mjd_tt"].shape[0])
+        alg_bytes = 88.0 * n_total_obs + 96.0 * T + 48.0 * T * K * nn
+        kepler_in_iod = counters["scorer_evals"] + counters["kepler_universal_solves"]
+        out = {
+            "metric": "full_iod_trajectories_per_s", "value": T * world / (ms * 1e-3), "unit": "trajectories/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": T * world / (e2e_ms * 1e-3), "unit": "trajectories/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                    "api": "outfit_b200_fit_full_iod (host buffers, pinned)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None, "kernel": "iod_kernel",
+                         "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flops,
+                         "algorithmic_flop_per_trajectory": flops / T, "libm_calls_per_launch": libm_calls(counters),
+                         "peak_source": "measured live: outfit_b200_measure_fp64_peak (independent DFMA chains, all SMs, CUDA events); MEASURED_PEAKS.json has no FP64 figure",
+                         "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": 6536.7,
+                                 "algorithmic_bytes_per_launch": alg_bytes,
+                                 "note": "observation + noise stream; the kernel is FP64-latency/issue bound, not HBM bound"}},
+            "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (kernel_ms * 1e-3),
+                       "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
+            "counters": counters,
+            "selected_ok_fraction": float((res_host["status"] == 0).mean()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, n, dt, oc = oracle_rate(batch, table, kw)
+            out["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                                   "sample": f"first {n} trajectories of the same batch, {dt:.1f} s wall on all {cores} host threads "
+                                             "(C restatement of the reference's Rayon path; per-candidate Earth re-evaluation kept)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -242,6 +242,21 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def from_soa_batch(batch):
+    """Re-pack a product-layout batch (plane-major SoA 3-vectors, [T,K,n,6] noise) for fit_full_iod
+    below (AoS 3-vectors, flat noise + per-trajectory offsets)."""
+    T = len(batch["traj_offset"]) - 1
+    out = {k: batch[k] for k in ("traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec")}
+    out["helio_equ"] = np.ascontiguousarray(batch["helio_equ"].T)
+    out["geo_ecl"] = np.ascontiguousarray(batch["geo_ecl"].T)
+    if batch.get("noise_z") is not None:
+        nz = batch["noise_z"]
+        stride = nz.shape[1] * nz.shape[2] * 6
+        out["noise_z"] = np.ascontiguousarray(nz.reshape(-1))
+        out["noise_offset"] = (np.arange(T + 1, dtype=np.uint64) * np.uint64(stride))
+    return out
+
+
 def fit_full_iod(batch, table, params, n_threads=0, dedup_earth=False):
     """batch: dict of contiguous float64/uint64 numpy arrays (see outfit_b200.synth)."""
     T = len(batch["traj_offset"]) - 1

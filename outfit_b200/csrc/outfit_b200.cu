@@ -584,9 +584,8 @@ extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodPa
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   // longest trajectory: read the offsets back once (T+1 words); callers that know it can avoid
   // this by using the host entry point, which computes it from the host copy.
-  unsigned max_obs = 0;
-  if (batch->n_traj) {
-    std::string keep;
+  unsigned max_obs = batch->max_obs_per_traj > 0xffffffffull ? 0xffffffffu : (unsigned)batch->max_obs_per_traj;
+  if (batch->n_traj && max_obs == 0) {
     unsigned long long *h = (unsigned long long *)malloc((batch->n_traj + 1) * sizeof(unsigned long long));
     if (!h) return fail(ctx, OUTFIT_E_ALLOC, "malloc(offsets)");
     cudaError_t e = cudaMemcpyAsync(h, batch->traj_offset, (batch->n_traj + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);

@@ -1,4 +1,4 @@
-"""Seeded synthetic inputs for the batched-IOD hot path (numpy only; no oracle, no CUDA).
+"""Seeded synthetic inputs for the batched-IOD hot path (numpy only; no CUDA).
 
 What is generated:
   * a DE440-SHAPED Chebyshev table (EMB 13 coefficients x 2 sub-intervals, Moon 13 x 8, Sun 11 x 2
@@ -248,20 +248,6 @@ def make_trajectories(n_traj, n_obs=12, seed=20261018, table=None, max_triplets=
                 body_fixed=c(body_fixed), mjd_ut1=c(t - 69.184 / 86400.0), noise_z=noise,
                 truth=np.stack([a, e, inc, node, argp, M0, epoch0], axis=1), table=table,
                 max_triplets=max_triplets, n_noise=n_noise)
-
-
-def to_oracle_batch(batch):
-    """Re-pack a batch for oracle.binding.fit_full_iod (AoS 3-vectors, flat noise + offsets)."""
-    T = len(batch["traj_offset"]) - 1
-    out = {k: batch[k] for k in ("traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec")}
-    out["helio_equ"] = np.ascontiguousarray(batch["helio_equ"].T)
-    out["geo_ecl"] = np.ascontiguousarray(batch["geo_ecl"].T)
-    if batch.get("noise_z") is not None:
-        nz = batch["noise_z"]
-        stride = nz.shape[1] * nz.shape[2] * 6
-        out["noise_z"] = np.ascontiguousarray(nz.reshape(-1))
-        out["noise_offset"] = (np.arange(T + 1, dtype=np.uint64) * np.uint64(stride))
-    return out
 
 
 # ------------------------------------------------------------------------------------------------

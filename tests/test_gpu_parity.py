@@ -1,0 +1,321 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs (sizes the oracle finishes in seconds), against the committed golden fixture, and
+at BASELINE.json's full sizes through size-independent properties."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parity_util import assert_iod_parity, oracle_floor
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+EPS = 2.220446049250313e-16
+
+
+@pytest.fixture(scope="module")
+def env(oracle):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from outfit_b200 import OutfitB200, synth
+    table = synth.make_ephemeris_table()
+    ctx = OutfitB200(0)  # raises if liboutfit_b200.so is missing: there is no fallback
+    ctx.load_ephemeris(table)
+    et = oracle.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    return dict(ctx=ctx, table=table, et=et, O=oracle, synth=synth)
+
+
+def run_both(env, T, n_obs, seed, K, nn, noise_scale=1.1, floor=True, **extra):
+    from outfit_b200 import IODParams
+    synth, O = env["synth"], env["O"]
+    batch = synth.make_trajectories(T, n_obs, seed=seed, table=env["table"], max_triplets=K, n_noise=max(nn, 1))
+    kw = dict(n_noise_realizations=nn, max_triplets=K, noise_scale=noise_scale, **extra)
+    got = env["ctx"].fit_full_iod(batch, IODParams.builder(**kw))
+    op = O.default_iod_params(**kw)
+    want = O.fit_full_iod(O.from_soa_batch(batch), env["et"], op, n_threads=0)
+    ef = rf = None
+    if floor:
+        ef, rf = oracle_floor(O, synth, batch, env["et"], op, want)
+    return batch, got, want, ef, rf
+
+
+def test_strict_parity_no_noise(env):
+    """n_noise_realizations = 0 (no RNG on the path): 2000 x 12 obs, default max_triplets."""
+    _, got, want, ef, rf = run_both(env, 2000, 12, seed=101, K=10, nn=0)
+    st = assert_iod_parity(got, want, ef, rf, min_plain_fraction=0.90)
+    assert st["n_ok"] > 1800
+
+
+def test_parity_example_params_with_host_deviates(env):
+    """examples/run_full_iod.rs parameters: max_triplets 30, 10 noisy copies, noise_scale 1.1."""
+    _, got, want, ef, rf = run_both(env, 600, 12, seed=102, K=30, nn=10)
+    st = assert_iod_parity(got, want, ef, rf, min_plain_fraction=0.90)
+    assert st["n_ok"] > 550
+
+
+def test_parity_ragged_8_to_30_observations(env):
+    _, got, want, ef, rf = run_both(env, 300, (8, 30), seed=103, K=30, nn=10)
+    assert_iod_parity(got, want, ef, rf)
+
+
+def test_parity_short_and_degenerate_trajectories(env):
+    """0..9 observations: empty, < 3 obs (NoFeasibleTriplets), fewer feasible triplets than K."""
+    from outfit_b200 import IODParams
+    synth, O = env["synth"], env["O"]
+    batch = synth.make_trajectories(400, (3, 9), seed=104, table=env["table"], max_triplets=10, n_noise=2)
+    # cut the first three trajectories down to 0, 1 and 2 observations
+    starts = batch["traj_offset"].astype(np.int64)[:-1]
+    lens = np.diff(batch["traj_offset"].astype(np.int64))
+    lens[0], lens[1], lens[2] = 0, 1, 2
+    sel = np.concatenate([np.arange(starts[t], starts[t] + lens[t]) for t in range(400)]).astype(np.int64)
+    nb = dict(batch)
+    nb["traj_offset"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "mjd_ut1"):
+        nb[k] = np.ascontiguousarray(batch[k][sel])
+    for k in ("helio_equ", "geo_ecl", "body_fixed"):
+        nb[k] = np.ascontiguousarray(batch[k][:, sel])
+    kw = dict(n_noise_realizations=2, max_triplets=10, noise_scale=1.0)
+    got = env["ctx"].fit_full_iod(nb, IODParams.builder(**kw))
+    op = O.default_iod_params(**kw)
+    want = O.fit_full_iod(O.from_soa_batch(nb), env["et"], op, n_threads=0)
+    assert list(want["status"][:3]) == [13, 13, 13]  # NoFeasibleTriplets
+    ef, rf = oracle_floor(O, synth, nb, env["et"], op, want)
+    assert_iod_parity(got, want, ef, rf)
+    assert (want["status"] == 14).any() or (want["status"] == 13).sum() >= 3
+
+
+def test_parity_hard_filters_produce_error_values(env):
+    """Tight acceptability filters drive NoViableOrbit with the reference's cause / attempts."""
+    _, got, want, ef, rf = run_both(env, 300, 12, seed=105, K=10, nn=1, max_ecc=0.05, floor=True)
+    assert_iod_parity(got, want, ef, rf)
+    assert (want["status"] == 14).sum() > 20
+    _, got, want, ef, rf = run_both(env, 200, 12, seed=106, K=5, nn=0, r2_min_au=2.0, r2_max_au=2.2)
+    assert_iod_parity(got, want, ef, rf)
+
+
+def test_parity_rms_window_and_downsampling_parameters(env):
+    """extf / dtmax select the RMS arc (trajectory.rs:294-350); max_obs_for_triplets down-samples
+    (index_generator.rs:66-75) and the un-remapped indices quirk is kept."""
+    _, got, want, ef, rf = run_both(env, 200, (10, 24), seed=107, K=10, nn=0, extf=1.5, dtmax=5.0)
+    assert_iod_parity(got, want, ef, rf)
+    _, got, want, ef, rf = run_both(env, 200, (10, 24), seed=108, K=10, nn=0, max_obs_for_triplets=6)
+    assert_iod_parity(got, want, ef, rf)
+    _, got, want, ef, rf = run_both(env, 100, (10, 24), seed=109, K=10, nn=0, max_obs_for_triplets=3)
+    assert_iod_parity(got, want, ef, rf)
+    _, got, want, ef, rf = run_both(env, 100, 12, seed=110, K=10, nn=0, max_tested_solutions=1)
+    assert_iod_parity(got, want, ef, rf)
+
+
+def test_golden_fixture(env):
+    """Committed oracle output for a fixed small batch (tests/golden/make_iod_golden.py)."""
+    from outfit_b200 import IODParams, RESULT_DTYPE
+    g = np.load(os.path.join(GOLD, "iod_golden.npz"))
+    meta = json.loads(str(g["meta"]))
+    batch = env["synth"].make_trajectories(meta["T"], meta["n_obs"], seed=meta["seed"], table=env["table"],
+                                           max_triplets=meta["K"], n_noise=meta["nn"])
+    got = env["ctx"].fit_full_iod(batch, IODParams.builder(n_noise_realizations=meta["nn"], max_triplets=meta["K"],
+                                                           noise_scale=meta["noise_scale"]))
+    want = np.frombuffer(g["results"].tobytes(), dtype=RESULT_DTYPE)
+    ef, rf = g["elem_floor"], g["rms_floor"]
+    assert_iod_parity(got, want, ef, rf)
+
+
+def test_body_fixed_path_matches_oracle_pvobs(env):
+    """On-device OutfitCache build (pvobs + heliocentric position) vs the oracle's restatement of
+    observer_extension.rs:180-237; then full IOD from body-fixed inputs equals IOD from that cache."""
+    import torch
+    from outfit_b200 import IODParams
+    O, synth = env["O"], env["synth"]
+    batch = synth.make_trajectories(200, 12, seed=111, table=env["table"], max_triplets=10, n_noise=1)
+    n = batch["mjd_tt"].shape[0]
+    geo, hel = np.zeros((3, n)), np.zeros((3, n))
+    for i in range(n):
+        dx, dv, h = O.D3(), O.D3(), O.D3()
+        O.lib().oo_pvobs(batch["mjd_tt"][i], batch["mjd_ut1"][i], O.d3(batch["body_fixed"][:, i]), O.d3([0, 0, 0]), dx, dv)
+        assert O.lib().oo_helio_position(C.byref(env["et"]), batch["mjd_tt"][i], dx, h) == 0
+        geo[:, i], hel[:, i] = list(dx), list(h)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    g_geo = torch.zeros(3, n, dtype=torch.float64, device="cuda")
+    g_hel = torch.zeros_like(g_geo)
+    env["ctx"].observer_cache_device(n, d(batch["mjd_tt"]), d(batch["mjd_ut1"]), d(batch["body_fixed"]), g_geo, g_hel)
+    torch.cuda.synchronize()
+    # geocentric vector ~4e-5 AU: 1e-12 relative; heliocentric ~1 AU: 1e-15 absolute
+    assert np.abs(g_geo.cpu().numpy() - geo).max() <= 1e-12 * 4.3e-5
+    assert np.abs(g_hel.cpu().numpy() - hel).max() <= 4e-16
+    kw = dict(n_noise_realizations=0, max_triplets=10)
+    b2 = dict(batch)
+    b2["geo_ecl"], b2["helio_equ"] = np.ascontiguousarray(geo), np.ascontiguousarray(hel)
+    op = O.default_iod_params(**kw)
+    want = O.fit_full_iod(O.from_soa_batch(b2), env["et"], op, n_threads=0)
+    got = env["ctx"].fit_full_iod(batch, IODParams.builder(**kw), use_body_fixed=True)
+    ef, rf = oracle_floor(O, synth, b2, env["et"], op, want)
+    assert_iod_parity(got, want, ef, rf)
+
+
+def test_device_counters_match_oracle_counters(env):
+    """The event counters that feed the algorithmic-flop figure agree with the oracle's."""
+    from outfit_b200 import IODParams
+    O, synth = env["O"], env["synth"]
+    batch = synth.make_trajectories(300, 12, seed=112, table=env["table"], max_triplets=10, n_noise=2)
+    kw = dict(n_noise_realizations=2, max_triplets=10)
+    env["ctx"].fit_full_iod(batch, IODParams.builder(**kw))
+    g = env["ctx"].last_iod_counters()
+    O.lib().oo_counters_reset()
+    O.fit_full_iod(O.from_soa_batch(batch), env["et"], O.default_iod_params(**kw), n_threads=0)
+    o = O.counters()
+    assert g["gauss_solves"] == o["gauss_solves"] and g["candidates"] == o["gauss_solves"]
+    assert g["aberth_sweeps"] == o["aberth_sweeps"]          # the Aberth sweep is bit-exact
+    assert g["roots_accepted"] == o["roots_accepted"]
+    for a, b in (("fg_iterations", "fg_iterations"), ("kepler_universal_solves", "kepler_universal_solves"),
+                 ("newton_steps", "newton_steps")):
+        assert abs(g[a] - o[b]) <= 2e-3 * o[b], (a, g[a], o[b])
+    # the oracle prunes the arc loop at the running best (trajectory.rs:405-426); the GPU scores
+    # every candidate over its whole arc
+    assert g["scorer_evals"] >= o["scorer_evals"]
+
+
+def test_api_errors(env):
+    from outfit_b200 import IODParams, OutfitB200, OutfitError
+    synth = env["synth"]
+    batch = synth.make_trajectories(8, 12, seed=113, table=env["table"], max_triplets=10, n_noise=1)
+    with pytest.raises(OutfitError):
+        IODParams.builder(r2_min_au=5.0, r2_max_au=1.0)
+    fresh = OutfitB200(0)
+    with pytest.raises(OutfitError) as e:
+        fresh.fit_full_iod(batch, IODParams.builder(n_noise_realizations=0))
+    assert e.value.code == -6  # no ephemeris loaded
+    b2 = dict(batch)
+    b2["noise_z"] = None
+    with pytest.raises(OutfitError):
+        env["ctx"].fit_full_iod(b2, IODParams.builder(n_noise_realizations=3))
+    # out-of-table epochs are reported per observation -> NaN observer -> no viable orbit, no trap
+    b3 = dict(batch)
+    b3["mjd_tt"] = batch["mjd_tt"] + 1.0e5
+    out = env["ctx"].fit_full_iod(b3, IODParams.builder(n_noise_realizations=0))
+    assert (out["status"] != 0).all()
+    # empty batch
+    e = dict(batch)
+    e["traj_offset"] = np.zeros(1, dtype=np.uint64)
+    for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec"):
+        e[k] = np.zeros(0)
+    for k in ("helio_equ", "geo_ecl"):
+        e[k] = np.zeros((3, 0))
+    assert len(env["ctx"].fit_full_iod(e, IODParams.builder(n_noise_realizations=0))) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# bulk propagate_universal
+# ---------------------------------------------------------------------------------------------
+def test_propagate_universal_reference_kats(env):
+    """The reference's own propagate_universal truth cases (propagation.rs:219-887), on the GPU."""
+    from outfit_b200 import SolverType
+    K = json.load(open(os.path.join(GOLD, "reference_kats.json")))["propagate_universal"]["cases"]
+    rv = np.ascontiguousarray(np.array([c["r"] + c["v"] for c in K]).T)
+    t0 = np.array([c["t0"] for c in K])
+    t1 = np.array([c["t1"] for c in K])
+    pg = np.array([c["psi_guess"] if c["psi_guess"] is not None else np.nan for c in K])
+    out, st = env["ctx"].propagate_universal(rv, t0, t1, SolverType(kind=2, convergency=2.220446049250313e-14))
+    assert (st == 0).all()
+    for i, c in enumerate(K):
+        assert np.linalg.norm(out[0:3, i] - np.array(c["r1"])) < c["tol"], c["name"]
+        assert np.linalg.norm(out[3:6, i] - np.array(c["v1"])) < c["tol"], c["name"]
+    # warm start (test_propag4)
+    i = [k for k, c in enumerate(K) if c["psi_guess"] is not None][0]
+    out2, st2 = env["ctx"].propagate_universal(np.ascontiguousarray(rv[:, i:i + 1]), t0[i:i + 1], t1[i:i + 1],
+                                               SolverType(kind=2, convergency=2.220446049250313e-14),
+                                               psi_guess=pg[i:i + 1].copy())
+    assert st2[0] == 0 and np.linalg.norm(out2[0:3, 0] - np.array(K[i]["r1"])) < 1e-9
+    # degenerate state -> DegenerateState value, not a trap (propagation.rs:808-818)
+    z = np.zeros((6, 1)); z[3, 0] = 0.01
+    _, st3 = env["ctx"].propagate_universal(z, np.array([60000.0]), np.array([60001.0]))
+    assert st3[0] == 8
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_propagate_universal_vs_oracle(env, kind):
+    from outfit_b200 import SolverType
+    rv, t0, t1 = env["synth"].make_propagation_states(200_000, seed=7 + kind)
+    st = SolverType(kind=kind)
+    out, status = env["ctx"].propagate_universal(rv, t0, t1, st)
+    want, wst = env["O"].propagate_universal_batch(rv, t0, t1, kind, st.convergency, 0)
+    assert np.array_equal(status, wst)
+    ok = wst == 0
+    assert ok.mean() > 0.99
+    scale_r = np.linalg.norm(want[0:3, ok], axis=0)
+    scale_v = np.linalg.norm(want[3:6, ok], axis=0)
+    # tolerance 1e-9 relative to |r1|, |v1| (the reference's own tolerance for this routine is
+    # 1e-9 / 1e-8 absolute, propagation.rs:245-262); typical agreement is ~1e-13
+    assert (np.linalg.norm(out[0:3, ok] - want[0:3, ok], axis=0) <= 1e-9 * scale_r).all()
+    assert (np.linalg.norm(out[3:6, ok] - want[3:6, ok], axis=0) <= 1e-9 * scale_v).all()
+    assert np.median(np.linalg.norm(out[0:3, ok] - want[0:3, ok], axis=0) / scale_r) < 1e-13
+
+
+def test_propagate_universal_full_size_properties(env):
+    """BASELINE configs[1] size (10 M): Lagrange identity f*gdot - fdot*g = 1, conservation of
+    energy and angular momentum, and forward/backward round trip (propagation.rs:1002-1198)."""
+    import torch
+    from outfit_b200 import SolverType
+    n = 10_000_000
+    rv, t0, t1 = env["synth"].make_propagation_states(n, seed=99)
+    dev = torch.device("cuda")
+    d_rv, d_t0, d_t1 = (torch.from_numpy(x).to(dev) for x in (rv, t0, t1))
+    d_o = torch.empty(11, n, dtype=torch.float64, device=dev)
+    d_s = torch.empty(n, dtype=torch.int32, device=dev)
+    env["ctx"].propagate_universal_device(n, d_rv, d_t0, d_t1, d_o, d_s, SolverType(kind=2))
+    torch.cuda.synchronize()
+    ok = d_s == 0
+    assert ok.double().mean().item() > 0.999
+    f, g, fd, gd = d_o[6][ok], d_o[7][ok], d_o[8][ok], d_o[9][ok]
+    ident = (f * gd - fd * g - 1.0).abs()
+    assert ident.max().item() < 1e-6 and ident.median().item() < 1e-13
+    mu = 0.01720209895 ** 2
+    r0, v0 = d_rv[0:3][:, ok], d_rv[3:6][:, ok]
+    r1, v1 = d_o[0:3][:, ok], d_o[3:6][:, ok]
+    en0 = 0.5 * (v0 * v0).sum(0) - mu / r0.norm(dim=0)
+    en1 = 0.5 * (v1 * v1).sum(0) - mu / r1.norm(dim=0)
+    rel_e = ((en1 - en0).abs() / en0.abs().clamp_min(1e-12))
+    assert rel_e.median().item() < 1e-12 and torch.quantile(rel_e[:1_000_000], 0.999).item() < 1e-6
+    h0 = torch.linalg.cross(r0.T, v0.T)
+    h1 = torch.linalg.cross(r1.T, v1.T)
+    rel_h = (h1 - h0).norm(dim=1) / h0.norm(dim=1)
+    assert rel_h.median().item() < 1e-13
+    # round trip
+    d_b = torch.empty(11, n, dtype=torch.float64, device=dev)
+    d_sb = torch.empty(n, dtype=torch.int32, device=dev)
+    state1 = d_o[0:6].contiguous()
+    env["ctx"].propagate_universal_device(n, state1, d_t1, d_t0, d_b, d_sb, SolverType(kind=2))
+    torch.cuda.synchronize()
+    both = ok & (d_sb == 0)
+    back = (d_b[0:3][:, both] - d_rv[0:3][:, both]).norm(dim=0) / d_rv[0:3][:, both].norm(dim=0)
+    assert back.median().item() < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties of the IOD path (BASELINE configs[2]: 100 k x 12)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties_100k(env):
+    """Idempotence (bitwise), independence from batch composition (= the multi-GPU sharding
+    property: a shard gives the same bits as the whole), and agreement with the oracle on a sample."""
+    from outfit_b200 import IODParams, shard
+    synth, O = env["synth"], env["O"]
+    T, K, nn = 100_000, 30, 2
+    batch = synth.make_trajectories(T, 12, seed=2026, table=env["table"], max_triplets=K, n_noise=nn)
+    params = IODParams.builder(n_noise_realizations=nn, max_triplets=K, noise_scale=1.1)
+    a = env["ctx"].fit_full_iod(batch, params)
+    b = env["ctx"].fit_full_iod(batch, params)
+    assert a.tobytes() == b.tobytes()
+    lo, hi = 37_123, 61_007
+    part = env["ctx"].fit_full_iod(shard.slice_batch(batch, lo, hi), params)
+    assert part.tobytes() == a[lo:hi].tobytes()
+    assert (a["status"] == 0).mean() > 0.9
+    ok = a["status"] == 0
+    assert np.isfinite(a["rms"][ok]).all() and (a["rms"][ok] > 0).all()
+    assert (a["triplet_idx"][ok, 0] < a["triplet_idx"][ok, 1]).all() and (a["triplet_idx"][ok, 1] < a["triplet_idx"][ok, 2]).all()
+    sl = shard.slice_batch(batch, 5000, 5400)
+    op = O.default_iod_params(n_noise_realizations=nn, max_triplets=K, noise_scale=1.1)
+    want = O.fit_full_iod(O.from_soa_batch(sl), env["et"], op, n_threads=0)
+    ef, rf = oracle_floor(O, synth, sl, env["et"], op, want)
+    assert_iod_parity(a[5000:5400], want, ef, rf)

@@ -54,11 +54,11 @@ for (T, nobs, K, nn, seed) in [(512, 12, 10, 0, 1), (512, 12, 30, 10, 2), (256, 
     params = IODParams.builder(**kw)
     t0 = time.time(); got = ctx.fit_full_iod(batch, params); t1 = time.time()
     got = ctx.fit_full_iod(batch, params); t2 = time.time()
-    want = O.fit_full_iod(synth.to_oracle_batch(batch), et, O.default_iod_params(**kw), n_threads=0); t3 = time.time()
+    want = O.fit_full_iod(O.from_soa_batch(batch), et, O.default_iod_params(**kw), n_threads=0); t3 = time.time()
     print(f"T={T} nobs={nobs} K={K} nn={nn}: gpu first {t1-t0:.3f}s second {t2-t1:.3f}s ({T/(t2-t1):.0f} traj/s) cpu {t3-t2:.3f}s ({T/(t3-t2):.0f} traj/s)")
     compare(got, want, f"K{K}n{nn}")
     # conditioning floor: the oracle against itself with RA/Dec moved by one ulp
-    ob = synth.to_oracle_batch(batch)
+    ob = O.from_soa_batch(batch)
     ob["ra"] = np.nextafter(ob["ra"], np.inf); ob["dec"] = np.nextafter(ob["dec"], -np.inf)
     pert = O.fit_full_iod(ob, et, O.default_iod_params(**kw), n_threads=0)
     print("   -- oracle vs oracle(+1ulp inputs):")

@@ -11,7 +11,7 @@ for K, nn in [(30, 0), (30, 1), (10, 3), (11, 2), (30, 10)]:
     batch = synth.make_trajectories(64, 12, seed=2, table=table, max_triplets=K, n_noise=max(nn, 1))
     kw = dict(n_noise_realizations=nn, max_triplets=K, noise_scale=1.1)
     got = ctx.fit_full_iod(batch, IODParams.builder(**kw))
-    want = O.fit_full_iod(synth.to_oracle_batch(batch), et, O.default_iod_params(**kw), n_threads=0)
+    want = O.fit_full_iod(O.from_soa_batch(batch), et, O.default_iod_params(**kw), n_threads=0)
     ok = (got["status"] == 0) & (want["status"] == 0)
     d = np.abs(got["elem"] - want["elem"]).max(axis=1)
     bad = np.where(ok & (d > 1e-6))[0]
