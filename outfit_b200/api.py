@@ -32,7 +32,8 @@ class OutfitError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "liboutfit_b200.so")
+    # OUTFIT_B200_LIB lets a developer A/B a differently built copy of the SAME library
+    return os.environ.get("OUTFIT_B200_LIB") or os.path.join(_HERE, "liboutfit_b200.so")
 
 
 class IODParams(C.Structure):

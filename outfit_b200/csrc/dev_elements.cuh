@@ -90,7 +90,7 @@ struct Equinoctial {
   double epoch, a, h, k, p, q, lambda;
 };
 // returns 0 or OUTFIT_ST_INVALID_CONVERSION (9) / OUTFIT_ST_INVALID_ORBIT (10)
-__device__ __forceinline__ int to_equinoctial(const Orbit &o, Equinoctial &q) {
+__device__ __noinline__ int to_equinoctial(const Orbit &o, Equinoctial &q) {
   double a = o.e[0], e = o.e[1], m = o.e[5];
   if (o.kind != 0) {
     if (fabs(e - 1.0) < 1e-12) return 9;
@@ -125,7 +125,7 @@ struct ScoreOrbit {
   V3 F, G;             // equinoctial frame vectors rotated to equatorial J2000
   bool elliptic;
 };
-__device__ __forceinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
+__device__ __noinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
   ScoreOrbit s;
   const double e2 = q.h * q.h + q.k * q.k;
   s.elliptic = !(sqrt(e2) >= 1.0);
@@ -145,7 +145,7 @@ __device__ __forceinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
 }
 
 // Normalised squared residual of one observation; false <=> the reference returns Err.
-__device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_obs, double ra_obs,
+__device__ __noinline__ bool ephemeris_error(const ScoreOrbit &s, double t_obs, double ra_obs,
                                                 double dec_obs, double cos_dec_obs, double sig_ra,
                                                 double sig_dec, V3 obs_equ, double &chi2, Work &w) {
   ++w.scorer_evals;
@@ -156,9 +156,11 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   double x = kPi + s.lon_peri;
   double sF, cF;
   int iter = 0;
+  bool last = false;
   for (;;) {
+    sincos(x, &sF, &cF);  // the only sincos site: also evaluates at the accepted root
+    if (last) break;
     ++w.scorer_newton;
-    sincos(x, &sF, &cF);
     const double f = x - s.k * sF + s.h * cF - lam1;
     const double d = 1.0 - s.k * cF - s.h * sF;
     if (fabs(f) < eps) break;
@@ -167,8 +169,9 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
       return false;
     }
     const double x1 = x - f / d;
-    if (fabs(x - x1) < eps) { x = x1; sincos(x, &sF, &cF); break; }
+    const bool conv = fabs(x - x1) < eps;
     x = x1;
+    if (conv) { last = true; continue; }
     if (++iter >= 25) return false;
   }
   const double xe = s.a * (s.ch * cF + s.bhk * sF - s.k);

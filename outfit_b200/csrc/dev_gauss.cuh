@@ -80,9 +80,11 @@ __device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6
   dp = d;
 }
 
-// returns 0 converged / 1 max-iter / 2 failed; roots in zr/zi (index order k)
+// returns 0 converged / 1 max-iter / 2 failed.  The 8 iterates live in shared memory, lane-strided
+// (z[k * 32 + lane]: conflict-free), so that the sweep can be a ROLLED loop: the instruction footprint
+// of the unrolled 8x8 version thrashed the instruction cache (ncu r01a: 73 % stall_no_inst).
 __device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned max_iter, double eps,
-                                    double (&zr)[8], double (&zi)[8], Work &w) {
+                                    double *__restrict__ zr, double *__restrict__ zi, Work &w) {
   // Cauchy-type start radius: smallest integer r0 with S(r0) > 0, S(w) = w^8 - |c6| w^6 - |c3| w^3 - |c0|
   const double s0 = -fabs(c0), s3 = -fabs(c3), s6 = -fabs(c6);
   double r0 = 1.0;
@@ -100,26 +102,26 @@ __device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned ma
     if (r > 0.0) break;
     r0 += 1.0;
   }
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) {
-    zr[k] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
-    zi[k] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
+    zr[k * 32] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
+    zi[k * 32] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
   }
   for (unsigned it = 0; it < max_iter; ++it) {
     ++w.aberth_sweeps;
-    double nr[8], ni[8];
+    double nr[8], ni[8];  // Jacobi: the sweep reads only the previous iterates
     bool converged = true;
     bool failed = false;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-      const Cx z = Cx{zr[i], zi[i]};
+      const Cx z = Cx{zr[i * 32], zi[i * 32]};
       Cx p, dp;
       poly8_eval(z, c0, c3, c6, p, dp);
       Cx sum = Cx{0.0, 0.0};
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; ++k) {
         if (k == i) continue;
-        sum = cx_add(sum, cx_recip(cx_sub(z, Cx{zr[k], zi[k]})));
+        sum = cx_add(sum, cx_recip(cx_sub(z, Cx{zr[k * 32], zi[k * 32]})));
       }
       const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, sum), dp)));
       nr[i] = nz.re;
@@ -128,8 +130,8 @@ __device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned ma
       if (!(fabs(__dsub_rn(nz.re, z.re)) < eps && fabs(__dsub_rn(nz.im, z.im)) < eps)) converged = false;
     }
     if (failed) return 2;  // the caller maps it to PolynomialRootFindingFailed
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { zr[i] = nr[i]; zi[i] = ni[i]; }
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) { zr[i * 32] = nr[i]; zi[i * 32] = ni[i]; }
     if (converged) return 0;
   }
   return 1;
@@ -154,7 +156,7 @@ struct GaussGeom {
 };
 
 // R*c with nalgebra's accumulation order, then rho, positions and light-time epoch (gauss.rs:702)
-__device__ __forceinline__ bool positions_from_c(const Triplet &g, const GaussGeom &gm, double c0,
+__device__ __noinline__ bool positions_from_c(const Triplet &g, const GaussGeom &gm, double c0,
                                                  double c1, double c2, double min_rho2, V3 (&pos)[3],
                                                  double &epoch) {
   const V3 gc = V3{(g.R[0].x * c0 + g.R[1].x * c1) + g.R[2].x * c2,
@@ -185,7 +187,7 @@ __device__ __forceinline__ V3 gibbs_velocity(const V3 (&pos)[3], double tau1, do
 }
 
 // Iterative two-sided Lagrange f-g refinement (gauss.rs:1284-1418).  Returns false <=> None.
-__device__ __forceinline__ bool pos_and_vel_correction(const Triplet &g, const GaussGeom &gm,
+__device__ __noinline__ bool pos_and_vel_correction(const Triplet &g, const GaussGeom &gm,
                                                        const IodDevParams &P, V3 (&pos)[3], V3 &vel,
                                                        double &epoch, Work &w) {
   const double dt01 = g.t[0] - g.t[1], dt21 = g.t[2] - g.t[1];

@@ -20,6 +20,7 @@ struct TrajSmem {
   unsigned short *trip;  // [max_triplets][4] : i, j, k, pad
   double *heap_w;        // [max_triplets] best-K heap: weights
   unsigned *heap_x;      // [max_triplets] best-K heap: packed (i<<20 | j<<10 | k)
+  double *zr, *zi;       // [8][32] Aberth iterates, lane-strided (this lane's base already applied)
 };
 constexpr int kObsPlanes = 12;
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ void heap_sift_down_to_bottom(double *hw, unsigned *h
   heap_sift_up(hw, hx, pos);
 }
 
-__device__ __forceinline__ unsigned select_triplets(const TrajSmem &sm, unsigned n_obs,
+__device__ __noinline__ unsigned select_triplets(const TrajSmem &sm, unsigned n_obs,
                                                     const IodDevParams &P, unsigned lane) {
   if (P.max_triplets == 0 || n_obs < 3) return 0;
   const unsigned nr = P.max_obs_for_triplets >= n_obs ? n_obs : (P.max_obs_for_triplets <= 3 ? 3u : P.max_obs_for_triplets);
@@ -158,7 +159,7 @@ __device__ __forceinline__ unsigned select_triplets(const TrajSmem &sm, unsigned
 
 // ---- one candidate: Gauss solve -> orbit (prelim_orbit, gauss.rs:1238) ------------------------
 // returns 0 or an OUTFIT_ST_* error code
-__device__ __forceinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i0, unsigned i1, unsigned i2,
+__device__ __noinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i0, unsigned i1, unsigned i2,
                                                   const double (&ra)[3], const double (&dec)[3],
                                                   const IodDevParams &P, Orbit &out, Work &w) {
   ++w.gauss_solves;
@@ -225,7 +226,7 @@ __device__ __forceinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i
     }
     if (count == 0) return 2;
   }
-  double zr[8], zi[8];
+  double *zr = sm.zr, *zi = sm.zi;
   if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) return 3;
 
   // roots in solver order -> accept -> correct -> first Corrected, else first pushed
@@ -233,8 +234,8 @@ __device__ __forceinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i
   unsigned n_solutions = 0;
 #pragma unroll 1
   for (int kroot = 0; kroot < 8; ++kroot) {
-    const double r2 = zr[kroot];
-    if (!(r2 > 0.0 && fabs(zi[kroot]) < P.root_imag_eps)) continue;
+    const double r2 = zr[kroot * 32];
+    if (!(r2 > 0.0 && fabs(zi[kroot * 32]) < P.root_imag_eps)) continue;
     if (!(r2 >= P.r2_min_au && r2 <= P.r2_max_au)) continue;
     // accept_root (gauss.rs:816-870)
     const double r2m3 = 1.0 / ((r2 * r2) * r2);

@@ -41,14 +41,18 @@ struct CandScore {
 };
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef OUTFIT_BLOCKS_PER_SM
+#define OUTFIT_BLOCKS_PER_SM 4
+#endif
+constexpr int kBlocksPerSm = OUTFIT_BLOCKS_PER_SM;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm)
 iod_kernel(IodBatchDev B, IodDevParams P, OutfitIodResult *__restrict__ out, unsigned n_obs_cap,
            unsigned long long *__restrict__ traj_counter, unsigned long long *__restrict__ work_counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
-  const size_t per_warp = (size_t)kObsPlanes * n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8);
+  const size_t per_warp = (size_t)kObsPlanes * n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8) + 16 * 32 * sizeof(double);
   const size_t per_warp_al = (per_warp + 15) & ~(size_t)15;
   unsigned char *base = smem_raw + warp * per_warp_al;
   TrajSmem sm;
@@ -58,7 +62,9 @@ iod_kernel(IodBatchDev B, IodDevParams P, OutfitIodResult *__restrict__ out, uns
     sm.sdec = d + 4 * n_obs_cap; sm.cosdec = d + 5 * n_obs_cap;
     sm.hx = d + 6 * n_obs_cap; sm.hy = d + 7 * n_obs_cap; sm.hz = d + 8 * n_obs_cap;
     sm.ox = d + 9 * n_obs_cap; sm.oy = d + 10 * n_obs_cap; sm.oz = d + 11 * n_obs_cap;
-    sm.heap_w = d + (size_t)kObsPlanes * n_obs_cap;
+    sm.zr = d + (size_t)kObsPlanes * n_obs_cap + lane;
+    sm.zi = sm.zr + 8 * 32;
+    sm.heap_w = d + (size_t)kObsPlanes * n_obs_cap + 16 * 32;
     sm.heap_x = reinterpret_cast<unsigned *>(sm.heap_w + P.max_triplets);
     sm.trip = reinterpret_cast<unsigned short *>(sm.heap_x + P.max_triplets);
   }
@@ -557,7 +563,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   B.helio = d_helio; B.scorer = d_scorer; B.noise_z = b->noise_z;
   const IodDevParams P = to_dev_params(*params);
   const unsigned cap = max_obs < 3 ? 4 : ((max_obs + 1) & ~1u);
-  size_t per_warp = (size_t)kObsPlanes * cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8);
+  size_t per_warp = (size_t)kObsPlanes * cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8) + 16 * 32 * sizeof(double);
   per_warp = (per_warp + 15) & ~(size_t)15;
   const size_t smem = per_warp * kWarpsPerBlock;
   if (smem > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");

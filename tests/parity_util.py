@@ -55,7 +55,9 @@ def assert_iod_parity(got, want, elem_floor=None, rms_floor=None, min_plain_frac
         return dict(n_ok=0)
     ee = elem_err(got["elem"][ok], want["elem"][ok])
     er = np.abs(got["rms"][ok] - want["rms"][ok]) / np.maximum(np.abs(want["rms"][ok]), 1e-300)
-    ep = np.abs(got["epoch"][ok] - want["epoch"][ok]) / np.abs(want["epoch"][ok])
+    # absolute, in days (light-time corrected epoch; it is 0.0 when no f-g iteration ever committed,
+    # gauss.rs:1299,1417 -- reference behaviour)
+    ep = np.abs(got["epoch"][ok] - want["epoch"][ok])
     etol = np.full(ok.sum(), ELEM_TOL)
     rtol = np.full(ok.sum(), RMS_TOL)
     if elem_floor is not None:
@@ -63,7 +65,12 @@ def assert_iod_parity(got, want, elem_floor=None, rms_floor=None, min_plain_frac
         rtol = np.maximum(rtol, FLOOR_FACTOR * rms_floor[ok])
     assert (ee <= etol).all(), f"element error {ee.max():.3e} beyond tolerance on {np.argwhere(ee > etol)[:5].ravel()}"
     assert (er <= rtol).all(), f"rms error {er.max():.3e} beyond tolerance"
-    assert (ep <= 1e-13).all(), f"epoch error {ep.max():.3e}"
+    # trajectories whose ORACLE answer is itself discontinuous under a 1-ulp move of the inputs
+    # (floor = inf: a different branch, e.g. an f-g loop that never commits) only have to agree on
+    # the integer / index fields; they must stay rare
+    chaotic = np.zeros(ok.sum(), dtype=bool) if elem_floor is None else ~np.isfinite(elem_floor[ok])
+    assert chaotic.mean() <= 0.02, chaotic.mean()
+    assert (ep[~chaotic] <= 1e-8).all(), f"epoch error {ep[~chaotic].max():.3e} d"
     if min_plain_fraction is not None:
         assert (ee <= ELEM_TOL).mean() >= min_plain_fraction, (ee <= ELEM_TOL).mean()
         assert (er <= RMS_TOL).mean() >= min_plain_fraction, (er <= RMS_TOL).mean()

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Dev script: device-resident throughput of the c3 workload + a parity spot check."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from outfit_b200 import IODParams, OutfitB200, RESULT_DTYPE, synth, shard
+T = int(os.environ.get("PERF_T", "100000")); K, nn = 30, 10
+nobs = 12 if os.environ.get("PERF_RAGGED") is None else (8, 30)
+table = synth.make_ephemeris_table()
+batch = synth.make_trajectories(T, nobs, seed=20261018, table=table, max_triplets=K, n_noise=nn)
+ctx = OutfitB200(0); ctx.load_ephemeris(table)
+kw = dict(n_noise_realizations=nn, noise_scale=1.1, max_triplets=K)
+params = IODParams.builder(**kw)
+dev = torch.device("cuda")
+keys = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "noise_z"]
+devb = {k: torch.from_numpy(batch[k].view(np.int64) if batch[k].dtype == np.uint64 else batch[k]).to(dev) for k in keys}
+devb["max_obs_per_traj"] = int(np.diff(batch["traj_offset"].astype(np.int64)).max())
+d_out = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+s = torch.cuda.current_stream().cuda_stream
+ctx.fit_full_iod_device(devb, params, d_out, stream=s); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(2): ctx.fit_full_iod_device(devb, params, d_out, stream=s)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 2
+res = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+print(f"LIB={os.environ.get('OUTFIT_B200_LIB','default')} T={T} {ms:.1f} ms  {T/ms*1e3:.0f} traj/s  ok={np.mean(res['status']==0):.4f}")
+if os.environ.get("PERF_PARITY", "1") == "1":
+    from oracle import binding as O
+    et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    n = 400
+    want = O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, n)), et, O.default_iod_params(**kw), n_threads=0)
+    got = res[:n]
+    ints = all(np.array_equal(got[f], want[f]) for f in ("status", "cause", "attempts", "corrected", "element_kind", "triplet_idx", "realization"))
+    ok = want["status"] == 0
+    rel = np.abs(got["elem"][ok] - want["elem"][ok]) / np.maximum(np.abs(want["elem"][ok]), 1e-3)
+    rr = np.abs(got["rms"][ok] - want["rms"][ok]) / want["rms"][ok]
+    print(f"   parity(400): int fields equal={ints} elem rel p50={np.median(rel.max(axis=1)):.2e} max={rel.max():.2e} rms rel p50={np.median(rr):.2e} max={rr.max():.2e}")
