@@ -1,5 +1,5 @@
-// dev_iod.cuh -- one warp per trajectory: triplet selection, one lane per (triplet, realization)
-// candidate, warp-level best-orbit selection.
+// dev_iod.cuh -- building blocks of the full-IOD pipeline: warp-per-trajectory triplet selection,
+// and the per-candidate (one lane per (triplet, realization)) Gauss geometry / polynomial / root solve.
 //
 // Reference behaviour:
 //   generate_triplets / best-K       triplet_generation/mod.rs:229-440, index_generator.rs:66-271
@@ -14,15 +14,10 @@ namespace ofb {
 
 // ---- per-warp shared-memory view of one trajectory ------------------------------------------
 struct TrajSmem {
-  double *t, *ra, *dec, *sra, *sdec, *cosdec;
-  double *hx, *hy, *hz;  // OutfitCache helio position (equatorial J2000)
-  double *ox, *oy, *oz;  // scorer observer position (observation_ephemeris.rs:303-318)
-  unsigned short *trip;  // [max_triplets][4] : i, j, k, pad
+  double *t;             // [n_obs] observation epochs of the trajectory
   double *heap_w;        // [max_triplets] best-K heap: weights
   unsigned *heap_x;      // [max_triplets] best-K heap: packed (i<<20 | j<<10 | k)
-  double *zr, *zi;       // [8][32] Aberth iterates, lane-strided (this lane's base already applied)
 };
-constexpr int kObsPlanes = 12;
 
 __device__ __forceinline__ unsigned keep_index(unsigned i, unsigned n, unsigned max_keep) {
   // downsample_uniform_with_edges (index_generator.rs:66-75)
@@ -42,7 +37,7 @@ __device__ __forceinline__ double s_gap(double dt, double inv_dtw) {
 // fed IN ORDER to a std::collections::BinaryHeap replica (push = sift_up; pop = swap-last +
 // sift_down_to_bottom + sift_up; replacement only on strict `<`, mod.rs:386-401), followed by the
 // stable insertion sort `sort_unstable_by` performs on short slices (mod.rs:405-407).
-// Returns the number found (warp-uniform); writes them (ascending) to sm.trip.
+// Returns the number found (warp-uniform); leaves them, ascending, packed in sm.heap_x.
 __device__ __forceinline__ bool heap_le(double wa, double wb) { return !(wa > wb); }  // a <= b by weight
 __device__ __forceinline__ void heap_sift_up(double *hw, unsigned *hx, unsigned pos) {
   const double w = hw[pos];
@@ -147,29 +142,14 @@ __device__ __noinline__ unsigned select_triplets(const TrajSmem &sm, unsigned n_
       while (b > 0 && w < hw[b - 1]) { hw[b] = hw[b - 1]; hx[b] = hx[b - 1]; --b; }
       hw[b] = w; hx[b] = x;
     }
-    for (unsigned a = 0; a < heap_len; ++a) {
-      sm.trip[4 * a + 0] = (unsigned short)(hx[a] >> 20);
-      sm.trip[4 * a + 1] = (unsigned short)((hx[a] >> 10) & 1023u);
-      sm.trip[4 * a + 2] = (unsigned short)(hx[a] & 1023u);
-    }
   }
   __syncwarp();
   return heap_len;
 }
 
-// ---- one candidate: Gauss solve -> orbit (prelim_orbit, gauss.rs:1238) ------------------------
-// returns 0 or an OUTFIT_ST_* error code
-__device__ __noinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i0, unsigned i1, unsigned i2,
-                                                  const double (&ra)[3], const double (&dec)[3],
-                                                  const IodDevParams &P, Orbit &out, Work &w) {
-  ++w.gauss_solves;
-  Triplet g;
-  g.t[0] = sm.t[i0]; g.t[1] = sm.t[i1]; g.t[2] = sm.t[i2];
-  g.R[0] = V3{sm.hx[i0], sm.hy[i0], sm.hz[i0]};
-  g.R[1] = V3{sm.hx[i1], sm.hy[i1], sm.hz[i1]};
-  g.R[2] = V3{sm.hx[i2], sm.hy[i2], sm.hz[i2]};
-  GaussGeom gm;
-  // gauss_prelim (gauss.rs:532-549)
+// ---- candidate geometry: gauss_prelim + unit matrix + cofactor inverse (gauss.rs:464-549) -------
+// false <=> SingularDirectionMatrix
+__device__ __noinline__ bool gauss_geometry(const Triplet &g, GaussGeom &gm) {
   gm.tau1 = kGaussK * (g.t[0] - g.t[1]);
   gm.tau3 = kGaussK * (g.t[2] - g.t[1]);
   const double tau13 = gm.tau3 - gm.tau1;
@@ -177,95 +157,75 @@ __device__ __noinline__ int gauss_prelim_orbit(const TrajSmem &sm, unsigned i0, 
   gm.a2 = -(gm.tau1 / tau13);
   gm.b0 = gm.a0 * (tau13 * tau13 - gm.tau3 * gm.tau3) / 6.0;
   gm.b2 = gm.a2 * (tau13 * tau13 - gm.tau1 * gm.tau1) / 6.0;
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     double sr, cr, sd, cd;
-    sincos(ra[c], &sr, &cr);
-    sincos(dec[c], &sd, &cd);
+    sincos(g.ra[c], &sr, &cr);
+    sincos(g.dec[c], &sd, &cd);
     gm.S[c] = V3{cr * cd, sr * cd, sd};
   }
-  {  // cofactor inverse (nalgebra try_inverse, dim 3); rows of the inverse
-    const double m11 = gm.S[0].x, m12 = gm.S[1].x, m13 = gm.S[2].x;
-    const double m21 = gm.S[0].y, m22 = gm.S[1].y, m23 = gm.S[2].y;
-    const double m31 = gm.S[0].z, m32 = gm.S[1].z, m33 = gm.S[2].z;
-    const double mi1 = m22 * m33 - m32 * m23;
-    const double mi2 = m21 * m33 - m31 * m23;
-    const double mi3 = m21 * m32 - m31 * m22;
-    const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;
-    if (det == 0.0) return 1;
-    gm.SiR[0] = V3{mi1 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det};
-    gm.SiR[1] = V3{-mi2 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det};
-    gm.SiR[2] = V3{mi3 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det};
-  }
-  // coeff_eight_poly (gauss.rs:585-614)
-  double c6, c3, c0;
-  {
-    const V3 ra_v = V3{(g.R[0].x * gm.a0 + g.R[1].x * -1.0) + g.R[2].x * gm.a2,
-                       (g.R[0].y * gm.a0 + g.R[1].y * -1.0) + g.R[2].y * gm.a2,
-                       (g.R[0].z * gm.a0 + g.R[1].z * -1.0) + g.R[2].z * gm.a2};
-    const V3 rb_v = V3{(g.R[0].x * gm.b0 + g.R[1].x * 0.0) + g.R[2].x * gm.b2,
-                       (g.R[0].y * gm.b0 + g.R[1].y * 0.0) + g.R[2].y * gm.b2,
-                       (g.R[0].z * gm.b0 + g.R[1].z * 0.0) + g.R[2].z * gm.b2};
-    const double a2s = dot(gm.SiR[1], ra_v);
-    const double b2s = dot(gm.SiR[1], rb_v);
-    const double r22 = dot(g.R[1], g.R[1]);
-    const double s2r2 = dot(gm.S[1], g.R[1]);
-    c6 = -(a2s * a2s) - r22 - (2.0 * a2s * s2r2);
-    c3 = -(2.0 * b2s * (a2s + s2r2));
-    c0 = -(b2s * b2s);
-  }
-  {  // Descartes prefilter (gauss.rs:214-240): no sign change <=> no positive real root
-    int last = 1, count = 0;
-    const double cs[3] = {c6, c3, c0};
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int cur = cs[q] == 0.0 ? 0 : (signbit(cs[q]) ? -1 : 1);
-      if (cur == 0) continue;
-      if (cur != last) ++count;
-      last = cur;
-    }
-    if (count == 0) return 2;
-  }
-  double *zr = sm.zr, *zi = sm.zi;
-  if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) return 3;
+  const double m11 = gm.S[0].x, m12 = gm.S[1].x, m13 = gm.S[2].x;
+  const double m21 = gm.S[0].y, m22 = gm.S[1].y, m23 = gm.S[2].y;
+  const double m31 = gm.S[0].z, m32 = gm.S[1].z, m33 = gm.S[2].z;
+  const double mi1 = m22 * m33 - m32 * m23;
+  const double mi2 = m21 * m33 - m31 * m23;
+  const double mi3 = m21 * m32 - m31 * m22;
+  const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;
+  if (det == 0.0) return false;
+  gm.SiR[0] = V3{mi1 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det};
+  gm.SiR[1] = V3{-mi2 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det};
+  gm.SiR[2] = V3{mi3 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det};
+  return true;
+}
 
-  // roots in solver order -> accept -> correct -> first Corrected, else first pushed
-  bool have_first = false;
-  unsigned n_solutions = 0;
-#pragma unroll 1
-  for (int kroot = 0; kroot < 8; ++kroot) {
-    const double r2 = zr[kroot * 32];
-    if (!(r2 > 0.0 && fabs(zi[kroot * 32]) < P.root_imag_eps)) continue;
-    if (!(r2 >= P.r2_min_au && r2 <= P.r2_max_au)) continue;
-    // accept_root (gauss.rs:816-870)
-    const double r2m3 = 1.0 / ((r2 * r2) * r2);
-    V3 pos[3];
-    double epoch;
-    if (!positions_from_c(g, gm, gm.a0 + gm.b0 * r2m3, -1.0, gm.a2 + gm.b2 * r2m3, P.min_rho2_au, pos, epoch))
-      continue;
-    V3 vel = gibbs_velocity(pos, gm.tau1, gm.tau3);
-    {
-      const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
-      if (!ec.defined || !ec.accepted) continue;
-    }
-    ++w.roots_accepted;
-    V3 cpos[3] = {pos[0], pos[1], pos[2]};
-    V3 cvel = vel;
-    double cepoch;
-    const bool corrected = pos_and_vel_correction(g, gm, P, cpos, cvel, cepoch, w);
-    ++n_solutions;
-    if (corrected || !have_first) {
-      // build_result (gauss.rs:1063): rotate to ecliptic J2000, state -> elements
-      const V3 rr = corrected ? cpos[1] : pos[1];
-      const V3 vv = corrected ? cvel : vel;
-      ccek1(equ_to_ecl(rr), equ_to_ecl(vv), corrected ? cepoch : epoch, out);
-      out.corrected = corrected ? 1 : 0;
-      have_first = true;
-      if (corrected) return 0;  // first CorrectedOrbit in discovery order wins (gauss.rs:1240-1245)
-    }
-    if (n_solutions >= P.max_tested_solutions) break;
+// coeff_eight_poly (gauss.rs:585-614) + Descartes prefilter (gauss.rs:214-240).
+// false <=> no sign change <=> no positive real root (GaussNoRootsFound)
+__device__ __forceinline__ bool gauss_polynomial(const Triplet &g, const GaussGeom &gm, double &c0, double &c3,
+                                                 double &c6) {
+  const V3 ra_v = V3{(g.R[0].x * gm.a0 + g.R[1].x * -1.0) + g.R[2].x * gm.a2,
+                     (g.R[0].y * gm.a0 + g.R[1].y * -1.0) + g.R[2].y * gm.a2,
+                     (g.R[0].z * gm.a0 + g.R[1].z * -1.0) + g.R[2].z * gm.a2};
+  const V3 rb_v = V3{(g.R[0].x * gm.b0 + g.R[1].x * 0.0) + g.R[2].x * gm.b2,
+                     (g.R[0].y * gm.b0 + g.R[1].y * 0.0) + g.R[2].y * gm.b2,
+                     (g.R[0].z * gm.b0 + g.R[1].z * 0.0) + g.R[2].z * gm.b2};
+  const double a2s = dot(gm.SiR[1], ra_v);
+  const double b2s = dot(gm.SiR[1], rb_v);
+  const double r22 = dot(g.R[1], g.R[1]);
+  const double s2r2 = dot(gm.S[1], g.R[1]);
+  c6 = -(a2s * a2s) - r22 - (2.0 * a2s * s2r2);
+  c3 = -(2.0 * b2s * (a2s + s2r2));
+  c0 = -(b2s * b2s);
+  int last = 1, count = 0;
+  const double cs[3] = {c6, c3, c0};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int cur = cs[q] == 0.0 ? 0 : (signbit(cs[q]) ? -1 : 1);
+    if (cur == 0) continue;
+    if (cur != last) ++count;
+    last = cur;
   }
-  return have_first ? 0 : 2;
+  return count != 0;
+}
+
+// One admissible root -> accept_root (gauss.rs:816-870) -> f-g correction (gauss.rs:1284).
+// returns 0 rejected, 1 PrelimOrbit state, 2 CorrectedOrbit state; state = r(t2), v(t2), epoch
+__device__ __forceinline__ int solve_root(const Triplet &g, const GaussGeom &gm, const IodDevParams &P, double r2,
+                                          V3 &r_out, V3 &v_out, double &epoch_out, Work &w) {
+  const double r2m3 = 1.0 / ((r2 * r2) * r2);
+  V3 pos[3];
+  double epoch;
+  if (!positions_from_c(g, gm, gm.a0 + gm.b0 * r2m3, -1.0, gm.a2 + gm.b2 * r2m3, P.min_rho2_au, pos, epoch)) return 0;
+  V3 vel = gibbs_velocity(pos, gm.tau1, gm.tau3);
+  {
+    const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
+    if (!ec.defined || !ec.accepted) return 0;
+  }
+  ++w.roots_accepted;
+  r_out = pos[1]; v_out = vel; epoch_out = epoch;
+  double cepoch;
+  if (!pos_and_vel_correction(g, gm, P, pos, vel, cepoch, w)) return 1;
+  r_out = pos[1]; v_out = vel; epoch_out = cepoch;
+  return 2;
 }
 
 }  // namespace ofb

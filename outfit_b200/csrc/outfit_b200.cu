@@ -1,7 +1,8 @@
 // outfit_b200.cu -- kernels + C-ABI (include/outfit_b200.h) of the B200-native batched IOD path.
 //
 // Kernels (all scalar FP64, sm_100a):
-//   iod_kernel                 one warp per trajectory, one lane per (triplet, realization)
+//   triplets / roots / correct / score / select kernels: the full-IOD pipeline (one warp per
+//                              trajectory for selection + fold, one lane per (triplet, realization))
 //   scorer_observer_kernel     per observation: DE-style Chebyshev Earth position + frame rotations
 //   propagate_universal_kernel one thread per two-body propagation
 //   fp64_peak_kernel           DFMA issue-rate probe (roofline denominator)
@@ -21,7 +22,18 @@
 using namespace ofb;
 
 // =================================================================================================
-// full-IOD kernel
+// full-IOD pipeline.  Mapping: one warp per trajectory for the two trajectory-level steps (triplet
+// selection, best-orbit fold with warp-shuffle argmin) and one lane per candidate = (triplet,
+// noise realization) for the three numeric phases.  The phases are separate launches over flat
+// candidate arrays because the fused single kernel was instruction-cache bound (ncu r01a/r01b:
+// 57-73 % stall_no_inst with ~100 KB of hot SASS); per phase the hot loop is a few KB, every warp
+// of an SM runs the same loop, and register use / occupancy is set per phase.
+//   P0 triplets_kernel   warp / trajectory   best-K triplets            -> trip[T][K], ktraj[T]
+//   P1 roots_kernel      lane / candidate    geometry, degree-8 poly, Aberth -> roots, code
+//   P2 correct_kernel    lane / candidate    accept root, f-g correction -> state (r, v, epoch)
+//   P3 score_kernel      lane / candidate    elements, equinoctial, arc RMS sum -> kind, sum, n_arc
+//   P4 select_kernel     warp / trajectory   order-preserving fold + result record
+// Candidate id = (t * K + r) * M + m  (K = max_triplets, M = 1 + n_noise_realizations).
 // =================================================================================================
 struct IodBatchDev {
   unsigned long long n_traj;
@@ -33,262 +45,372 @@ struct IodBatchDev {
   const double *noise_z; // [n_traj][max_triplets][n_noise][6] or null
 };
 
-struct CandScore {
-  int kind;     // 0 = gauss error (code), 1 = abort trajectory (code), 2 = score break, 3 = score sum
-  int code;
-  double sum;
-  unsigned n_arc;
+struct IodScratch {
+  unsigned *trip;        // [T][K] packed (i<<20 | j<<10 | k), ascending weight
+  unsigned *ktraj;       // [T] number of triplets found
+  int *code;             // [C] P1: 0 ok | OUTFIT_ST_* ; P3 overwrites with the score kind
+  unsigned char *nroots; // [C]
+  double *roots;         // [8][C] admissible roots in solver order
+  int *state_kind;       // [C] 0 none, 1 PrelimOrbit, 2 CorrectedOrbit
+  double *state;         // [7][C] r(t2) xyz, v(t2) xyz, epoch
+  int *score_kind;       // [C] 0 gauss error (code in score_code), 1 abort, 2 break, 3 sum
+  int *score_code;       // [C]
+  double *score_sum;     // [C]
+  unsigned *score_narc;  // [C]
+  unsigned long long n_cand;
 };
 
 constexpr int kWarpsPerBlock = 4;
-#ifndef OUTFIT_BLOCKS_PER_SM
-#define OUTFIT_BLOCKS_PER_SM 4
-#endif
-constexpr int kBlocksPerSm = OUTFIT_BLOCKS_PER_SM;
+constexpr int kCandThreads = 128;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm)
-iod_kernel(IodBatchDev B, IodDevParams P, OutfitIodResult *__restrict__ out, unsigned n_obs_cap,
-           unsigned long long *__restrict__ traj_counter, unsigned long long *__restrict__ work_counters) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void flush_work(const Work &w, unsigned long long *__restrict__ work_counters) {
+  const unsigned *wp = reinterpret_cast<const unsigned *>(&w);
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = threadIdx.x >> 5;
-  const size_t per_warp = (size_t)kObsPlanes * n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8) + 16 * 32 * sizeof(double);
-  const size_t per_warp_al = (per_warp + 15) & ~(size_t)15;
-  unsigned char *base = smem_raw + warp * per_warp_al;
-  TrajSmem sm;
-  {
-    double *d = reinterpret_cast<double *>(base);
-    sm.t = d; sm.ra = d + n_obs_cap; sm.dec = d + 2 * n_obs_cap; sm.sra = d + 3 * n_obs_cap;
-    sm.sdec = d + 4 * n_obs_cap; sm.cosdec = d + 5 * n_obs_cap;
-    sm.hx = d + 6 * n_obs_cap; sm.hy = d + 7 * n_obs_cap; sm.hz = d + 8 * n_obs_cap;
-    sm.ox = d + 9 * n_obs_cap; sm.oy = d + 10 * n_obs_cap; sm.oz = d + 11 * n_obs_cap;
-    sm.zr = d + (size_t)kObsPlanes * n_obs_cap + lane;
-    sm.zi = sm.zr + 8 * 32;
-    sm.heap_w = d + (size_t)kObsPlanes * n_obs_cap + 16 * 32;
-    sm.heap_x = reinterpret_cast<unsigned *>(sm.heap_w + P.max_triplets);
-    sm.trip = reinterpret_cast<unsigned short *>(sm.heap_x + P.max_triplets);
-  }
-  Work w;
-  memset(&w, 0, sizeof w);
-  const unsigned M = P.n_noise + 1;
-
-  for (;;) {
-    // dynamic trajectory fetch: one atomic per warp (trajectories differ in n_obs and work)
-    unsigned long long tr = 0;
-    if (lane == 0) tr = atomicAdd(traj_counter, 1ull);
-    tr = __shfl_sync(0xffffffffu, tr, 0);
-    if (tr >= B.n_traj) break;
-    const unsigned long long o0 = B.traj_offset[tr];
-    const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-    __syncwarp();
-    // stage the trajectory's observation stream: coalesced 8-byte lanes per plane
-    for (unsigned i = lane; i < n_obs; i += 32) {
-      const unsigned long long gI = o0 + i;
-      sm.t[i] = B.mjd_tt[gI];
-      sm.ra[i] = B.ra[gI];
-      const double d = B.dec[gI];
-      sm.dec[i] = d;
-      sm.cosdec[i] = cos(d);
-      sm.sra[i] = B.sigma_ra[gI];
-      sm.sdec[i] = B.sigma_dec[gI];
-      sm.hx[i] = B.helio[gI]; sm.hy[i] = B.helio[B.n_obs + gI]; sm.hz[i] = B.helio[2 * B.n_obs + gI];
-      sm.ox[i] = B.scorer[gI]; sm.oy[i] = B.scorer[B.n_obs + gI]; sm.oz[i] = B.scorer[2 * B.n_obs + gI];
-    }
-    __syncwarp();
-
-    OutfitIodResult res;
-    memset(&res, 0, sizeof res);
-    res.rms = NAN;
-    const unsigned K = select_triplets(sm, n_obs, P, lane);
-    if (K == 0) {
-      if (lane == 0) {
-        res.status = OUTFIT_ST_NO_FEASIBLE_TRIPLETS;
-        res.span = n_obs == 0 ? 0.0 : sm.t[n_obs - 1] - sm.t[0];
-        out[tr] = res;
-      }
-      continue;
-    }
-    const unsigned n_cand = K * M;
-    // warp-uniform fold state (identical in every lane)
-    double best_rms = INFINITY;
-    unsigned best_c = 0xffffffffu;
-    int abort_code = 0;
-    unsigned abort_c = 0xffffffffu;
-    // warp-uniform copy of the currently selected orbit (broadcast from the owning lane)
-    int bo_kind = 0, bo_corrected = 0;
-    double bo_epoch = 0.0, bo_e0 = 0.0, bo_e1 = 0.0, bo_e2 = 0.0, bo_e3 = 0.0, bo_e4 = 0.0, bo_e5 = 0.0;
-    int last_kind = 0, last_code = 0;
-    double last_val = 0.0;
-
-    for (unsigned cbase = 0; cbase < n_cand; cbase += 32) {
-      const unsigned c = cbase + lane;
-      CandScore cs;
-      cs.kind = -1; cs.code = 0; cs.sum = 0.0; cs.n_arc = 0;
-      Orbit orb;
-      orb.kind = 0; orb.corrected = 0; orb.epoch = 0.0;
-      if (c < n_cand) {
-        ++w.candidates;
-        const unsigned r = c / M, m = c - r * M;
-        const unsigned i0 = sm.trip[4 * r], i1 = sm.trip[4 * r + 1], i2 = sm.trip[4 * r + 2];
-        double ra[3] = {sm.ra[i0], sm.ra[i1], sm.ra[i2]};
-        double dec[3] = {sm.dec[i0], sm.dec[i1], sm.dec[i2]};
-        if (m > 0) {
-          // realizations_iter (gauss.rs:323-387): z order ra0,ra1,ra2,dec0,dec1,dec2
-          const double *z = B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6;
-          const double2 z01 = __ldg(reinterpret_cast<const double2 *>(z));
-          const double2 z23 = __ldg(reinterpret_cast<const double2 *>(z) + 1);
-          const double2 z45 = __ldg(reinterpret_cast<const double2 *>(z) + 2);
-          ra[0] = ra[0] + z01.x * (sm.sra[i0] * P.noise_scale);
-          ra[1] = ra[1] + z01.y * (sm.sra[i1] * P.noise_scale);
-          ra[2] = ra[2] + z23.x * (sm.sra[i2] * P.noise_scale);
-          dec[0] = dec[0] + z23.y * (sm.sdec[i0] * P.noise_scale);
-          dec[1] = dec[1] + z45.x * (sm.sdec[i1] * P.noise_scale);
-          dec[2] = dec[2] + z45.y * (sm.sdec[i2] * P.noise_scale);
-        }
-        const int rc = gauss_prelim_orbit(sm, i0, i1, i2, ra, dec, P, orb, w);
-        if (rc != 0) {
-          cs.kind = 0; cs.code = rc;
-        } else {
-          Equinoctial eq;
-          const int rq = to_equinoctial(orb, eq);
-          if (rq != 0) {
-            cs.kind = 1; cs.code = rq;
-          } else {
-            // select_rms_interval (trajectory.rs:294-350)
-            const double t1 = sm.t[i0], t3 = sm.t[i2];
-            double dtw = P.extf >= 0.0 ? (t3 - t1) * P.extf : 10.0 * (sm.t[n_obs - 1] - sm.t[0]);
-            if (P.dtmax >= 0.0) dtw = fmax(dtw, P.dtmax);
-            unsigned is = 0, ie = n_obs - 1;
-            for (int ii = (int)i0; ii >= 0; --ii) {
-              if (t1 - sm.t[ii] > dtw) break;
-              is = (unsigned)ii;
-            }
-            for (unsigned ii = i2; ii < n_obs; ++ii) {
-              if (sm.t[ii] - t3 > dtw) break;
-              ie = ii;
-            }
-            cs.n_arc = ie - is + 1;
-            const ScoreOrbit so = make_score_orbit(eq);
-            cs.kind = 3;
-            double sum = 0.0;
-            if (!so.elliptic) {
-              cs.kind = 2;
-            } else {
-              for (unsigned ii = is; ii <= ie; ++ii) {
-                double v;
-                if (!ephemeris_error(so, sm.t[ii], sm.ra[ii], sm.dec[ii], sm.cosdec[ii], sm.sra[ii],
-                                     sm.sdec[ii], V3{sm.ox[ii], sm.oy[ii], sm.oz[ii]}, v, w)) {
-                  cs.kind = 2;
-                  break;
-                }
-                const double ns = sum + v;
-                if (ns >= INFINITY) { cs.kind = 2; break; }
-                sum = ns;
-              }
-            }
-            cs.sum = sum;
-          }
-        }
-      }
-      __syncwarp();
-      // ---- order-preserving fold of this chunk (trajectory.rs:465-528) ------------------------
-      // (a) the first candidate whose conversion to equinoctial fails aborts the trajectory
-      {
-        const unsigned ab = __ballot_sync(0xffffffffu, cs.kind == 1);
-        if (ab != 0 && abort_c == 0xffffffffu) {
-          const int src = __ffs(ab) - 1;
-          abort_c = cbase + src;
-          abort_code = __shfl_sync(0xffffffffu, cs.code, src);
-        }
-      }
-      // (b) running-best selection with the reference's pruning rule: a candidate replaces the
-      //     best iff its full sum stays below best^2 * 2N (never pruned) and sqrt(sum/2N) < best
-      {
-        const double denom = 2.0 * (double)cs.n_arc;
-        const double rms_c = sqrt(cs.sum / denom);
-        unsigned from = 0;
-        for (;;) {
-          const double cutoff = isfinite(best_rms) ? best_rms * best_rms * denom : INFINITY;
-          const bool acc = cs.kind == 3 && lane >= from && !(cs.sum >= cutoff) && isfinite(rms_c) && rms_c < best_rms;
-          const unsigned bal = __ballot_sync(0xffffffffu, acc);
-          if (bal == 0) break;
-          const int src = __ffs(bal) - 1;
-          best_rms = __shfl_sync(0xffffffffu, rms_c, src);
-          best_c = cbase + src;
-          bo_kind = __shfl_sync(0xffffffffu, orb.kind, src);
-          bo_corrected = __shfl_sync(0xffffffffu, orb.corrected, src);
-          bo_epoch = __shfl_sync(0xffffffffu, orb.epoch, src);
-          bo_e0 = __shfl_sync(0xffffffffu, orb.e[0], src);
-          bo_e1 = __shfl_sync(0xffffffffu, orb.e[1], src);
-          bo_e2 = __shfl_sync(0xffffffffu, orb.e[2], src);
-          bo_e3 = __shfl_sync(0xffffffffu, orb.e[3], src);
-          bo_e4 = __shfl_sync(0xffffffffu, orb.e[4], src);
-          bo_e5 = __shfl_sync(0xffffffffu, orb.e[5], src);
-          from = src + 1;
-          if (from >= 32) break;
-        }
-      }
-      // (c) error of the LAST candidate in evaluation order (only used when nothing succeeds,
-      //     in which case best_rms stayed +inf for every candidate)
-      if (c == n_cand - 1) {
-        if (cs.kind == 0) { last_kind = 0; last_code = cs.code; last_val = 0.0; }
-        else if (cs.kind == 2) { last_kind = 1; last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = INFINITY; }
-        else if (cs.kind == 3) {
-          last_kind = 1; last_code = OUTFIT_ST_NON_FINITE_SCORE;
-          last_val = sqrt(cs.sum / (2.0 * (double)cs.n_arc));
-        }
-      }
-    }
-
-    // ---- result ---------------------------------------------------------------------------
-    const unsigned last_lane = (n_cand - 1) & 31u;
-    const int l_code = __shfl_sync(0xffffffffu, last_code, last_lane);
-    const double l_val = __shfl_sync(0xffffffffu, last_val, last_lane);
-    (void)last_kind;
-    if (abort_c != 0xffffffffu) {
-      // `?` in trajectory.rs:491-497 returns the conversion error for the whole trajectory
-      if (lane == 0) {
-        res.status = abort_code;
-        res.attempts = abort_c + 1;
-        out[tr] = res;
-      }
-    } else if (best_c != 0xffffffffu) {
-      if (lane == 0) {
-        const unsigned r = best_c / M;
-        res.status = OUTFIT_ST_OK;
-        res.attempts = n_cand;
-        res.corrected = bo_corrected;
-        res.element_kind = bo_kind;
-        res.epoch = bo_epoch;
-        res.elem[0] = bo_e0; res.elem[1] = bo_e1; res.elem[2] = bo_e2;
-        res.elem[3] = bo_e3; res.elem[4] = bo_e4; res.elem[5] = bo_e5;
-        res.rms = best_rms;
-        res.triplet_idx[0] = sm.trip[4 * r];
-        res.triplet_idx[1] = sm.trip[4 * r + 1];
-        res.triplet_idx[2] = sm.trip[4 * r + 2];
-        res.triplet_rank = r;
-        res.realization = best_c - r * M;
-        out[tr] = res;
-      }
-    } else if (lane == 0) {
-      res.status = OUTFIT_ST_NO_VIABLE_ORBIT;
-      res.cause = l_code;
-      res.cause_value = l_val;
-      res.attempts = n_cand;
-      out[tr] = res;
-    }
-    __syncwarp();
-  }
-
-  // work counters: warp reduce, one atomic per counter per warp
-  unsigned *wp = reinterpret_cast<unsigned *>(&w);
 #pragma unroll
   for (int q = 0; q < (int)(sizeof(Work) / sizeof(unsigned)); ++q) {
     unsigned long long v = wp[q];
+    if (__any_sync(0xffffffffu, v != 0)) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0 && work_counters) atomicAdd(&work_counters[q], v);
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && work_counters) atomicAdd(&work_counters[q], v);
+    }
   }
+}
+
+// ---- P0: best-K triplets, one warp per trajectory --------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+triplets_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned n_obs_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const size_t per_warp = ((size_t)n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4) + 15) & ~(size_t)15;
+  TrajSmem sm;
+  sm.t = reinterpret_cast<double *>(smem_raw + warp * per_warp);
+  sm.heap_w = sm.t + n_obs_cap;
+  sm.heap_x = reinterpret_cast<unsigned *>(sm.heap_w + P.max_triplets);
+  const unsigned long long tr = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp;
+  if (tr >= B.n_traj) return;
+  const unsigned long long o0 = B.traj_offset[tr];
+  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+  for (unsigned i = lane; i < n_obs; i += 32) sm.t[i] = B.mjd_tt[o0 + i];
+  __syncwarp();
+  const unsigned K = select_triplets(sm, n_obs, P, lane);
+  for (unsigned a = lane; a < K; a += 32) S.trip[tr * P.max_triplets + a] = sm.heap_x[a];
+  if (lane == 0) S.ktraj[tr] = K;
+}
+
+// candidate id -> (trajectory, triplet rank, realization); false when the slot is unused
+__device__ __forceinline__ bool decode_candidate(unsigned long long cid, const IodDevParams &P, const IodScratch &S,
+                                                 unsigned long long &tr, unsigned &r, unsigned &m) {
+  const unsigned M = P.n_noise + 1;
+  const unsigned long long tk = cid / M;
+  m = (unsigned)(cid - tk * M);
+  tr = tk / P.max_triplets;
+  r = (unsigned)(tk - tr * P.max_triplets);
+  return r < S.ktraj[tr];
+}
+
+// observations of the triplet (+ the host-drawn noise of this realization, gauss.rs:323-387)
+__device__ __forceinline__ void load_triplet(const IodBatchDev &B, const IodDevParams &P, const IodScratch &S,
+                                             unsigned long long tr, unsigned r, unsigned m, Triplet &g, unsigned (&idx)[3]) {
+  const unsigned packed = S.trip[tr * P.max_triplets + r];
+  idx[0] = packed >> 20; idx[1] = (packed >> 10) & 1023u; idx[2] = packed & 1023u;
+  const unsigned long long o0 = B.traj_offset[tr];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const unsigned long long gI = o0 + idx[c];
+    g.t[c] = __ldg(B.mjd_tt + gI);
+    g.ra[c] = __ldg(B.ra + gI);
+    g.dec[c] = __ldg(B.dec + gI);
+    g.R[c] = V3{__ldg(B.helio + gI), __ldg(B.helio + B.n_obs + gI), __ldg(B.helio + 2 * B.n_obs + gI)};
+  }
+  if (m > 0) {
+    const double *z = B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6;
+    const double2 z01 = __ldg(reinterpret_cast<const double2 *>(z));
+    const double2 z23 = __ldg(reinterpret_cast<const double2 *>(z) + 1);
+    const double2 z45 = __ldg(reinterpret_cast<const double2 *>(z) + 2);
+    const unsigned long long g0 = o0 + idx[0], g1 = o0 + idx[1], g2 = o0 + idx[2];
+    g.ra[0] = g.ra[0] + z01.x * (__ldg(B.sigma_ra + g0) * P.noise_scale);
+    g.ra[1] = g.ra[1] + z01.y * (__ldg(B.sigma_ra + g1) * P.noise_scale);
+    g.ra[2] = g.ra[2] + z23.x * (__ldg(B.sigma_ra + g2) * P.noise_scale);
+    g.dec[0] = g.dec[0] + z23.y * (__ldg(B.sigma_dec + g0) * P.noise_scale);
+    g.dec[1] = g.dec[1] + z45.x * (__ldg(B.sigma_dec + g1) * P.noise_scale);
+    g.dec[2] = g.dec[2] + z45.y * (__ldg(B.sigma_dec + g2) * P.noise_scale);
+  }
+}
+
+// ---- P1: geometry + polynomial + Aberth ---------------------------------------------------------
+__global__ void __launch_bounds__(kCandThreads)
+roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
+  __shared__ double zsm[kCandThreads * 16];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  double *zr = zsm + warp * 512 + lane, *zi = zr + 256;
+  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
+  Work w;
+  memset(&w, 0, sizeof w);
+  unsigned long long tr;
+  unsigned r, m;
+  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
+    ++w.candidates;
+    ++w.gauss_solves;
+    Triplet g;
+    unsigned idx[3];
+    load_triplet(B, P, S, tr, r, m, g, idx);
+    GaussGeom gm;
+    int code = 0;
+    unsigned n = 0;
+    double c0, c3, c6;
+    if (!gauss_geometry(g, gm)) code = OUTFIT_ST_SINGULAR_DIRECTION_MATRIX;
+    else if (!gauss_polynomial(g, gm, c0, c3, c6)) code = OUTFIT_ST_GAUSS_NO_ROOTS;
+    else if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) code = OUTFIT_ST_POLY_ROOT_FAILED;
+    else {
+      // visit_real_positive_roots + plausibility window (gauss.rs:975-981, 1148), solver order kept
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) {
+        const double re = zr[k * 32];
+        if (re > 0.0 && fabs(zi[k * 32]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
+          S.roots[(size_t)n * S.n_cand + cid] = re;
+          ++n;
+        }
+      }
+      if (n == 0) code = OUTFIT_ST_GAUSS_NO_ROOTS;
+    }
+    S.code[cid] = code;
+    S.nroots[cid] = (unsigned char)n;
+  }
+  flush_work(w, work_counters);
+}
+
+// ---- P2: roots -> accepted state, f-g correction ---------------------------------------------------
+__global__ void __launch_bounds__(kCandThreads)
+correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
+  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
+  Work w;
+  memset(&w, 0, sizeof w);
+  unsigned long long tr;
+  unsigned r, m;
+  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
+    int kind = 0;
+    const unsigned n = S.code[cid] == 0 ? S.nroots[cid] : 0u;
+    if (n > 0) {
+      Triplet g;
+      unsigned idx[3];
+      load_triplet(B, P, S, tr, r, m, g, idx);
+      GaussGeom gm;
+      gauss_geometry(g, gm);
+      unsigned n_solutions = 0;
+#pragma unroll 1
+      for (unsigned k = 0; k < n; ++k) {
+        V3 rr, vv;
+        double ep;
+        const int sk = solve_root(g, gm, P, S.roots[(size_t)k * S.n_cand + cid], rr, vv, ep, w);
+        if (sk == 0) continue;
+        ++n_solutions;
+        // prelim_orbit (gauss.rs:1238-1247): first CorrectedOrbit in discovery order, else first pushed
+        if (sk == 2 || kind == 0) {
+          kind = sk;
+          S.state[0 * S.n_cand + cid] = rr.x; S.state[1 * S.n_cand + cid] = rr.y; S.state[2 * S.n_cand + cid] = rr.z;
+          S.state[3 * S.n_cand + cid] = vv.x; S.state[4 * S.n_cand + cid] = vv.y; S.state[5 * S.n_cand + cid] = vv.z;
+          S.state[6 * S.n_cand + cid] = ep;
+          if (sk == 2) break;
+        }
+        if (n_solutions >= P.max_tested_solutions) break;
+      }
+    }
+    S.state_kind[cid] = kind;
+  }
+  flush_work(w, work_counters);
+}
+
+__device__ __forceinline__ void state_to_orbit(const IodScratch &S, unsigned long long cid, int state_kind, Orbit &orb) {
+  const V3 rr = V3{S.state[0 * S.n_cand + cid], S.state[1 * S.n_cand + cid], S.state[2 * S.n_cand + cid]};
+  const V3 vv = V3{S.state[3 * S.n_cand + cid], S.state[4 * S.n_cand + cid], S.state[5 * S.n_cand + cid]};
+  // build_result (gauss.rs:1063): rotate to ecliptic J2000, state -> elements
+  ccek1(equ_to_ecl(rr), equ_to_ecl(vv), S.state[6 * S.n_cand + cid], orb);
+  orb.corrected = state_kind == 2 ? 1 : 0;
+}
+
+// ---- P3: elements -> equinoctial -> arc RMS sum --------------------------------------------------
+__global__ void __launch_bounds__(kCandThreads)
+score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
+  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
+  Work w;
+  memset(&w, 0, sizeof w);
+  unsigned long long tr;
+  unsigned r, m;
+  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
+    int kind, code = 0;
+    double sum = 0.0;
+    unsigned n_arc = 0;
+    const int gcode = S.code[cid];
+    const int sk = S.state_kind[cid];
+    if (gcode != 0) { kind = 0; code = gcode; }
+    else if (sk == 0) { kind = 0; code = OUTFIT_ST_GAUSS_NO_ROOTS; }
+    else {
+      Orbit orb;
+      state_to_orbit(S, cid, sk, orb);
+      Equinoctial eq;
+      const int rq = to_equinoctial(orb, eq);
+      if (rq != 0) { kind = 1; code = rq; }
+      else {
+        // select_rms_interval (trajectory.rs:294-350)
+        const unsigned packed = S.trip[tr * P.max_triplets + r];
+        const unsigned i0 = packed >> 20, i2 = packed & 1023u;
+        const unsigned long long o0 = B.traj_offset[tr];
+        const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+        const double *T = B.mjd_tt + o0;
+        const double t1 = __ldg(T + i0), t3 = __ldg(T + i2);
+        double dtw = P.extf >= 0.0 ? (t3 - t1) * P.extf : 10.0 * (__ldg(T + n_obs - 1) - __ldg(T));
+        if (P.dtmax >= 0.0) dtw = fmax(dtw, P.dtmax);
+        unsigned is = 0, ie = n_obs - 1;
+        for (int ii = (int)i0; ii >= 0; --ii) {
+          if (t1 - __ldg(T + ii) > dtw) break;
+          is = (unsigned)ii;
+        }
+        for (unsigned ii = i2; ii < n_obs; ++ii) {
+          if (__ldg(T + ii) - t3 > dtw) break;
+          ie = ii;
+        }
+        n_arc = ie - is + 1;
+        const ScoreOrbit so = make_score_orbit(eq);
+        kind = 3;
+        if (!so.elliptic) {
+          kind = 2;
+        } else {
+#pragma unroll 1
+          for (unsigned ii = is; ii <= ie; ++ii) {
+            const unsigned long long gI = o0 + ii;
+            const double dec_o = __ldg(B.dec + gI);
+            double v;
+            if (!ephemeris_error(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos(dec_o), __ldg(B.sigma_ra + gI),
+                                 __ldg(B.sigma_dec + gI),
+                                 V3{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)},
+                                 v, w)) {
+              kind = 2;
+              break;
+            }
+            const double ns = sum + v;
+            if (ns >= INFINITY) { kind = 2; break; }
+            sum = ns;
+          }
+        }
+      }
+    }
+    S.score_kind[cid] = kind;
+    S.score_code[cid] = code;
+    S.score_sum[cid] = sum;
+    S.score_narc[cid] = n_arc;
+  }
+  flush_work(w, work_counters);
+}
+
+// ---- P4: per-trajectory fold, one warp per trajectory (trajectory.rs:429-545) ----------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+select_kernel(IodBatchDev B, IodDevParams P, IodScratch S, OutfitIodResult *__restrict__ out) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long tr = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp;
+  if (tr >= B.n_traj) return;
+  const unsigned M = P.n_noise + 1;
+  const unsigned K = S.ktraj[tr];
+  const unsigned long long o0 = B.traj_offset[tr];
+  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+  OutfitIodResult res;
+  memset(&res, 0, sizeof res);
+  res.rms = NAN;
+  if (K == 0) {
+    if (lane == 0) {
+      res.status = OUTFIT_ST_NO_FEASIBLE_TRIPLETS;
+      res.span = n_obs == 0 ? 0.0 : B.mjd_tt[o0 + n_obs - 1] - B.mjd_tt[o0];
+      out[tr] = res;
+    }
+    return;
+  }
+  const unsigned n_cand = K * M;
+  const unsigned long long cbase0 = tr * (unsigned long long)P.max_triplets * M;
+  double best_rms = INFINITY;
+  unsigned best_c = 0xffffffffu;
+  int abort_code = 0;
+  unsigned abort_c = 0xffffffffu;
+  int last_code = 0;
+  double last_val = 0.0;
+  for (unsigned cbase = 0; cbase < n_cand; cbase += 32) {
+    const unsigned c = cbase + lane;
+    int kind = -1, code = 0;
+    double sum = 0.0;
+    unsigned n_arc = 0;
+    if (c < n_cand) {
+      kind = S.score_kind[cbase0 + c];
+      code = S.score_code[cbase0 + c];
+      sum = S.score_sum[cbase0 + c];
+      n_arc = S.score_narc[cbase0 + c];
+    }
+    // (a) the first candidate whose conversion to equinoctial fails aborts the trajectory (`?`)
+    {
+      const unsigned ab = __ballot_sync(0xffffffffu, kind == 1);
+      if (ab != 0 && abort_c == 0xffffffffu) {
+        const int src = __ffs(ab) - 1;
+        abort_c = cbase + src;
+        abort_code = __shfl_sync(0xffffffffu, code, src);
+      }
+    }
+    // (b) running best with the reference's pruning rule: a candidate replaces the best iff its
+    //     full sum stays below best^2 * 2N (never pruned) and sqrt(sum / 2N) < best (strict)
+    {
+      const double denom = 2.0 * (double)n_arc;
+      const double rms_c = sqrt(sum / denom);
+      unsigned from = 0;
+      for (;;) {
+        const double cutoff = isfinite(best_rms) ? best_rms * best_rms * denom : INFINITY;
+        const bool acc = kind == 3 && lane >= from && !(sum >= cutoff) && isfinite(rms_c) && rms_c < best_rms;
+        const unsigned bal = __ballot_sync(0xffffffffu, acc);
+        if (bal == 0) break;
+        const int src = __ffs(bal) - 1;
+        best_rms = __shfl_sync(0xffffffffu, rms_c, src);
+        best_c = cbase + src;
+        from = src + 1;
+        if (from >= 32) break;
+      }
+    }
+    // (c) error of the LAST candidate in evaluation order (used only when nothing succeeded, in
+    //     which case the running best stayed +inf for every candidate)
+    if (c == n_cand - 1) {
+      if (kind == 0) { last_code = code; last_val = 0.0; }
+      else if (kind == 2) { last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = INFINITY; }
+      else if (kind == 3) { last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = sqrt(sum / (2.0 * (double)n_arc)); }
+    }
+  }
+  const unsigned last_lane = (n_cand - 1) & 31u;
+  const int l_code = __shfl_sync(0xffffffffu, last_code, last_lane);
+  const double l_val = __shfl_sync(0xffffffffu, last_val, last_lane);
+  if (lane != 0) return;
+  if (abort_c != 0xffffffffu) {
+    res.status = abort_code;
+    res.attempts = abort_c + 1;
+  } else if (best_c != 0xffffffffu) {
+    const unsigned r = best_c / M;
+    const unsigned long long cid = cbase0 + best_c;
+    Orbit orb;
+    state_to_orbit(S, cid, S.state_kind[cid], orb);
+    res.status = OUTFIT_ST_OK;
+    res.attempts = n_cand;
+    res.corrected = orb.corrected;
+    res.element_kind = orb.kind;
+    res.epoch = orb.epoch;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) res.elem[q] = orb.e[q];
+    res.rms = best_rms;
+    const unsigned packed = S.trip[tr * P.max_triplets + r];
+    res.triplet_idx[0] = packed >> 20;
+    res.triplet_idx[1] = (packed >> 10) & 1023u;
+    res.triplet_idx[2] = packed & 1023u;
+    res.triplet_rank = r;
+    res.realization = best_c - r * M;
+  } else {
+    res.status = OUTFIT_ST_NO_VIABLE_ORBIT;
+    res.cause = l_code;
+    res.cause_value = l_val;
+    res.attempts = n_cand;
+  }
+  out[tr] = res;
 }
 
 // =================================================================================================
@@ -380,6 +502,8 @@ struct OutfitCtx {
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   void *h_scratch = nullptr;
+  void *iod_scratch = nullptr;  // per-candidate arrays of the phase pipeline
+  size_t iod_scratch_bytes = 0;
 };
 
 static int fail(OutfitCtx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -471,6 +595,7 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   if (ctx->d_cheb) cudaFree(ctx->d_cheb);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->iod_scratch) cudaFree(ctx->iod_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   delete ctx;
 }
@@ -505,6 +630,14 @@ static int ensure_scratch(OutfitCtx *ctx, size_t bytes) {
   if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
   if (cudaMalloc(&ctx->scratch, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(scratch)");
   ctx->scratch_bytes = bytes;
+  return OUTFIT_OK;
+}
+
+static int ensure_iod_scratch(OutfitCtx *ctx, size_t bytes) {
+  if (ctx->iod_scratch_bytes >= bytes) return OUTFIT_OK;
+  if (ctx->iod_scratch) { cudaFree(ctx->iod_scratch); ctx->iod_scratch = nullptr; ctx->iod_scratch_bytes = 0; }
+  if (cudaMalloc(&ctx->iod_scratch, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(candidate scratch)");
+  ctx->iod_scratch_bytes = bytes;
   return OUTFIT_OK;
 }
 
@@ -557,25 +690,54 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   }
   if (n) scorer_observer_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, d_geo, d_scorer, d_status);
 
-  IodBatchDev B;
-  B.n_traj = b->n_traj; B.n_obs = n; B.traj_offset = reinterpret_cast<const unsigned long long *>(b->traj_offset);
-  B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
-  B.helio = d_helio; B.scorer = d_scorer; B.noise_z = b->noise_z;
   const IodDevParams P = to_dev_params(*params);
+  const unsigned M = P.n_noise + 1;
+  const unsigned long long cand_per_traj = (unsigned long long)P.max_triplets * M;
+  // per-candidate scratch (bytes): code 4 + nroots 1 + roots 64 + state_kind 4 + state 56 + score 20
+  const size_t per_cand = 4 + 1 + 64 + 4 + 56 + 4 + 4 + 8 + 4;
+  const size_t per_traj = (size_t)cand_per_traj * per_cand + (size_t)P.max_triplets * 4 + 4;
+  const size_t budget = (size_t)6 << 30;  // candidate scratch per chunk
+  unsigned long long chunk = b->n_traj;
+  if (per_traj * chunk > budget) chunk = budget / per_traj ? budget / per_traj : 1;
+  rc = ensure_iod_scratch(ctx, per_traj * chunk + 64 * 256);
+  if (rc) return rc;
   const unsigned cap = max_obs < 3 ? 4 : ((max_obs + 1) & ~1u);
-  size_t per_warp = (size_t)kObsPlanes * cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4 + 8) + 16 * 32 * sizeof(double);
-  per_warp = (per_warp + 15) & ~(size_t)15;
-  const size_t smem = per_warp * kWarpsPerBlock;
-  if (smem > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");
-  CK(cudaFuncSetAttribute(iod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, iod_kernel, kWarpsPerBlock * 32, smem));
-  if (occ < 1) occ = 1;
-  unsigned long long want = (b->n_traj + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  unsigned grid = (unsigned)ctx->sm_count * (unsigned)occ;  // persistent: a multiple of the SM count
-  if (want < grid) grid = (unsigned)(want ? want : 1);
+  size_t per_warp = ((size_t)cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4) + 15) & ~(size_t)15;
+  const size_t smem0 = per_warp * kWarpsPerBlock;
+  if (smem0 > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");
+  CK(cudaFuncSetAttribute(triplets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
   CK(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), stream));
-  if (b->n_traj) iod_kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(B, P, d_out, cap, ctx->d_counters, ctx->d_counters + 1);
+  for (unsigned long long t0 = 0; t0 < b->n_traj; t0 += chunk) {
+    const unsigned long long tn = b->n_traj - t0 < chunk ? b->n_traj - t0 : chunk;
+    IodBatchDev B;
+    B.n_traj = tn; B.n_obs = n;
+    B.traj_offset = reinterpret_cast<const unsigned long long *>(b->traj_offset) + t0;
+    B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
+    B.helio = d_helio; B.scorer = d_scorer;
+    B.noise_z = b->noise_z ? b->noise_z + (size_t)t0 * P.max_triplets * P.n_noise * 6 : nullptr;
+    IodScratch S;
+    S.n_cand = tn * cand_per_traj;
+    unsigned char *p = reinterpret_cast<unsigned char *>(ctx->iod_scratch);
+    auto take = [&](size_t bytes) { void *q = p; p += (bytes + 255) & ~(size_t)255; return q; };
+    S.roots = (double *)take(8 * S.n_cand * 8);
+    S.state = (double *)take(7 * S.n_cand * 8);
+    S.score_sum = (double *)take(S.n_cand * 8);
+    S.code = (int *)take(S.n_cand * 4);
+    S.state_kind = (int *)take(S.n_cand * 4);
+    S.score_kind = (int *)take(S.n_cand * 4);
+    S.score_code = (int *)take(S.n_cand * 4);
+    S.score_narc = (unsigned *)take(S.n_cand * 4);
+    S.trip = (unsigned *)take(tn * P.max_triplets * 4);
+    S.ktraj = (unsigned *)take(tn * 4);
+    S.nroots = (unsigned char *)take(S.n_cand);
+    const unsigned tblocks = (unsigned)((tn + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
+    triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+    roots_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    correct_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    score_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    select_kernel<<<tblocks, kWarpsPerBlock * 32, 0, stream>>>(B, P, S, d_out + t0);
+  }
   CK(cudaGetLastError());
   return OUTFIT_OK;
 }
