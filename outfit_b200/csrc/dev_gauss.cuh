@@ -80,11 +80,14 @@ __device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6
   dp = d;
 }
 
-// returns 0 converged / 1 max-iter / 2 failed.  The 8 iterates live in shared memory, lane-strided
-// (z[k * 32 + lane]: conflict-free), so that the sweep can be a ROLLED loop: the instruction footprint
-// of the unrolled 8x8 version thrashed the instruction cache (ncu r01a: 73 % stall_no_inst).
-__device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned max_iter, double eps,
-                                    double *__restrict__ zr, double *__restrict__ zi, Work &w) {
+// returns 0 converged / 1 max-iter / 2 failed; the 8 iterates (index order k) are left in zr/zi.
+// One Jacobi sweep = (1) the 28 pair reciprocals 1/(z_i - z_k), i < k, each added to sum_i and
+// subtracted from sum_k -- IEEE negation is exact, and visiting the pairs in lexicographic order
+// delivers every sum its terms in increasing index order, so the sums are bit-identical to the
+// crate's 56-reciprocal double loop at half the divisions; (2) per root: dense Horner p, p',
+// w = p / (p * sum - p'), z += w.  Fully unrolled on registers (this kernel's code is small).
+__device__ __forceinline__ int aberth8(double c0, double c3, double c6, unsigned max_iter, double eps,
+                                       double (&zr)[8], double (&zi)[8], Work &w) {
   // Cauchy-type start radius: smallest integer r0 with S(r0) > 0, S(w) = w^8 - |c6| w^6 - |c3| w^3 - |c0|
   const double s0 = -fabs(c0), s3 = -fabs(c3), s6 = -fabs(c6);
   double r0 = 1.0;
@@ -102,36 +105,41 @@ __device__ __noinline__ int aberth8(double c0, double c3, double c6, unsigned ma
     if (r > 0.0) break;
     r0 += 1.0;
   }
-#pragma unroll 1
+#pragma unroll
   for (int k = 0; k < 8; ++k) {
-    zr[k * 32] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
-    zi[k * 32] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
+    zr[k] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
+    zi[k] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
   }
   for (unsigned it = 0; it < max_iter; ++it) {
     ++w.aberth_sweeps;
-    double nr[8], ni[8];  // Jacobi: the sweep reads only the previous iterates
+    double sr[8], si[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sr[k] = 0.0; si[k] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int k = i + 1; k < 8; ++k) {
+        const Cx rec = cx_recip(Cx{__dsub_rn(zr[i], zr[k]), __dsub_rn(zi[i], zi[k])});
+        sr[i] = __dadd_rn(sr[i], rec.re);
+        si[i] = __dadd_rn(si[i], rec.im);
+        sr[k] = __dadd_rn(sr[k], -rec.re);  // 1/(z_k - z_i) = -(1/(z_i - z_k)) exactly
+        si[k] = __dadd_rn(si[k], -rec.im);
+      }
+    }
     bool converged = true;
     bool failed = false;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const Cx z = Cx{zr[i * 32], zi[i * 32]};
+      const Cx z = Cx{zr[i], zi[i]};
       Cx p, dp;
       poly8_eval(z, c0, c3, c6, p, dp);
-      Cx sum = Cx{0.0, 0.0};
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        if (k == i) continue;
-        sum = cx_add(sum, cx_recip(cx_sub(z, Cx{zr[k * 32], zi[k * 32]})));
-      }
-      const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, sum), dp)));
-      nr[i] = nz.re;
-      ni[i] = nz.im;
+      const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, Cx{sr[i], si[i]}), dp)));
       if (!(isfinite(nz.re) && isfinite(nz.im))) failed = true;
       if (!(fabs(__dsub_rn(nz.re, z.re)) < eps && fabs(__dsub_rn(nz.im, z.im)) < eps)) converged = false;
+      zr[i] = nz.re;  // in place: no later root of this sweep reads z_i (the sums are complete)
+      zi[i] = nz.im;
     }
     if (failed) return 2;  // the caller maps it to PolynomialRootFindingFailed
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) { zr[i * 32] = nr[i]; zi[i * 32] = ni[i]; }
     if (converged) return 0;
   }
   return 1;
@@ -187,23 +195,28 @@ __device__ __forceinline__ V3 gibbs_velocity(const V3 (&pos)[3], double tau1, do
 }
 
 // Iterative two-sided Lagrange f-g refinement (gauss.rs:1284-1418).  Returns false <=> None.
+// `ec0` = eccentricity_control of the incoming (pos[1], vel) (accept_root computed it with the same
+// limits); the control evaluated on a committed update is the one the next iteration's velocity
+// corrections would recompute, so it is carried instead.
 __device__ __noinline__ bool pos_and_vel_correction(const Triplet &g, const GaussGeom &gm,
-                                                       const IodDevParams &P, V3 (&pos)[3], V3 &vel,
-                                                       double &epoch, Work &w) {
+                                                    const IodDevParams &P, V3 (&pos)[3], V3 &vel,
+                                                    const EccCtl &ec0, double &epoch, Work &w) {
   const double dt01 = g.t[0] - g.t[1], dt21 = g.t[2] - g.t[1];
   double ep = 0.0;
   if (fabs(dt01) <= kEps || fabs(dt21) <= kEps) return false;
-  bool has01 = false, has21 = false;
+  bool has_chi = false;
   double chi01 = 0.0, chi21 = 0.0;
+  MidState mid = mid_state(pos[1], vel, ec0);
   for (unsigned it = 0; it < P.newton_max_it; ++it) {
     ++w.fg_iterations;
-    const VelCor L = velocity_correction(pos[0], pos[1], vel, dt01, P.max_perihelion_au, P.max_ecc,
-                                         has01, chi01, P.kepler_eps, w);
-    const VelCor Rr = velocity_correction(pos[2], pos[1], vel, dt21, P.max_perihelion_au, P.max_ecc,
-                                          has21, chi21, P.kepler_eps, w);
-    if (!(L.ok && Rr.ok)) continue;
-    has01 = true; chi01 = L.chi;
-    has21 = true; chi21 = Rr.chi;
+    const VelCor L = velocity_correction_side(pos[0], pos[1], mid, dt01, has_chi, chi01, P.kepler_eps, w);
+    const VelCor Rr = velocity_correction_side(pos[2], pos[1], mid, dt21, has_chi, chi21, P.kepler_eps, w);
+    if (!(L.ok && Rr.ok)) {
+      // nothing was updated: every remaining iteration would repeat this one exactly
+      if (!has_chi) { w.fg_iterations += P.newton_max_it - 1 - it; break; }
+      continue;
+    }
+    has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
     if (!isfinite(L.g) || !isfinite(Rr.g)) continue;
     const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
     const double fl = L.f * Rr.g - Rr.f * L.g;
@@ -221,6 +234,7 @@ __device__ __noinline__ bool pos_and_vel_correction(const Triplet &g, const Gaus
     pos[0] = np[0]; pos[1] = np[1]; pos[2] = np[2];
     vel = nv;
     ep = nep;
+    mid = mid_state(pos[1], vel, ec);
     if (rel <= P.newton_eps) break;
   }
   epoch = ep;

@@ -216,14 +216,12 @@ __device__ __forceinline__ int solve_root(const Triplet &g, const GaussGeom &gm,
   double epoch;
   if (!positions_from_c(g, gm, gm.a0 + gm.b0 * r2m3, -1.0, gm.a2 + gm.b2 * r2m3, P.min_rho2_au, pos, epoch)) return 0;
   V3 vel = gibbs_velocity(pos, gm.tau1, gm.tau3);
-  {
-    const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
-    if (!ec.defined || !ec.accepted) return 0;
-  }
+  const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
+  if (!ec.defined || !ec.accepted) return 0;
   ++w.roots_accepted;
   r_out = pos[1]; v_out = vel; epoch_out = epoch;
   double cepoch;
-  if (!pos_and_vel_correction(g, gm, P, pos, vel, cepoch, w)) return 1;
+  if (!pos_and_vel_correction(g, gm, P, pos, vel, ec, cepoch, w)) return 1;
   r_out = pos[1]; v_out = vel; epoch_out = cepoch;
   return 2;
 }

@@ -141,9 +141,7 @@ __device__ __forceinline__ void load_triplet(const IodBatchDev &B, const IodDevP
 // ---- P1: geometry + polynomial + Aberth ---------------------------------------------------------
 __global__ void __launch_bounds__(kCandThreads)
 roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  __shared__ double zsm[kCandThreads * 16];
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  double *zr = zsm + warp * 512 + lane, *zi = zr + 256;
+  double zr[8], zi[8];
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
   Work w;
   memset(&w, 0, sizeof w);
@@ -164,10 +162,10 @@ roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
     else if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) code = OUTFIT_ST_POLY_ROOT_FAILED;
     else {
       // visit_real_positive_roots + plausibility window (gauss.rs:975-981, 1148), solver order kept
-#pragma unroll 1
+#pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const double re = zr[k * 32];
-        if (re > 0.0 && fabs(zi[k * 32]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
+        const double re = zr[k];
+        if (re > 0.0 && fabs(zi[k]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
           S.roots[(size_t)n * S.n_cand + cid] = re;
           ++n;
         }
@@ -181,7 +179,10 @@ roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
 }
 
 // ---- P2: roots -> accepted state, f-g correction ---------------------------------------------------
-__global__ void __launch_bounds__(kCandThreads)
+#ifndef OUTFIT_CORRECT_BPS
+#define OUTFIT_CORRECT_BPS 4
+#endif
+__global__ void __launch_bounds__(kCandThreads, OUTFIT_CORRECT_BPS)
 correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
   Work w;
@@ -585,6 +586,14 @@ extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
     dir[2 * k + 1] = sin(theta);
   }
   if (cudaMemcpyToSymbol(c_aberth_dir, dir, sizeof dir) != cudaSuccess) { cudaFree(ctx->d_counters); delete ctx; return OUTFIT_E_CUDA; }
+  // correctly rounded reciprocals of the Stumpff-series denominators (see div_by_const)
+  double rcp[2 * kSeriesTable];
+  for (int j = 0; j < kSeriesTable; ++j) {
+    const double d = 3.0 + 2.0 * j;
+    rcp[2 * j] = 1.0 / (d * (d + 1.0));
+    rcp[2 * j + 1] = 1.0 / ((d + 1.0) * (d + 2.0));
+  }
+  if (cudaMemcpyToSymbol(c_series_rcp, rcp, sizeof rcp) != cudaSuccess) { cudaFree(ctx->d_counters); delete ctx; return OUTFIT_E_CUDA; }
   *out = ctx;
   return OUTFIT_OK;
 }
