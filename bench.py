@@ -46,8 +46,17 @@ W_FLOP = dict(sfunct_terms=12.0, newton_steps=15.0 + 9.0, fg_iterations=2 * 60.0
 W_LIBM = dict(gauss_solves=12.0, candidates=15.0, scorer_evals=4.0, scorer_newton_steps=2.0)
 
 
-def algorithmic_flops(counters):
-    return sum(W_FLOP[k] * counters[k] for k in W_FLOP)
+# which kernel executes which counted events (phase pipeline, outfit_b200.cu)
+KERNEL_EVENTS = {
+    "roots_kernel": ("gauss_solves", "aberth_sweeps"),
+    "correct_kernel": ("roots_accepted", "fg_iterations", "newton_steps", "sfunct_terms"),
+    "score_kernel": ("candidates", "scorer_evals", "scorer_newton_steps"),
+}
+KERNEL_PHASE = {"roots_kernel": "roots_ms", "correct_kernel": "correct_ms", "score_kernel": "score_ms"}
+
+
+def algorithmic_flops(counters, keys=None):
+    return sum(W_FLOP[k] * counters[k] for k in (keys or W_FLOP))
 
 
 def libm_calls(counters):
@@ -226,6 +235,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    ctx.set_work_counters(False)  # timed steps run the plain instantiation of the kernels
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
@@ -239,18 +249,19 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / max(1, args.steps)
-    counters = ctx.last_iod_counters()
-    launches = args.steps * 2  # scorer_observer_kernel + iod_kernel per step (memset is not ours)
-
-    # kernel-only timing of the dominant kernel path (no gather), for the roofline
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    k0.record()
+    # per-kernel durations of the LAST timed step: CUDA events the library records on the launching
+    # stream between its kernels (outfit_b200_last_iod_phase_ms)
+    phases = ctx.last_iod_phase_ms()
+    per_step_launches = int(phases["kernel_launches"])
+    launches = (max(3, args.warmup) + args.steps) * per_step_launches
+    kernel_ms = phases["total_ms"]  # all kernels of one step, no gather
+    # one extra, untimed step with the counting instantiation: the event counts behind the flop figure
+    ctx.set_work_counters(True)
     ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
-    k1.record()
     torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1)
-    launches += 2
+    counters = ctx.last_iod_counters()
+    ctx.set_work_counters(False)
+    launches += per_step_launches
 
     # e2e: host-buffer C-ABI entry (H2D of the pinned inputs + kernels + D2H of the results)
     ctx.fit_full_iod(host_batch, params)
@@ -261,7 +272,7 @@ def main():
         res_host = ctx.fit_full_iod(host_batch, params)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    launches += 2 * (e2e_steps + 1)
+    launches += per_step_launches * (e2e_steps + 1)
     clocks = sampler.stop()
 
     # Kepler leg: 10 M propagate_universal (BASELINE configs[1]), device-resident
@@ -302,6 +313,16 @@ def main():
     if rank == 0:
         flops = algorithmic_flops(counters)
         achieved = flops / (kernel_ms * 1e-3)
+        kernels = {}
+        for kname, ev in KERNEL_EVENTS.items():
+            kms = phases[KERNEL_PHASE[kname]]
+            kfl = algorithmic_flops(counters, ev)
+            kernels[kname] = {"ms": kms, "share_of_step": kms / kernel_ms, "algorithmic_flop": kfl,
+                              "tflops": kfl / (kms * 1e-3) / 1e12, "frac_fp64_peak": kfl / (kms * 1e-3) / fp64_peak}
+        for kname, key in (("scorer_observer_kernel", "observer_ms"), ("triplets_kernel", "triplets_ms"),
+                           ("select_kernel", "select_ms")):
+            kernels[kname] = {"ms": phases[key], "share_of_step": phases[key] / kernel_ms}
+        dom = max(KERNEL_EVENTS, key=lambda k: kernels[k]["ms"])
         n_total_obs = int(batch["mjd_tt"].shape[0])
         alg_bytes = 88.0 * n_total_obs + 96.0 * T + 48.0 * T * K * nn
         kepler_in_iod = counters["scorer_evals"] + counters["kepler_universal_solves"]
@@ -315,10 +336,13 @@ def main():
                     "api": "outfit_b200_fit_full_iod (host buffers, pinned)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None, "kernel": "iod_kernel",
-                         "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flops,
-                         "algorithmic_flop_per_trajectory": flops / T, "libm_calls_per_launch": libm_calls(counters),
+            "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": kernels[dom]["frac_fp64_peak"], "traffic": None, "kernel": dom,
+                         "kernel_ms": kernels[dom]["ms"], "algorithmic_flop_per_launch": kernels[dom]["algorithmic_flop"],
+                         "step": {"achieved": achieved / 1e12, "frac": achieved / fp64_peak, "ms": kernel_ms,
+                                  "algorithmic_flop": flops, "algorithmic_flop_per_trajectory": flops / T,
+                                  "libm_calls": libm_calls(counters)},
+                         "kernels": kernels,
                          "peak_source": "measured live: outfit_b200_measure_fp64_peak (independent DFMA chains, all SMs, CUDA events); MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": 6536.7,
                                  "algorithmic_bytes_per_launch": alg_bytes,

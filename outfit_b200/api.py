@@ -97,6 +97,12 @@ class IodCounters(C.Structure):
         "newton_steps", "sfunct_terms", "scorer_evals", "scorer_newton_steps", "candidates")]
 
 
+class IodPhaseMs(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("observer_ms", "triplets_ms", "roots_ms", "correct_ms", "score_ms",
+                                         "select_ms", "total_ms")] + [("n_chunks", C.c_uint32),
+                                                                      ("kernel_launches", C.c_uint32)]
+
+
 RESULT_DTYPE = np.dtype([
     ("status", "<i4"), ("cause", "<i4"), ("cause_value", "<f8"), ("attempts", "<u8"), ("span", "<f8"),
     ("corrected", "<i4"), ("element_kind", "<i4"), ("epoch", "<f8"), ("elem", "<f8", (6,)),
@@ -110,7 +116,8 @@ ABI_SYMBOLS = [
     "outfit_b200_solver_type_default", "outfit_b200_init", "outfit_b200_destroy",
     "outfit_b200_load_ephemeris", "outfit_b200_fit_full_iod", "outfit_b200_fit_full_iod_device",
     "outfit_b200_observer_cache_device", "outfit_b200_propagate_universal",
-    "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters",
+    "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters", "outfit_b200_last_iod_phase_ms",
+    "outfit_b200_set_work_counters",
     "outfit_b200_measure_fp64_peak",
 ]
 
@@ -148,6 +155,8 @@ def load_library():
     L.outfit_b200_propagate_universal_device.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(SolverType),
                                                          vp, vp, vp]
     L.outfit_b200_last_iod_counters.argtypes = [vp, C.POINTER(IodCounters)]
+    L.outfit_b200_set_work_counters.argtypes = [vp, C.c_int]
+    L.outfit_b200_last_iod_phase_ms.argtypes = [vp, C.POINTER(IodPhaseMs)]
     L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _LIB = L
     return L
@@ -242,6 +251,16 @@ class OutfitB200:
         c = IodCounters()
         self._check(self._L.outfit_b200_last_iod_counters(self._h, C.byref(c)))
         return {n: getattr(c, n) for n, _ in IodCounters._fields_}
+
+    def set_work_counters(self, enabled):
+        """Select the counting (exact work counters) or the plain instantiation of the kernels."""
+        self._check(self._L.outfit_b200_set_work_counters(self._h, 1 if enabled else 0))
+
+    def last_iod_phase_ms(self):
+        """CUDA-event durations (ms) of each kernel of the last full-IOD launch (blocks until done)."""
+        c = IodPhaseMs()
+        self._check(self._L.outfit_b200_last_iod_phase_ms(self._h, C.byref(c)))
+        return {n: getattr(c, n) for n, _ in IodPhaseMs._fields_}
 
     # -- OutfitCache::build ---------------------------------------------------------------------
     def observer_cache_device(self, n, mjd_tt, mjd_ut1, body_fixed, geo_ecl, helio_equ, status=None, stream=0):

@@ -1,0 +1,360 @@
+// dev_correct.cuh -- the f-g correction phase (P2) as one register-resident loop per candidate.
+//
+// Reference behaviour restated here (same operations, same order, same bits as dev_gauss.cuh /
+// dev_kepler.cuh, which remain the readable statement of the algorithm and serve the bulk
+// propagator):
+//   accept_root / positions / Gibbs          gauss.rs:702-870
+//   pos_and_vel_correction                   gauss.rs:1284-1418
+//   velocity_correction_with_guess           kepler/velocity.rs:94-211
+//   UniversalKeplerParams::solve (Newton)    kepler/newton_solver.rs:151-352
+//   s_funct                                  kepler/stumpff.rs:78-297
+//   eccentricity_control                     orb_elem.rs:257-301
+//
+// Why a second statement: ncu (profiles/r01d) showed the first version of this phase bound by
+// fixed-latency dependency stalls (37 %) and local-memory round trips (12.7 % of the warp
+// instructions were LDL/STL: structs handed by reference to un-inlined functions), with FP64
+// instructions only 44 % of the instruction stream.  Here
+//   * everything is inlined and every per-candidate quantity lives in registers, except the
+//     loop-invariant geometry (R, S, S^-1, tau, a, b: 34 doubles) which is staged in shared memory
+//     [slot][thread] (conflict-free 8-byte lanes) and read once per f-g iteration;
+//   * divisions that share a denominator use one correctly rounded reciprocal + Markstein's exact
+//     correction (q0 = a*y; r = fma(-n, q0, a); q = fma(r, y, q0)), which returns RN(a/n) -- the
+//     same bits as the division -- at 3 FP64 instructions per extra numerator; divisions by
+//     compile-time constants use the same form with a literal reciprocal;
+//   * the Stumpff series computes the (loop-independent) term ratios beta/c_k four terms ahead of
+//     the running product, so the dependent chain per term is one DMUL + one DADD;
+//   * the work counters are compiled in only for the counting instantiation (COUNT = true).
+#pragma once
+#include "dev_iod.cuh"
+
+namespace ofb {
+
+constexpr int kCorrectThreads = 128;
+// shared-memory slots per thread (doubles)
+enum {
+  SL_R0 = 0, SL_R1 = 3, SL_R2 = 6, SL_S0 = 9, SL_S1 = 12, SL_S2 = 15, SL_I0 = 18, SL_I1 = 21, SL_I2 = 24,
+  SL_TAU1 = 27, SL_TAU3 = 28, SL_A0 = 29, SL_A2 = 30, SL_B0 = 31, SL_B2 = 32, SL_T0 = 33, SL_T1 = 34, SL_T2 = 35,
+  SL_COUNT = 36
+};
+constexpr size_t kCorrectSmemBytes = (size_t)SL_COUNT * kCorrectThreads * sizeof(double);
+
+// RN(a / n) from y = RN(1 / n) (Markstein); a and n must be finite, n != 0, no over/underflow
+__device__ __forceinline__ double div_mk(double a, double n, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double r = __fma_rn(-n, q0, a);
+  return __fma_rn(r, y, q0);
+}
+// true when the Markstein form may replace a division by n (sane magnitude; everything on this path
+// is AU / day scale, the guard only routes pathological values to the IEEE division)
+__device__ __forceinline__ bool mk_ok(double n) { return fabs(n) > 1e-100 && fabs(n) < 1e100; }
+
+struct WorkC {
+  unsigned roots_accepted, fg_iterations, kepler_solves, newton_steps, sfunct_terms;
+};
+
+// ---- s_funct, |beta| >= 100 (rare): halving + duplication, as stumpff.rs:200-297 ----------------
+__device__ __noinline__ void s_funct_large(double psi, double alpha, double beta, double *out4, unsigned *terms) {
+  const double tol = 100.0 * kEps, big = 1.0 / kEps;
+  double rp = psi, rb = beta;
+  int halvings = 0;
+  while (fabs(rb) >= 100.0 && halvings < 30) { rp *= 0.5; rb *= 0.25; ++halvings; }
+  double s0 = 1.0, s1 = rp, t0 = 1.0, t1 = rp;
+  unsigned n = 0;
+  for (int k = 1; k <= 70; ++k) {
+    ++n;
+    t0 *= rb / ((double)(2 * k - 1) * (double)(2 * k));
+    s0 += t0;
+    if (fabs(t0) < tol || fabs(t0) > big) break;
+  }
+  for (int k = 1; k <= 70; ++k) {
+    ++n;
+    t1 *= rb / ((double)(2 * k) * (double)(2 * k + 1));
+    s1 += t1;
+    if (fabs(t1) < tol || fabs(t1) > big) break;
+  }
+  for (int h = 0; h < halvings; ++h) {
+    const double c = s0, sn = s1;
+    s0 = 2.0 * c * c - 1.0;
+    s1 = 2.0 * c * sn;
+  }
+  out4[0] = s0; out4[1] = s1; out4[2] = (s0 - 1.0) / alpha; out4[3] = (s1 - psi) / alpha;
+  *terms += n;
+}
+
+// series tail beyond the 8 unrolled terms (it >= 8): table reciprocals up to kSeriesTable, then IEEE
+__device__ __noinline__ void s_funct_tail(double beta, double *st /* s2,t2,s3,t3 in/out */, unsigned *terms) {
+  const double tol = 100.0 * kEps, big = 1.0 / kEps;
+  double s2 = st[0], t2 = st[1], s3 = st[2], t3 = st[3];
+  double d = 3.0 + 2.0 * 8;
+  unsigned n = 0;
+  for (int it = 8; it < 70; ++it) {
+    ++n;
+    double q2, q3;
+    if (it < kSeriesTable) {
+      q2 = div_by_const(beta, d * (d + 1.0), c_series_rcp[2 * it]);
+      q3 = div_by_const(beta, (d + 1.0) * (d + 2.0), c_series_rcp[2 * it + 1]);
+    } else {
+      q2 = beta / (d * (d + 1.0));
+      q3 = beta / ((d + 1.0) * (d + 2.0));
+    }
+    t2 *= q2; s2 += t2;
+    t3 *= q3; s3 += t3;
+    const double a2 = fabs(t2), a3 = fabs(t3);
+    if ((a2 < tol && a3 < tol) || a2 > big || a3 > big) break;
+    d += 2.0;
+  }
+  st[0] = s2; st[1] = t2; st[2] = s3; st[3] = t3;
+  *terms += n;
+}
+
+// denominators of the first 8 series terms: (2k+3)(2k+4) and (2k+4)(2k+5)
+#define OFB_SERIES_TERM(C2, C3)                                                     \
+  {                                                                                 \
+    t2 = t2 * q2_##C2; s2 = s2 + t2;                                                \
+    t3 = t3 * q3_##C3; s3 = s3 + t3;                                                \
+    if (COUNT) ++terms;                                                             \
+    const double a2 = fabs(t2), a3 = fabs(t3);                                      \
+    if ((a2 < tol && a3 < tol) || a2 > big || a3 > big) goto series_done;           \
+  }
+#define OFB_SERIES_Q(C2, C3)                                                        \
+  const double q2_##C2 = div_mk(beta, (double)C2, 1.0 / (double)C2);                \
+  const double q3_##C3 = div_mk(beta, (double)C3, 1.0 / (double)C3);
+
+template <bool COUNT>
+__device__ __forceinline__ void s_funct_fast(double psi, double alpha, double &s0, double &s1, double &s2o,
+                                             double &s3o, unsigned &terms) {
+  const double tol = 100.0 * kEps, big = 1.0 / kEps;
+  if (psi == 0.0) { s0 = 1.0; s1 = 0.0; s2o = 0.0; s3o = 0.0; return; }
+  const double psi2 = psi * psi;
+  const double beta = alpha * psi2;
+  if (!(fabs(beta) < 100.0)) {
+    double o[4];
+    unsigned n = 0;
+    s_funct_large(psi, alpha, beta, o, &n);
+    if (COUNT) terms += n;
+    s0 = o[0]; s1 = o[1]; s2o = o[2]; s3o = o[3];
+    return;
+  }
+  double s2 = 0.5 * psi2, t2 = s2;
+  double s3 = div_mk(s2 * psi, 3.0, 1.0 / 3.0), t3 = s3;
+  {
+    OFB_SERIES_Q(12, 20) OFB_SERIES_Q(30, 42) OFB_SERIES_Q(56, 72) OFB_SERIES_Q(90, 110)
+    OFB_SERIES_TERM(12, 20) OFB_SERIES_TERM(30, 42) OFB_SERIES_TERM(56, 72) OFB_SERIES_TERM(90, 110)
+  }
+  {
+    OFB_SERIES_Q(132, 156) OFB_SERIES_Q(182, 210) OFB_SERIES_Q(240, 272) OFB_SERIES_Q(306, 342)
+    OFB_SERIES_TERM(132, 156) OFB_SERIES_TERM(182, 210) OFB_SERIES_TERM(240, 272) OFB_SERIES_TERM(306, 342)
+  }
+  {
+    double st[4] = {s2, t2, s3, t3};
+    unsigned n = 0;
+    s_funct_tail(beta, st, &n);
+    if (COUNT) terms += n;
+    s2 = st[0]; s3 = st[2];
+  }
+series_done:
+  s1 = psi + alpha * s3;
+  s0 = 1.0 + alpha * s2;
+  s2o = s2;
+  s3o = s3;
+}
+#undef OFB_SERIES_TERM
+#undef OFB_SERIES_Q
+
+// cold-start guess (first f-g iteration of a root only): scalars by value, no stack traffic in the caller
+__device__ __noinline__ double prelim_kepuni_v(double dt, double r0, double sig0, double alpha, double e0,
+                                               double convergency) {
+  KepIn kp;
+  kp.dt = dt; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
+  kp.convergency = convergency; kp.max_iter_prelim = 20; kp.parabolic_newton = 0;
+  return prelim_kepuni(kp);
+}
+
+// Newton on the universal Kepler equation (newton_solver.rs:240-352); one s_funct site.
+// Returns ok; on success psi and (s2, s3) of the accepted evaluation.
+template <bool COUNT>
+__device__ __forceinline__ bool kepuni_newton_fast(double dt, double r0, double sig0, double alpha, double convergency,
+                                                   double &psi, double &s2, double &s3, WorkC &w) {
+  const double sdt = kGaussK * dt;
+  const double tol = 10.0 * kEps * (1.0 + fabs(sdt));
+  bool final_eval = false;
+  int it = 0;
+  for (;;) {
+    if (!final_eval) {
+      if (it >= 50) return false;
+      ++it;
+      if (COUNT) ++w.newton_steps;
+      if (!isfinite(psi)) { psi = 0.5; continue; }
+    }
+    double s0, s1;
+    s_funct_fast<COUNT>(psi, alpha, s0, s1, s2, s3, w.sfunct_terms);
+    if (final_eval) return true;
+    const double res = r0 * s1 + sig0 * s2 + s3 - sdt;
+    const double der = r0 * s0 + sig0 * s1 + s2;
+    if (fabs(res) <= tol) return true;
+    if (!isfinite(der) || fabs(der) < 10.0 * kEps) { psi *= 0.5; continue; }
+    const double mx = 2.0 * (1.0 + fabs(psi));
+    const double step = clampd(-res / der, -mx, mx);
+    double cand = psi + step;
+    if (cand * psi < 0.0) cand = 0.5 * psi;
+    psi = cand;
+    const double sa = fabs(step);
+    if (sa <= convergency) return true;  // (s2, s3) of the evaluation before the step, like the reference
+    if (sa <= convergency * (1.0 + fabs(psi))) final_eval = true;
+  }
+}
+
+// middle state shared by the two sides of one f-g iteration (eccentricity_control + mid_state)
+struct MidC {
+  double r2, inv_r2, sig0, hn, ecc, alpha;
+  bool defined, accepted;
+};
+__device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double ecc_max) {
+  MidC m;
+  const double v2 = dot(v, v);
+  const double dist = norm(r);
+  const V3 h = cross(r, v);
+  const double h2 = dot(h, h);
+  m.hn = sqrt(h2);
+  m.defined = !(m.hn == 0.0);
+  const V3 vxh = cross(v, h);
+  const double inv_mu = 1.0 / kMu;
+  const double inv_d = 1.0 / dist;
+  const V3 lenz = V3{vxh.x * inv_mu - r.x * inv_d, vxh.y * inv_mu - r.y * inv_d, vxh.z * inv_mu - r.z * inv_d};
+  m.ecc = norm(lenz);
+  const double peri = h2 / (kMu * (1.0 + m.ecc));
+  const double energy = v2 / 2.0 - (mk_ok(dist) ? div_mk(kMu, dist, inv_d) : kMu / dist);
+  m.accepted = (m.ecc < ecc_max) && (peri < peri_max);
+  m.r2 = dist;
+  m.inv_r2 = inv_d;
+  m.sig0 = div_mk(dot(r, v), kGaussK, 1.0 / kGaussK);
+  m.alpha = div_mk(2.0 * energy, kMu, 1.0 / kMu);
+  return m;
+}
+
+struct SideC {
+  bool ok;
+  V3 v;
+  double f, g, chi;
+};
+template <bool COUNT>
+__device__ __forceinline__ SideC correction_side(V3 x1, V3 x2, const MidC &m, double dt, bool has_guess, double chi_guess,
+                                                 double eps, WorkC &w) {
+  SideC o;
+  o.ok = false;
+  if (COUNT) ++w.kepler_solves;
+  double psi = has_guess ? chi_guess : prelim_kepuni_v(dt, m.r2, m.sig0, m.alpha, m.ecc, eps);
+  double s2, s3;
+  if (!kepuni_newton_fast<COUNT>(dt, m.r2, m.sig0, m.alpha, eps, psi, s2, s3, w)) return o;
+  const double f = 1.0 - (mk_ok(m.r2) ? div_mk(s2, m.r2, m.inv_r2) : s2 / m.r2);
+  const double g = dt - div_mk(s3, kGaussK, 1.0 / kGaussK);
+  const double ga = fabs(g);
+  if (!isfinite(ga) || ga < 100.0 * kEps * (1.0 + fabs(dt))) return o;
+  const double nx = (-f) * x2.x + x1.x, ny = (-f) * x2.y + x1.y, nz = (-f) * x2.z + x1.z;
+  if (mk_ok(g)) {
+    const double yg = 1.0 / g;
+    o.v = V3{div_mk(nx, g, yg), div_mk(ny, g, yg), div_mk(nz, g, yg)};
+  } else {
+    o.v = V3{nx / g, ny / g, nz / g};
+  }
+  o.f = f; o.g = g; o.chi = psi;
+  o.ok = true;
+  return o;
+}
+
+// shared-memory view of this thread's loop-invariant geometry
+// (volatile: keeps the compiler from hoisting these loop-invariant loads into registers, which is
+// exactly the register pressure -- and the spills -- the staging exists to avoid)
+struct GeoSm {
+  const volatile double *p;  // &smem[threadIdx.x]
+  __device__ __forceinline__ double at(int slot) const { return p[slot * kCorrectThreads]; }
+  __device__ __forceinline__ V3 v3(int slot) const { return V3{at(slot), at(slot + 1), at(slot + 2)}; }
+};
+
+// positions_from_c with c1 = -1 (gauss.rs:702): -(x / -1) == x exactly, so rho1 = S^-1 row 1 . gc
+__device__ __forceinline__ bool positions_c(const GeoSm &G, double c0, double c2, double min_rho2, V3 &p0, V3 &p1,
+                                            V3 &p2, double &epoch) {
+  const V3 R0 = G.v3(SL_R0), R1 = G.v3(SL_R1), R2 = G.v3(SL_R2);
+  const V3 gc = V3{(R0.x * c0 + R1.x * -1.0) + R2.x * c2, (R0.y * c0 + R1.y * -1.0) + R2.y * c2,
+                   (R0.z * c0 + R1.z * -1.0) + R2.z * c2};
+  const double rho0 = -(dot(G.v3(SL_I0), gc) / c0);
+  const double rho1 = dot(G.v3(SL_I1), gc);
+  const double rho2 = -(dot(G.v3(SL_I2), gc) / c2);
+  if (rho1 < min_rho2) return false;
+  p0 = R0 + rho0 * G.v3(SL_S0);
+  p1 = R1 + rho1 * G.v3(SL_S1);
+  p2 = R2 + rho2 * G.v3(SL_S2);
+  epoch = G.at(SL_T1) - div_mk(rho1, kVlightAu, 1.0 / kVlightAu);
+  return true;
+}
+
+// accept_root (gauss.rs:816-870): positions, light-time epoch, Gibbs velocity, acceptability.
+template <bool COUNT>
+__device__ __forceinline__ bool accept_root_fast(const GeoSm &G, const IodDevParams &P, double root, V3 &p0, V3 &p1,
+                                                 V3 &p2, V3 &vel, double &epoch, MidC &mid, WorkC &w) {
+  const double r2m3 = 1.0 / ((root * root) * root);
+  if (!positions_c(G, G.at(SL_A0) + G.at(SL_B0) * r2m3, G.at(SL_A2) + G.at(SL_B2) * r2m3, P.min_rho2_au, p0, p1, p2, epoch))
+    return false;
+  {
+    const V3 pos[3] = {p0, p1, p2};
+    vel = gibbs_velocity(pos, G.at(SL_TAU1), G.at(SL_TAU3));
+  }
+  mid = middle_state(p1, vel, P.max_perihelion_au, P.max_ecc);
+  if (!mid.defined || !mid.accepted) return false;
+  if (COUNT) ++w.roots_accepted;
+  return true;
+}
+
+// pos_and_vel_correction (gauss.rs:1284-1418) on an accepted root.  false <=> None (the caller keeps
+// the accepted state as a PrelimOrbit); true: (p1, vel, ep) hold the corrected state.
+template <bool COUNT>
+__device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevParams &P, V3 &p0, V3 &p1, V3 &p2,
+                                                   V3 &vel, MidC &mid, double &ep, WorkC &w) {
+  const double dt01 = G.at(SL_T0) - G.at(SL_T1), dt21 = G.at(SL_T2) - G.at(SL_T1);
+  if (fabs(dt01) <= kEps || fabs(dt21) <= kEps) return false;
+  ep = 0.0;
+  bool has_chi = false;
+  double chi01 = 0.0, chi21 = 0.0;
+#pragma unroll 1
+  for (unsigned it = 0; it < P.newton_max_it; ++it) {
+    if (COUNT) ++w.fg_iterations;
+    // velocity_correction_with_guess guards (velocity.rs:105-123), identical for both sides
+    const bool sides_ok = isfinite(mid.hn) && !(mid.hn <= 1e6 * kEps) && mid.defined;
+    SideC L, Rr;
+    L.ok = false; Rr.ok = false;
+    if (sides_ok) {
+      L = correction_side<COUNT>(p0, p1, mid, dt01, has_chi, chi01, P.kepler_eps, w);
+      Rr = correction_side<COUNT>(p2, p1, mid, dt21, has_chi, chi21, P.kepler_eps, w);
+    }
+    if (!(L.ok && Rr.ok)) {
+      // nothing was updated: every remaining iteration would repeat this one exactly
+      if (!has_chi) {
+        if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
+        break;
+      }
+      continue;
+    }
+    has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
+    const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
+    const double fl = L.f * Rr.g - Rr.f * L.g;
+    if (!isfinite(fl) || fabs(fl) < kEps) continue;
+    const double inv_f = 1.0 / fl;
+    V3 n0, n1, n2;
+    double nep;
+    if (!positions_c(G, Rr.g * inv_f, -L.g * inv_f, P.min_rho2_au, n0, n1, n2, nep)) continue;
+    const MidC nm = middle_state(n1, nv, P.max_perihelion_au, P.max_ecc);
+    if (!nm.defined || !nm.accepted) return false;
+    const double denom = sqrt((dot(n0, n0) + dot(n1, n1)) + dot(n2, n2));
+    if (!isfinite(denom) || denom <= kEps) continue;
+    const V3 d0 = n0 - p0, d1 = n1 - p1, d2 = n2 - p2;
+    const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
+    p0 = n0; p1 = n1; p2 = n2;
+    vel = nv;
+    ep = nep;
+    mid = nm;
+    if (rel <= P.newton_eps) break;
+  }
+  return true;
+}
+
+}  // namespace ofb

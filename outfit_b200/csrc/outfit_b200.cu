@@ -14,9 +14,11 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/outfit_b200.h"
 #include "dev_iod.cuh"
+#include "dev_correct.cuh"
 #include "dev_geometry.cuh"
 
 using namespace ofb;
@@ -179,47 +181,108 @@ roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
 }
 
 // ---- P2: roots -> accepted state, f-g correction ---------------------------------------------------
+// One lane per candidate, register-resident f-g loop (dev_correct.cuh).  The triplet geometry is
+// rebuilt here (6 sincos + the cofactor inverse: ~3 % of this phase) instead of being carried from P1
+// through HBM (144 B per candidate).
 #ifndef OUTFIT_CORRECT_BPS
 #define OUTFIT_CORRECT_BPS 4
 #endif
-__global__ void __launch_bounds__(kCandThreads, OUTFIT_CORRECT_BPS)
+template <bool COUNT>
+__global__ void __launch_bounds__(kCorrectThreads, OUTFIT_CORRECT_BPS)
 correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
-  Work w;
-  memset(&w, 0, sizeof w);
+  extern __shared__ __align__(16) double geo_sm[];
+  double *my = geo_sm + threadIdx.x;
+  const unsigned long long cid = (unsigned long long)blockIdx.x * kCorrectThreads + threadIdx.x;
+  WorkC w;
+  w.roots_accepted = 0; w.fg_iterations = 0; w.kepler_solves = 0; w.newton_steps = 0; w.sfunct_terms = 0;
   unsigned long long tr;
   unsigned r, m;
   if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
     int kind = 0;
     const unsigned n = S.code[cid] == 0 ? S.nroots[cid] : 0u;
     if (n > 0) {
-      Triplet g;
-      unsigned idx[3];
-      load_triplet(B, P, S, tr, r, m, g, idx);
-      GaussGeom gm;
-      gauss_geometry(g, gm);
+      // ---- triplet + noise -> unit vectors, heliocentric observer positions (shared memory) ----
+      const unsigned packed = S.trip[tr * P.max_triplets + r];
+      const unsigned long long o0 = B.traj_offset[tr];
+      const double *z = m > 0 ? B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        const unsigned long long gI = o0 + ((packed >> (20 - 10 * c)) & 1023u);
+        double ra = __ldg(B.ra + gI), dec = __ldg(B.dec + gI);
+        if (m > 0) {
+          ra = ra + __ldg(z + c) * (__ldg(B.sigma_ra + gI) * P.noise_scale);
+          dec = dec + __ldg(z + 3 + c) * (__ldg(B.sigma_dec + gI) * P.noise_scale);
+        }
+        double sr, cr, sd, cd;
+        sincos(ra, &sr, &cr);
+        sincos(dec, &sd, &cd);
+        my[(SL_S0 + 3 * c + 0) * kCorrectThreads] = cr * cd;
+        my[(SL_S0 + 3 * c + 1) * kCorrectThreads] = sr * cd;
+        my[(SL_S0 + 3 * c + 2) * kCorrectThreads] = sd;
+        my[(SL_R0 + 3 * c + 0) * kCorrectThreads] = __ldg(B.helio + gI);
+        my[(SL_R0 + 3 * c + 1) * kCorrectThreads] = __ldg(B.helio + B.n_obs + gI);
+        my[(SL_R0 + 3 * c + 2) * kCorrectThreads] = __ldg(B.helio + 2 * B.n_obs + gI);
+        my[(SL_T0 + c) * kCorrectThreads] = __ldg(B.mjd_tt + gI);
+      }
+      const GeoSm G{my};
+      {
+        // gauss_prelim (gauss.rs:464-549): tau, a, b, cofactor inverse (rows of S^-1)
+        const double t0 = G.at(SL_T0), t1 = G.at(SL_T1), t2 = G.at(SL_T2);
+        const double tau1 = kGaussK * (t0 - t1), tau3 = kGaussK * (t2 - t1);
+        const double tau13 = tau3 - tau1;
+        const double a0 = tau3 / tau13, a2 = -(tau1 / tau13);
+        my[SL_TAU1 * kCorrectThreads] = tau1;
+        my[SL_TAU3 * kCorrectThreads] = tau3;
+        my[SL_A0 * kCorrectThreads] = a0;
+        my[SL_A2 * kCorrectThreads] = a2;
+        my[SL_B0 * kCorrectThreads] = a0 * (tau13 * tau13 - tau3 * tau3) / 6.0;
+        my[SL_B2 * kCorrectThreads] = a2 * (tau13 * tau13 - tau1 * tau1) / 6.0;
+        const V3 S0 = G.v3(SL_S0), S1 = G.v3(SL_S1), S2 = G.v3(SL_S2);
+        const double m11 = S0.x, m12 = S1.x, m13 = S2.x, m21 = S0.y, m22 = S1.y, m23 = S2.y, m31 = S0.z, m32 = S1.z, m33 = S2.z;
+        const double mi1 = m22 * m33 - m32 * m23, mi2 = m21 * m33 - m31 * m23, mi3 = m21 * m32 - m31 * m22;
+        const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;  // != 0: P1 accepted this candidate
+        const double num[9] = {mi1, m13 * m32 - m33 * m12, m12 * m23 - m22 * m13, -mi2, m11 * m33 - m31 * m13,
+                               m13 * m21 - m23 * m11, mi3, m12 * m31 - m32 * m11, m11 * m22 - m21 * m12};
+        const bool mk = mk_ok(det);
+        const double yd = 1.0 / det;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) my[(SL_I0 + q) * kCorrectThreads] = mk ? div_mk(num[q], det, yd) : num[q] / det;
+      }
       unsigned n_solutions = 0;
 #pragma unroll 1
       for (unsigned k = 0; k < n; ++k) {
-        V3 rr, vv;
+        V3 p0, p1, p2, vel;
         double ep;
-        const int sk = solve_root(g, gm, P, S.roots[(size_t)k * S.n_cand + cid], rr, vv, ep, w);
-        if (sk == 0) continue;
+        MidC mid;
+        if (!accept_root_fast<COUNT>(G, P, S.roots[(size_t)k * S.n_cand + cid], p0, p1, p2, vel, ep, mid, w)) continue;
         ++n_solutions;
         // prelim_orbit (gauss.rs:1238-1247): first CorrectedOrbit in discovery order, else first pushed
-        if (sk == 2 || kind == 0) {
-          kind = sk;
-          S.state[0 * S.n_cand + cid] = rr.x; S.state[1 * S.n_cand + cid] = rr.y; S.state[2 * S.n_cand + cid] = rr.z;
-          S.state[3 * S.n_cand + cid] = vv.x; S.state[4 * S.n_cand + cid] = vv.y; S.state[5 * S.n_cand + cid] = vv.z;
+        const bool first = kind == 0;
+        if (first) {
+          kind = 1;
+          S.state[0 * S.n_cand + cid] = p1.x; S.state[1 * S.n_cand + cid] = p1.y; S.state[2 * S.n_cand + cid] = p1.z;
+          S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
           S.state[6 * S.n_cand + cid] = ep;
-          if (sk == 2) break;
+        }
+        if (fg_correction_fast<COUNT>(G, P, p0, p1, p2, vel, mid, ep, w)) {
+          kind = 2;
+          S.state[0 * S.n_cand + cid] = p1.x; S.state[1 * S.n_cand + cid] = p1.y; S.state[2 * S.n_cand + cid] = p1.z;
+          S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
+          S.state[6 * S.n_cand + cid] = ep;
+          break;
         }
         if (n_solutions >= P.max_tested_solutions) break;
       }
     }
     S.state_kind[cid] = kind;
   }
-  flush_work(w, work_counters);
+  if (COUNT) {
+    Work wk;
+    memset(&wk, 0, sizeof wk);
+    wk.roots_accepted = w.roots_accepted; wk.fg_iterations = w.fg_iterations; wk.kepler_solves = w.kepler_solves;
+    wk.newton_steps = w.newton_steps; wk.sfunct_terms = w.sfunct_terms;
+    flush_work(wk, work_counters);
+  }
 }
 
 __device__ __forceinline__ void state_to_orbit(const IodScratch &S, unsigned long long cid, int state_kind, Orbit &orb) {
@@ -505,6 +568,12 @@ struct OutfitCtx {
   void *h_scratch = nullptr;
   void *iod_scratch = nullptr;  // per-candidate arrays of the phase pipeline
   size_t iod_scratch_bytes = 0;
+  // CUDA events bracketing every phase of the last full-IOD launch (outfit_b200_last_iod_phase_ms)
+  std::vector<cudaEvent_t> phase_ev;
+  unsigned phase_chunks = 0;
+  unsigned phase_observer_kernels = 0;
+  bool phase_valid = false;
+  bool count_work = true;  // work counters on (outfit_b200_set_work_counters)
 };
 
 static int fail(OutfitCtx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -606,6 +675,7 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->iod_scratch) cudaFree(ctx->iod_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -691,6 +761,18 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   int *d_status = reinterpret_cast<int *>(d_scorer + planes * n);
   const int tpb = 128;
   const unsigned gblocks = (unsigned)((n + tpb - 1) / tpb);
+  // phase events: [0] start, [1] after the observer kernels, then 5 per chunk (after each phase)
+  ctx->phase_valid = false;
+  size_t ev_next = 0;
+  auto mark = [&]() {
+    if (ev_next == ctx->phase_ev.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      ctx->phase_ev.push_back(e);
+    }
+    cudaEventRecord(ctx->phase_ev[ev_next++], stream);
+  };
+  mark();
   if (!have_cache) {
     double *geo = d_scorer + 3 * n, *helio = d_scorer + 6 * n;
     if (n) observer_cache_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, b->mjd_ut1, b->observer_body_fixed, geo, helio, d_status);
@@ -698,6 +780,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     d_helio = helio;
   }
   if (n) scorer_observer_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, d_geo, d_scorer, d_status);
+  mark();
 
   const IodDevParams P = to_dev_params(*params);
   const unsigned M = P.n_noise + 1;
@@ -716,6 +799,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   if (smem0 > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");
   CK(cudaFuncSetAttribute(triplets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
   CK(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), stream));
+  unsigned n_chunks = 0;
   for (unsigned long long t0 = 0; t0 < b->n_traj; t0 += chunk) {
     const unsigned long long tn = b->n_traj - t0 < chunk ? b->n_traj - t0 : chunk;
     IodBatchDev B;
@@ -742,12 +826,22 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     const unsigned tblocks = (unsigned)((tn + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
     triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+    mark();
     roots_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
-    correct_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    mark();
+    if (ctx->count_work) correct_kernel<true><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
+    else correct_kernel<false><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
+    mark();
     score_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    mark();
     select_kernel<<<tblocks, kWarpsPerBlock * 32, 0, stream>>>(B, P, S, d_out + t0);
+    mark();
+    ++n_chunks;
   }
   CK(cudaGetLastError());
+  ctx->phase_chunks = n_chunks;
+  ctx->phase_observer_kernels = n ? (have_cache ? 1u : 2u) : 0u;
+  ctx->phase_valid = ev_next == 2 + 5 * (size_t)n_chunks;
   return OUTFIT_OK;
 }
 
@@ -848,6 +942,35 @@ extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *
   out->gauss_solves = h[1]; out->aberth_sweeps = h[2]; out->roots_accepted = h[3]; out->fg_iterations = h[4];
   out->kepler_universal_solves = h[5]; out->newton_steps = h[6]; out->sfunct_terms = h[7];
   out->scorer_evals = h[8]; out->scorer_newton_steps = h[9]; out->candidates = h[10];
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_set_work_counters(OutfitCtx *ctx, int enabled) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  ctx->count_work = enabled != 0;
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_last_iod_phase_ms(OutfitCtx *ctx, OutfitIodPhaseMs *out) {
+  if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
+  memset(out, 0, sizeof *out);
+  if (!ctx->phase_valid) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "no full-IOD launch recorded on this context");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n_ev = 2 + 5 * (size_t)ctx->phase_chunks;
+  CK(cudaEventSynchronize(ctx->phase_ev[n_ev - 1]));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->phase_ev[0], ctx->phase_ev[1]));
+  out->observer_ms = ms;
+  float *acc[5] = {&out->triplets_ms, &out->roots_ms, &out->correct_ms, &out->score_ms, &out->select_ms};
+  for (unsigned c = 0; c < ctx->phase_chunks; ++c)
+    for (int q = 0; q < 5; ++q) {
+      CK(cudaEventElapsedTime(&ms, ctx->phase_ev[1 + 5 * c + q], ctx->phase_ev[2 + 5 * c + q]));
+      *acc[q] += ms;
+    }
+  CK(cudaEventElapsedTime(&ms, ctx->phase_ev[0], ctx->phase_ev[n_ev - 1]));
+  out->total_ms = ms;
+  out->n_chunks = ctx->phase_chunks;
+  out->kernel_launches = ctx->phase_chunks * 5u + ctx->phase_observer_kernels;
   return OUTFIT_OK;
 }
 

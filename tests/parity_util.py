@@ -33,7 +33,8 @@ def oracle_floor(O, synth, batch, et, op, base):
         ob["dec"] = np.nextafter(ob["dec"], sgn_dec)
         pert = O.fit_full_iod(ob, et, op, n_threads=0)
         same = (pert["status"] == 0) & (base["status"] == 0) & (pert["realization"] == base["realization"]) & \
-               (pert["triplet_idx"] == base["triplet_idx"]).all(axis=1)
+               (pert["triplet_idx"] == base["triplet_idx"]).all(axis=1) & \
+               (np.abs(pert["epoch"] - base["epoch"]) <= 1e-8)  # an f-g loop that commits or not (epoch 0.0 quirk)
         e = np.where(same, elem_err(pert["elem"], base["elem"]), np.inf)
         r = np.where(same, np.abs(pert["rms"] - base["rms"]) / np.maximum(np.abs(base["rms"]), 1e-300), np.inf)
         ef = np.maximum(ef, e)

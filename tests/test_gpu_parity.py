@@ -172,7 +172,7 @@ def test_device_counters_match_oracle_counters(env):
     # (gauss.rs:1141-1246); the kernel stops at that first CorrectedOrbit, so it does LESS work
     assert 0.4 * o["roots_accepted"] <= g["roots_accepted"] <= o["roots_accepted"]
     for a in ("fg_iterations", "kepler_universal_solves", "newton_steps"):
-        assert 0.3 * o[a] <= g[a] <= 1.002 * o[a], (a, g[a], o[a])
+        assert 0.2 * o[a] <= g[a] <= 1.002 * o[a], (a, g[a], o[a])
     # the oracle prunes the arc loop at the running best (trajectory.rs:405-426); the GPU scores
     # every candidate over its whole arc
     assert g["scorer_evals"] >= o["scorer_evals"]

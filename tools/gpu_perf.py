@@ -9,6 +9,7 @@ nobs = 12 if os.environ.get("PERF_RAGGED") is None else (8, 30)
 table = synth.make_ephemeris_table()
 batch = synth.make_trajectories(T, nobs, seed=20261018, table=table, max_triplets=K, n_noise=nn)
 ctx = OutfitB200(0); ctx.load_ephemeris(table)
+ctx.set_work_counters(os.environ.get("PERF_COUNT", "0") == "1")
 kw = dict(n_noise_realizations=nn, noise_scale=1.1, max_triplets=K)
 params = IODParams.builder(**kw)
 dev = torch.device("cuda")
@@ -24,6 +25,8 @@ for _ in range(2): ctx.fit_full_iod_device(devb, params, d_out, stream=s)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 2
 res = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+ph = ctx.last_iod_phase_ms()
+print("   phases ms:", " ".join(f"{k[:-3]}={v:.2f}" for k, v in ph.items() if k.endswith("_ms")))
 print(f"LIB={os.environ.get('OUTFIT_B200_LIB','default')} T={T} {ms:.1f} ms  {T/ms*1e3:.0f} traj/s  ok={np.mean(res['status']==0):.4f}")
 if os.environ.get("PERF_PARITY", "1") == "1":
     from oracle import binding as O
