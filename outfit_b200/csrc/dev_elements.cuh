@@ -125,7 +125,7 @@ struct ScoreOrbit {
   V3 F, G;             // equinoctial frame vectors rotated to equatorial J2000
   bool elliptic;
 };
-__device__ __noinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
+__device__ __forceinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
   ScoreOrbit s;
   const double e2 = q.h * q.h + q.k * q.k;
   s.elliptic = !(sqrt(e2) >= 1.0);
@@ -145,10 +145,12 @@ __device__ __noinline__ ScoreOrbit make_score_orbit(const Equinoctial &q) {
 }
 
 // Normalised squared residual of one observation; false <=> the reference returns Err.
-__device__ __noinline__ bool ephemeris_error(const ScoreOrbit &s, double t_obs, double ra_obs,
+// COUNT = false compiles the work counters out (w is then untouched).
+template <bool COUNT>
+__device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_obs, double ra_obs,
                                                 double dec_obs, double cos_dec_obs, double sig_ra,
                                                 double sig_dec, V3 obs_equ, double &chi2, Work &w) {
-  ++w.scorer_evals;
+  if (COUNT) ++w.scorer_evals;
   double lam1 = rem_euclid(s.lambda + s.n * ((t_obs - s.epoch) - 0.0), kTwoPi);
   if (lam1 < s.lon_peri) lam1 += kTwoPi;
   // generalised Kepler equation F - k sin F + h cos F = lambda  (roots 0.0.8 Newton, eps 100 ulp, 25 its)
@@ -160,7 +162,7 @@ __device__ __noinline__ bool ephemeris_error(const ScoreOrbit &s, double t_obs, 
   for (;;) {
     sincos(x, &sF, &cF);  // the only sincos site: also evaluates at the accepted root
     if (last) break;
-    ++w.scorer_newton;
+    if (COUNT) ++w.scorer_newton;
     const double f = x - s.k * sF + s.h * cF - lam1;
     const double d = 1.0 - s.k * cF - s.h * sF;
     if (fabs(f) < eps) break;

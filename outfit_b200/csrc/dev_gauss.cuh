@@ -37,15 +37,35 @@ __device__ __forceinline__ Cx cx_mul(Cx a, Cx b) {
   return Cx{__dsub_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im)),
             __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re))};
 }
+// Two quotients over one denominator n: one correctly rounded reciprocal y = RN(1/n) and Markstein's
+// correction (q0 = a*y; r = fma(-n, q0, a); q = fma(r, y, q0)) give RN(a/n), the bits of the IEEE
+// division, for finite operands of sane magnitude; anything else (a vanished or overflowed
+// denominator: coincident iterates, the crate's `Failed` path) takes the IEEE divisions.
+__device__ __noinline__ void div2_ieee(double a, double b, double n, double *out) {
+  out[0] = __ddiv_rn(a, n);
+  out[1] = __ddiv_rn(b, n);
+}
+__device__ __forceinline__ Cx div2_same_denominator(double a, double b, double n) {
+  const double an = fabs(n);
+  if (an > 1e-200 && an < 1e200) {  // (a non-finite numerator yields NaN instead of +-inf: both are `Failed`)
+    const double y = __drcp_rn(n);
+    const double qa = __dmul_rn(a, y), qb = __dmul_rn(b, y);
+    const double ra = __fma_rn(-n, qa, a), rb = __fma_rn(-n, qb, b);
+    return Cx{__fma_rn(ra, y, qa), __fma_rn(rb, y, qb)};
+  }
+  double o[2];
+  div2_ieee(a, b, n, o);
+  return Cx{o[0], o[1]};
+}
 __device__ __forceinline__ Cx cx_div(Cx a, Cx b) {
   const double n = __dadd_rn(__dmul_rn(b.re, b.re), __dmul_rn(b.im, b.im));
   const double re = __dadd_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im));
   const double im = __dsub_rn(__dmul_rn(a.im, b.re), __dmul_rn(a.re, b.im));
-  return Cx{__ddiv_rn(re, n), __ddiv_rn(im, n)};
+  return div2_same_denominator(re, im, n);
 }
 __device__ __forceinline__ Cx cx_recip(Cx b) {  // (1 + 0i) / b
   const double n = __dadd_rn(__dmul_rn(b.re, b.re), __dmul_rn(b.im, b.im));
-  return Cx{__ddiv_rn(b.re, n), __ddiv_rn(-b.im, n)};
+  return div2_same_denominator(b.re, -b.im, n);
 }
 // one Horner step r*x + c with the fused form of num-complex's MulAdd
 __device__ __forceinline__ Cx cx_horner_step(Cx r, Cx x, double c) {

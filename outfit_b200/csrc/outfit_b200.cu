@@ -294,6 +294,7 @@ __device__ __forceinline__ void state_to_orbit(const IodScratch &S, unsigned lon
 }
 
 // ---- P3: elements -> equinoctial -> arc RMS sum --------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kCandThreads)
 score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
@@ -345,7 +346,7 @@ score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
             const unsigned long long gI = o0 + ii;
             const double dec_o = __ldg(B.dec + gI);
             double v;
-            if (!ephemeris_error(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos(dec_o), __ldg(B.sigma_ra + gI),
+            if (!ephemeris_error<COUNT>(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos(dec_o), __ldg(B.sigma_ra + gI),
                                  __ldg(B.sigma_dec + gI),
                                  V3{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)},
                                  v, w)) {
@@ -364,7 +365,7 @@ score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
     S.score_sum[cid] = sum;
     S.score_narc[cid] = n_arc;
   }
-  flush_work(w, work_counters);
+  if (COUNT) flush_work(w, work_counters);
 }
 
 // ---- P4: per-trajectory fold, one warp per trajectory (trajectory.rs:429-545) ----------------------
@@ -832,7 +833,8 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     if (ctx->count_work) correct_kernel<true><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
     else correct_kernel<false><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
     mark();
-    score_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    if (ctx->count_work) score_kernel<true><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    else score_kernel<false><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
     mark();
     select_kernel<<<tblocks, kWarpsPerBlock * 32, 0, stream>>>(B, P, S, d_out + t0);
     mark();

@@ -3,7 +3,7 @@
 # `ncu --set full` capture of the three numeric kernels.  Outputs land in gpurun_out/<tag>_*.
 TAG=${1:-r01}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest_gpu.log
+python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest_gpu.log
 tail -3 gpurun_out/${TAG}_pytest_gpu.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cut -c1-600 gpurun_out/${TAG}_bench.json

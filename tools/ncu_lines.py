@@ -13,6 +13,8 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
 prof = []
 for r in rows[hi + 1:]:
+    if r and r[0] == "Kernel Name":
+        break  # the page repeats the kernel: keep the first copy only
     if len(r) < len(hdr) or r[0] == "Address":
         continue
     try:
@@ -42,6 +44,9 @@ print(f"ncu instructions {len(prof)}, nvdisasm instructions {len(ins)}")
 n = min(len(prof), len(ins))
 bad = sum(1 for i in range(n) if prof[i][0].split()[0:1] != ins[i][0].split()[0:1])
 print(f"opcode mismatches in the first {n}: {bad}")
+if bad or len(prof) != len(ins):
+    print("the in-tree build is not the profiled build: no line attribution")
+    sys.exit(0)
 by = Counter(); ex = Counter(); tot = sum(p[1] for p in prof); tex = sum(p[2] for p in prof)
 for i in range(n):
     by[ins[i][1]] += prof[i][1]; ex[ins[i][1]] += prof[i][2]

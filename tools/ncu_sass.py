@@ -13,6 +13,8 @@ hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = Counter(); samples = inst = 0; op = Counter(); ops = Counter(); data = []
 for r in rows[hi + 1:]:
+    if r and r[0] == "Kernel Name":
+        break  # the page repeats the kernel: keep the first copy only
     if len(r) < len(hdr) or r[0] == "Address":
         continue
     try:
