@@ -151,7 +151,8 @@ def main():
                           f"noise_scale={nscale}); synthetic DE440-shaped ephemeris",
               "trajectories_per_gpu": T, "n_obs": n_obs, "max_triplets": K, "n_noise_realizations": nn,
               "candidates_per_trajectory": K * (nn + 1), "sharding": f"trajectory-index x{world}",
-              "l2": "inputs (>1 GB noise + observation stream per step) exceed the 126 MB L2"}
+              "l2": "inputs (>1 GB noise + observation stream per step) exceed the 126 MB L2",
+              "passes_in_flight": 8}
 
     from outfit_b200 import synth
     table = synth.make_ephemeris_table()
@@ -249,19 +250,27 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / max(1, args.steps)
-    # per-kernel durations of the LAST timed step: CUDA events the library records on the launching
-    # stream between its kernels (outfit_b200_last_iod_phase_ms)
-    phases = ctx.last_iod_phase_ms()
-    per_step_launches = int(phases["kernel_launches"])
+    per_step_launches = int(ctx.last_iod_phase_ms()["kernel_launches"])  # 8 passes x 5 kernels + observer
     launches = (max(3, args.warmup) + args.steps) * per_step_launches
-    kernel_ms = phases["total_ms"]  # all kernels of one step, no gather
+    # per-kernel durations: the timed steps keep 8 passes in flight on 8 streams, where kernels of
+    # different passes overlap; the per-kernel figures come from extra steps run as ONE pass on the
+    # launching stream, bracketed by CUDA events the library records between its kernels
+    ctx.set_pass_streams(1)
+    single_ms = []
+    for _ in range(3):
+        ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
+        phases = ctx.last_iod_phase_ms()
+        single_ms.append(phases["total_ms"])
+    launches += 3 * int(phases["kernel_launches"])
+    kernel_ms = phases["total_ms"]  # all kernels of one single-pass step, no gather
     # one extra, untimed step with the counting instantiation: the event counts behind the flop figure
     ctx.set_work_counters(True)
     ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
     torch.cuda.synchronize()
     counters = ctx.last_iod_counters()
     ctx.set_work_counters(False)
-    launches += per_step_launches
+    launches += int(phases["kernel_launches"])
+    ctx.set_pass_streams(8)
 
     # e2e: host-buffer C-ABI entry (H2D of the pinned inputs + kernels + D2H of the results)
     ctx.fit_full_iod(host_batch, params)
@@ -339,7 +348,9 @@ def main():
             "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": kernels[dom]["frac_fp64_peak"], "traffic": None, "kernel": dom,
                          "kernel_ms": kernels[dom]["ms"], "algorithmic_flop_per_launch": kernels[dom]["algorithmic_flop"],
-                         "step": {"achieved": achieved / 1e12, "frac": achieved / fp64_peak, "ms": kernel_ms,
+                         "step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / fp64_peak, "ms": ms,
+                                  "single_pass_ms": kernel_ms, "single_pass_frac": achieved / fp64_peak,
+                                  "note": "timed steps keep 8 passes in flight on 8 streams (straggler overlap); per-kernel ms are from single-pass steps",
                                   "algorithmic_flop": flops, "algorithmic_flop_per_trajectory": flops / T,
                                   "libm_calls": libm_calls(counters)},
                          "kernels": kernels,
@@ -347,7 +358,7 @@ def main():
                          "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": 6536.7,
                                  "algorithmic_bytes_per_launch": alg_bytes,
                                  "note": "observation + noise stream; the kernel is FP64-latency/issue bound, not HBM bound"}},
-            "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (kernel_ms * 1e-3),
+            "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (ms * 1e-3),
                        "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
             "counters": counters,
             "selected_ok_fraction": float((res_host["status"] == 0).mean()),

@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     "outfit_b200_load_ephemeris", "outfit_b200_fit_full_iod", "outfit_b200_fit_full_iod_device",
     "outfit_b200_observer_cache_device", "outfit_b200_propagate_universal",
     "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters", "outfit_b200_last_iod_phase_ms",
-    "outfit_b200_set_work_counters",
+    "outfit_b200_set_work_counters", "outfit_b200_set_pass_streams",
     "outfit_b200_measure_fp64_peak",
 ]
 
@@ -156,6 +156,7 @@ def load_library():
                                                          vp, vp, vp]
     L.outfit_b200_last_iod_counters.argtypes = [vp, C.POINTER(IodCounters)]
     L.outfit_b200_set_work_counters.argtypes = [vp, C.c_int]
+    L.outfit_b200_set_pass_streams.argtypes = [vp, C.c_int]
     L.outfit_b200_last_iod_phase_ms.argtypes = [vp, C.POINTER(IodPhaseMs)]
     L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _LIB = L
@@ -255,6 +256,10 @@ class OutfitB200:
     def set_work_counters(self, enabled):
         """Select the counting (exact work counters) or the plain instantiation of the kernels."""
         self._check(self._L.outfit_b200_set_work_counters(self._h, 1 if enabled else 0))
+
+    def set_pass_streams(self, n_streams):
+        """Passes in flight for large batches (default 8); 1 = single pass, per-phase timings available."""
+        self._check(self._L.outfit_b200_set_pass_streams(self._h, int(n_streams)))
 
     def last_iod_phase_ms(self):
         """CUDA-event durations (ms) of each kernel of the last full-IOD launch (blocks until done)."""

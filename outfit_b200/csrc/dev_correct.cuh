@@ -48,6 +48,14 @@ __device__ __forceinline__ double div_mk(double a, double n, double y) {
 // is AU / day scale, the guard only routes pathological values to the IEEE division)
 __device__ __forceinline__ bool mk_ok(double n) { return fabs(n) > 1e-100 && fabs(n) < 1e100; }
 
+// Correctly rounded reciprocals of the compile-time denominators, in the constant bank: an FP64
+// instruction takes c[bank][offset] as a direct operand, whereas a 64-bit literal costs two UMOVs.
+enum { RC_3 = 16, RC_GAUSSK = 17, RC_MU = 18, RC_VLIGHT = 19 };
+__constant__ double c_rcp[20] = {
+    1.0 / 12.0,  1.0 / 20.0,  1.0 / 30.0,  1.0 / 42.0,  1.0 / 56.0,  1.0 / 72.0,  1.0 / 90.0,  1.0 / 110.0,
+    1.0 / 132.0, 1.0 / 156.0, 1.0 / 182.0, 1.0 / 210.0, 1.0 / 240.0, 1.0 / 272.0, 1.0 / 306.0, 1.0 / 342.0,
+    1.0 / 3.0,   1.0 / kGaussK, 1.0 / kMu, 1.0 / kVlightAu};
+
 struct WorkC {
   unsigned roots_accepted, fg_iterations, kepler_solves, newton_steps, sfunct_terms;
 };
@@ -116,9 +124,9 @@ __device__ __noinline__ void s_funct_tail(double beta, double *st /* s2,t2,s3,t3
     const double a2 = fabs(t2), a3 = fabs(t3);                                      \
     if ((a2 < tol && a3 < tol) || a2 > big || a3 > big) goto series_done;           \
   }
-#define OFB_SERIES_Q(C2, C3)                                                        \
-  const double q2_##C2 = div_mk(beta, (double)C2, 1.0 / (double)C2);                \
-  const double q3_##C3 = div_mk(beta, (double)C3, 1.0 / (double)C3);
+#define OFB_SERIES_Q(K, C2, C3)                                                     \
+  double q2_##C2 = div_mk(beta, (double)C2, c_rcp[2 * K]);                          \
+  double q3_##C3 = div_mk(beta, (double)C3, c_rcp[2 * K + 1]);
 
 template <bool COUNT>
 __device__ __forceinline__ void s_funct_fast(double psi, double alpha, double &s0, double &s1, double &s2o,
@@ -136,13 +144,17 @@ __device__ __forceinline__ void s_funct_fast(double psi, double alpha, double &s
     return;
   }
   double s2 = 0.5 * psi2, t2 = s2;
-  double s3 = div_mk(s2 * psi, 3.0, 1.0 / 3.0), t3 = s3;
+  double s3 = div_mk(s2 * psi, 3.0, c_rcp[RC_3]), t3 = s3;
   {
-    OFB_SERIES_Q(12, 20) OFB_SERIES_Q(30, 42) OFB_SERIES_Q(56, 72) OFB_SERIES_Q(90, 110)
+    OFB_SERIES_Q(0, 12, 20) OFB_SERIES_Q(1, 30, 42) OFB_SERIES_Q(2, 56, 72) OFB_SERIES_Q(3, 90, 110)
+    // scheduling fence: the eight independent ratio chains are issued back to back BEFORE the running
+    // products start (the compiler otherwise sinks each ratio into its term, serialising 5 FP64 ops)
+    asm volatile("" : "+d"(q2_12), "+d"(q3_20), "+d"(q2_30), "+d"(q3_42), "+d"(q2_56), "+d"(q3_72), "+d"(q2_90), "+d"(q3_110));
     OFB_SERIES_TERM(12, 20) OFB_SERIES_TERM(30, 42) OFB_SERIES_TERM(56, 72) OFB_SERIES_TERM(90, 110)
   }
   {
-    OFB_SERIES_Q(132, 156) OFB_SERIES_Q(182, 210) OFB_SERIES_Q(240, 272) OFB_SERIES_Q(306, 342)
+    OFB_SERIES_Q(4, 132, 156) OFB_SERIES_Q(5, 182, 210) OFB_SERIES_Q(6, 240, 272) OFB_SERIES_Q(7, 306, 342)
+    asm volatile("" : "+d"(q2_132), "+d"(q3_156), "+d"(q2_182), "+d"(q3_210), "+d"(q2_240), "+d"(q3_272), "+d"(q2_306), "+d"(q3_342));
     OFB_SERIES_TERM(132, 156) OFB_SERIES_TERM(182, 210) OFB_SERIES_TERM(240, 272) OFB_SERIES_TERM(306, 342)
   }
   {
@@ -218,7 +230,7 @@ __device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double
   m.hn = sqrt(h2);
   m.defined = !(m.hn == 0.0);
   const V3 vxh = cross(v, h);
-  const double inv_mu = 1.0 / kMu;
+  const double inv_mu = c_rcp[RC_MU];
   const double inv_d = 1.0 / dist;
   const V3 lenz = V3{vxh.x * inv_mu - r.x * inv_d, vxh.y * inv_mu - r.y * inv_d, vxh.z * inv_mu - r.z * inv_d};
   m.ecc = norm(lenz);
@@ -227,8 +239,8 @@ __device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double
   m.accepted = (m.ecc < ecc_max) && (peri < peri_max);
   m.r2 = dist;
   m.inv_r2 = inv_d;
-  m.sig0 = div_mk(dot(r, v), kGaussK, 1.0 / kGaussK);
-  m.alpha = div_mk(2.0 * energy, kMu, 1.0 / kMu);
+  m.sig0 = div_mk(dot(r, v), kGaussK, c_rcp[RC_GAUSSK]);
+  m.alpha = div_mk(2.0 * energy, kMu, c_rcp[RC_MU]);
   return m;
 }
 
@@ -247,7 +259,7 @@ __device__ __forceinline__ SideC correction_side(V3 x1, V3 x2, const MidC &m, do
   double s2, s3;
   if (!kepuni_newton_fast<COUNT>(dt, m.r2, m.sig0, m.alpha, eps, psi, s2, s3, w)) return o;
   const double f = 1.0 - (mk_ok(m.r2) ? div_mk(s2, m.r2, m.inv_r2) : s2 / m.r2);
-  const double g = dt - div_mk(s3, kGaussK, 1.0 / kGaussK);
+  const double g = dt - div_mk(s3, kGaussK, c_rcp[RC_GAUSSK]);
   const double ga = fabs(g);
   if (!isfinite(ga) || ga < 100.0 * kEps * (1.0 + fabs(dt))) return o;
   const double nx = (-f) * x2.x + x1.x, ny = (-f) * x2.y + x1.y, nz = (-f) * x2.z + x1.z;
@@ -284,7 +296,7 @@ __device__ __forceinline__ bool positions_c(const GeoSm &G, double c0, double c2
   p0 = R0 + rho0 * G.v3(SL_S0);
   p1 = R1 + rho1 * G.v3(SL_S1);
   p2 = R2 + rho2 * G.v3(SL_S2);
-  epoch = G.at(SL_T1) - div_mk(rho1, kVlightAu, 1.0 / kVlightAu);
+  epoch = G.at(SL_T1) - div_mk(rho1, kVlightAu, c_rcp[RC_VLIGHT]);
   return true;
 }
 

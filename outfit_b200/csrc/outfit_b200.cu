@@ -10,8 +10,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -569,6 +571,14 @@ struct OutfitCtx {
   void *h_scratch = nullptr;
   void *iod_scratch = nullptr;  // per-candidate arrays of the phase pipeline
   size_t iod_scratch_bytes = 0;
+  // host entry point: cached input arena, copy / compute streams, per-slice copy events
+  unsigned char *arena = nullptr;
+  size_t arena_bytes = 0;
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  std::vector<cudaEvent_t> copy_ev;
+  int n_streams = 8;  // passes in flight (outfit_b200_set_pass_streams; 1 = one pass on the caller's stream)
+  cudaStream_t aux_stream[7] = {};  // extra compute streams (pass overlap)
+  cudaEvent_t fork_ev = nullptr, join_ev[7] = {};
   // CUDA events bracketing every phase of the last full-IOD launch (outfit_b200_last_iod_phase_ms)
   std::vector<cudaEvent_t> phase_ev;
   unsigned phase_chunks = 0;
@@ -664,7 +674,17 @@ extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
     rcp[2 * j + 1] = 1.0 / ((d + 1.0) * (d + 2.0));
   }
   if (cudaMemcpyToSymbol(c_series_rcp, rcp, sizeof rcp) != cudaSuccess) { cudaFree(ctx->d_counters); delete ctx; return OUTFIT_E_CUDA; }
+  if (const char *ev = getenv("OUTFIT_B200_STREAMS")) {
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 8) ctx->n_streams = v;
+  }
   *out = ctx;
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_set_pass_streams(OutfitCtx *ctx, int n_streams) {
+  if (!ctx || n_streams < 1 || n_streams > 8) return OUTFIT_E_INVALID_ARGUMENT;
+  ctx->n_streams = n_streams;
   return OUTFIT_OK;
 }
 
@@ -677,6 +697,15 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   if (ctx->iod_scratch) cudaFree(ctx->iod_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->copy_ev) cudaEventDestroy(e);
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+  for (int i = 0; i < 7; ++i) {
+    if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
+    if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+  }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   delete ctx;
 }
 
@@ -741,8 +770,18 @@ constexpr unsigned kMaxObsPerTraj = 448;
 constexpr unsigned kMaxTriplets = 1024;
 
 // Launch the device pipeline on device-resident buffers.  `max_obs` = longest trajectory.
+// `max_chunk` (0 = as large as the scratch budget allows) bounds the trajectories per pipeline pass;
+// `before_chunk(t0, tn, s)` is called before the kernels of trajectories [t0, t0 + tn) are enqueued on
+// stream s (the host entry point uses it to make s wait for that slice of the input copy).
+// With `stream2` the passes alternate between the two streams (each with its own candidate scratch):
+// a handful of candidates per pass run ~100x longer than the rest (f-g loops whose every Kepler solve
+// exhausts its 50 Newton steps -- reference behaviour), and a pass boundary on ONE stream leaves the
+// GPU idle until they finish; on two streams the next pass fills the machine meanwhile.
 static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *b,
-                      OutfitIodResult *d_out, unsigned max_obs, cudaStream_t stream) {
+                      OutfitIodResult *d_out, unsigned max_obs, cudaStream_t stream,
+                      unsigned long long max_chunk = 0,
+                      const std::function<void(unsigned long long, unsigned long long, cudaStream_t)> *before_chunk = nullptr,
+                      int n_streams = 1) {
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
   if (max_obs > kMaxObsPerTraj) return fail(ctx, OUTFIT_E_UNSUPPORTED, "trajectory longer than 448 observations");
   if (params->max_triplets > kMaxTriplets) return fail(ctx, OUTFIT_E_UNSUPPORTED, "max_triplets > 1024");
@@ -766,6 +805,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   ctx->phase_valid = false;
   size_t ev_next = 0;
   auto mark = [&]() {
+    if (n_streams > 1) return;
     if (ev_next == ctx->phase_ev.size()) {
       cudaEvent_t e;
       if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -792,7 +832,18 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   const size_t budget = (size_t)6 << 30;  // candidate scratch per chunk
   unsigned long long chunk = b->n_traj;
   if (per_traj * chunk > budget) chunk = budget / per_traj ? budget / per_traj : 1;
-  rc = ensure_iod_scratch(ctx, per_traj * chunk + 64 * 256);
+  if (max_chunk && chunk > max_chunk) chunk = max_chunk;
+  constexpr int kMaxStreams = 8;
+  const int ns = n_streams < 1 ? 1 : (n_streams > kMaxStreams ? kMaxStreams : n_streams);
+  cudaStream_t st[kMaxStreams];
+  st[0] = stream;
+  for (int i = 1; i < ns; ++i) {
+    if (!ctx->aux_stream[i - 1]) CK(cudaStreamCreateWithFlags(&ctx->aux_stream[i - 1], cudaStreamNonBlocking));
+    if (!ctx->join_ev[i - 1]) CK(cudaEventCreateWithFlags(&ctx->join_ev[i - 1], cudaEventDisableTiming));
+    st[i] = ctx->aux_stream[i - 1];
+  }
+  const size_t scratch_half = (per_traj * chunk + 64 * 256 + 255) & ~(size_t)255;
+  rc = ensure_iod_scratch(ctx, scratch_half * ns);
   if (rc) return rc;
   const unsigned cap = max_obs < 3 ? 4 : ((max_obs + 1) & ~1u);
   size_t per_warp = ((size_t)cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4) + 15) & ~(size_t)15;
@@ -800,9 +851,16 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   if (smem0 > 200 * 1024) return fail(ctx, OUTFIT_E_UNSUPPORTED, "shared memory per block exceeds 200 KB");
   CK(cudaFuncSetAttribute(triplets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
   CK(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), stream));
+  if (ns > 1) {  // fork: the other streams start after the observer kernels and the counter reset
+    if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->fork_ev, st[0]));
+    for (int i = 1; i < ns; ++i) CK(cudaStreamWaitEvent(st[i], ctx->fork_ev, 0));
+  }
   unsigned n_chunks = 0;
   for (unsigned long long t0 = 0; t0 < b->n_traj; t0 += chunk) {
     const unsigned long long tn = b->n_traj - t0 < chunk ? b->n_traj - t0 : chunk;
+    cudaStream_t stream = st[n_chunks % ns];  // shadows the argument inside the pass
+    if (before_chunk) (*before_chunk)(t0, tn, stream);
     IodBatchDev B;
     B.n_traj = tn; B.n_obs = n;
     B.traj_offset = reinterpret_cast<const unsigned long long *>(b->traj_offset) + t0;
@@ -811,7 +869,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     B.noise_z = b->noise_z ? b->noise_z + (size_t)t0 * P.max_triplets * P.n_noise * 6 : nullptr;
     IodScratch S;
     S.n_cand = tn * cand_per_traj;
-    unsigned char *p = reinterpret_cast<unsigned char *>(ctx->iod_scratch);
+    unsigned char *p = reinterpret_cast<unsigned char *>(ctx->iod_scratch) + (n_chunks % ns) * scratch_half;
     auto take = [&](size_t bytes) { void *q = p; p += (bytes + 255) & ~(size_t)255; return q; };
     S.roots = (double *)take(8 * S.n_cand * 8);
     S.state = (double *)take(7 * S.n_cand * 8);
@@ -840,10 +898,14 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     mark();
     ++n_chunks;
   }
+  for (int i = 1; i < ns; ++i) {  // join
+    CK(cudaEventRecord(ctx->join_ev[i - 1], st[i]));
+    CK(cudaStreamWaitEvent(st[0], ctx->join_ev[i - 1], 0));
+  }
   CK(cudaGetLastError());
   ctx->phase_chunks = n_chunks;
   ctx->phase_observer_kernels = n ? (have_cache ? 1u : 2u) : 0u;
-  ctx->phase_valid = ev_next == 2 + 5 * (size_t)n_chunks;
+  ctx->phase_valid = ns == 1 && ev_next == 2 + 5 * (size_t)n_chunks;  // per-phase times need ONE stream
   return OUTFIT_OK;
 }
 
@@ -870,6 +932,10 @@ extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodPa
     }
     free(h);
   }
+  // large batches run as n_streams passes in flight (see launch_iod); per-phase timings need n_streams = 1
+  const unsigned long long passes = (unsigned long long)ctx->n_streams;
+  if (passes > 1 && batch->n_traj >= passes * 1024)
+    return launch_iod(ctx, params, batch, out, max_obs, stream, (batch->n_traj + passes - 1) / passes, nullptr, ctx->n_streams);
   return launch_iod(ctx, params, batch, out, max_obs, stream);
 }
 
@@ -894,17 +960,23 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
   const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
   if (!have_cache && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_helio_equ+obs_geo_ecl or observer_body_fixed+mjd_ut1");
   const size_t n_noise_doubles = hb->noise_z ? T * (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
-  // one device arena for the inputs and the results (every sub-buffer 256-B aligned)
+  // one cached device arena for the inputs and the results (every sub-buffer 256-B aligned)
   const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 +
                        T * sizeof(OutfitIodResult) + 16 * 256;
-  unsigned char *arena = nullptr;
-  if (cudaMalloc(&arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(batch arena)");
-  cudaStream_t stream = 0;
+  if (ctx->arena_bytes < bytes) {
+    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(batch arena)");
+    ctx->arena_bytes = bytes;
+  }
+  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+  unsigned char *arena = ctx->arena;
+  cudaStream_t cs = ctx->copy_stream, stream = ctx->compute_stream;
   size_t off = 0;
   auto put = [&](const void *src, size_t nbytes) -> void * {
     void *dst = arena + off;
     off += (nbytes + 255) & ~(size_t)255;
-    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream);
+    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs);
     return dst;
   };
   OutfitObsBatch db = *hb;
@@ -923,15 +995,52 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
     db.mjd_ut1 = (const double *)put(hb->mjd_ut1, n * 8);
     db.obs_helio_equ = nullptr; db.obs_geo_ecl = nullptr;
   }
-  db.noise_z = n_noise_doubles ? (const double *)put(hb->noise_z, n_noise_doubles * 8) : nullptr;
+  // The observation stream is small (88 B per observation); the noise deviates are the bulk of the
+  // input (48 B per noisy candidate).  They are copied in trajectory slices on the copy stream while
+  // the compute stream works on the slices that already arrived.
+  const size_t want = ctx->n_streams > 1 ? (n_noise_doubles ? 2 * (size_t)ctx->n_streams : (size_t)ctx->n_streams) : 1;
+  size_t n_slices = T < want * 1024 ? (T + 1023) / 1024 : want;
+  if (const char *ev = getenv("OUTFIT_B200_COPY_SLICES")) {  // tuning knob: 1 = no copy/compute overlap
+    const long v = atol(ev);
+    if (v >= 1) n_slices = (size_t)v < T ? (size_t)v : T;
+  }
+  const unsigned long long slice = (T + n_slices - 1) / n_slices;
+  while (ctx->copy_ev.size() < n_slices + 1) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_ev.push_back(e);
+  }
+  CK(cudaEventRecord(ctx->copy_ev[0], cs));  // observation arrays are in flight up to here
+  double *d_noise = nullptr;
+  if (n_noise_doubles) {
+    d_noise = (double *)put(nullptr, n_noise_doubles * 8);
+    const size_t per_traj = (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6;
+    for (size_t sidx = 0; sidx < n_slices; ++sidx) {
+      const size_t t0 = sidx * slice, t1 = t0 + slice < T ? t0 + slice : T;
+      if (t1 > t0)
+        cudaMemcpyAsync(d_noise + t0 * per_traj, hb->noise_z + t0 * per_traj, (t1 - t0) * per_traj * 8, cudaMemcpyHostToDevice, cs);
+      CK(cudaEventRecord(ctx->copy_ev[sidx + 1], cs));
+    }
+  }
+  db.noise_z = d_noise;
   OutfitIodResult *d_out = (OutfitIodResult *)put(nullptr, T * sizeof(OutfitIodResult));
-  rc = launch_iod(ctx, params, &db, d_out, max_obs, stream);
+  CK(cudaStreamWaitEvent(stream, ctx->copy_ev[0], 0));
+  const std::function<void(unsigned long long, unsigned long long, cudaStream_t)> wait_slice =
+      [&](unsigned long long t0, unsigned long long tn, cudaStream_t s) {
+        if (!n_noise_doubles) return;
+        const size_t last = (size_t)((t0 + tn - 1) / slice);
+        cudaStreamWaitEvent(s, ctx->copy_ev[(last < n_slices ? last : n_slices - 1) + 1], 0);
+      };
+  rc = launch_iod(ctx, params, &db, d_out, max_obs, stream, n_slices > 1 ? slice : 0, &wait_slice,
+                  n_slices > 1 ? ctx->n_streams : 1);
   if (rc == OUTFIT_OK) {
     cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitIodResult), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
     if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "fit_full_iod: copy back / kernel", e);
+  } else {
+    cudaStreamSynchronize(cs);
   }
-  cudaFree(arena);
   return rc;
 }
 
@@ -956,7 +1065,12 @@ extern "C" int outfit_b200_set_work_counters(OutfitCtx *ctx, int enabled) {
 extern "C" int outfit_b200_last_iod_phase_ms(OutfitCtx *ctx, OutfitIodPhaseMs *out) {
   if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
   memset(out, 0, sizeof *out);
-  if (!ctx->phase_valid) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "no full-IOD launch recorded on this context");
+  out->n_chunks = ctx->phase_chunks;
+  out->kernel_launches = ctx->phase_chunks * 5u + ctx->phase_observer_kernels;
+  if (!ctx->phase_valid) {  // several passes in flight: only the launch counts are meaningful
+    out->observer_ms = out->triplets_ms = out->roots_ms = out->correct_ms = out->score_ms = out->select_ms = out->total_ms = -1.f;
+    return ctx->phase_chunks ? OUTFIT_OK : fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "no full-IOD launch recorded on this context");
+  }
   CK(cudaSetDevice(ctx->device));
   const size_t n_ev = 2 + 5 * (size_t)ctx->phase_chunks;
   CK(cudaEventSynchronize(ctx->phase_ev[n_ev - 1]));
