@@ -309,6 +309,41 @@ def main():
                "workload": "10M random elliptic/hyperbolic heliocentric states, SolverKind::Auto, convergency 100 eps"}
         del d_rv, d_t0, d_t1, d_o, d_s
 
+    # Ephemeris leg: BASELINE configs[4], 1 M orbits x 100 daily epochs, Combined output, device-resident
+    eph = None
+    if not args.no_kepler:
+        n_orb, n_ep = 1_000_000, 100
+        kind, epoch0, elem = synth.make_ephemeris_orbits(n_orb, seed=20261018 + rank)
+        tt, ut1, bf = synth.make_ephemeris_epochs(n_ep)
+        d_kind, d_ep, d_el, d_tt, d_ut = (torch.from_numpy(x).to(dev) for x in (kind, epoch0, elem, tt, ut1))
+        d_eo = torch.empty(9 * n_ep * n_orb, dtype=torch.float64, device=dev)
+        d_es = torch.empty(n_ep * n_orb, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ctx.ephemeris_twobody_device(n_orb, d_kind, d_ep, d_el, n_ep, d_tt, d_ut, bf, d_eo, d_es, stream=stream)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(3):
+            ctx.ephemeris_twobody_device(n_orb, d_kind, d_ep, d_el, n_ep, d_tt, d_ut, bf, d_eo, d_es, stream=stream)
+        q1.record()
+        torch.cuda.synchronize()
+        ems = q0.elapsed_time(q1) / 3
+        launches += 5 * 2
+        n_ent = n_orb * n_ep
+        eph = {"entries_per_s": n_ent / (ems * 1e-3), "orbits": n_orb, "epochs": n_ep, "ms": ems,
+               "hbm_gbs": (76.0 * n_ent + 60.0 * n_orb) / (ems * 1e-3) / 1e9, "hbm_frac": (76.0 * n_ent + 60.0 * n_orb) / (ems * 1e-3) / 1e9 / 6536.7,
+               "ok_fraction": float((d_es == 0).float().mean().item()),
+               "workload": "1M elliptic orbits x 100 daily epochs, one topocentric observer, two-body, first-order aberration, Combined output (9 f64 + status per entry)"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import binding as O
+            et_ = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+            ns = 20000
+            t0 = time.perf_counter()
+            O.ephemeris_twobody_batch(et_, kind[:ns].copy(), epoch0[:ns].copy(), np.ascontiguousarray(elem[:, :ns]), tt, ut1, bf)
+            eph["cpu_entries_per_s"] = ns * n_ep / (time.perf_counter() - t0)
+            eph["cpu_sample"] = f"{ns} orbits x {n_ep} epochs, oracle on all {cores} host threads (observer state re-evaluated per entry like the reference)"
+        del d_eo, d_es
+
     # max over ranks
     tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -360,6 +395,7 @@ def main():
                                  "note": "observation + noise stream; the kernel is FP64-latency/issue bound, not HBM bound"}},
             "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (ms * 1e-3),
                        "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
+            "ephemeris": eph,
             "counters": counters,
             "selected_ok_fraction": float((res_host["status"] == 0).mean()),
         }

@@ -286,6 +286,26 @@ void oo_fit_full_iod(size_t n_traj, const uint64_t *traj_offset, const double *m
                      const uint64_t *noise_offset, oo_iod_result *out, int n_threads,
                      int dedup_earth);
 
+/* ---- two-body `Combined` ephemeris (ephemeris/mod.rs:189-292; oo_ephemeris.c) -------------- */
+/* apparent_position.rs:264-296 : observer position / velocity (= Earth velocity) / Earth position,
+   equatorial mean J2000, AU and AU/day */
+int oo_ephemeris_observer_pv(const oo_ephem_table *tab, double mjd_tt, double mjd_ut1,
+                             const double r_bf[3], double obs_pos_equ[3], double obs_vel_equ[3],
+                             double earth_pos_equ[3]);
+/* one entry: out[9] = ra, dec, geocentric_dist, heliocentric_dist, phase_angle, solar_elongation,
+   radial_velocity, d_ra_dt, d_dec_dt (apparent_position.rs:315-340, geometry.rs:204-345) */
+int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const double obs_pos[3],
+                       const double obs_vel[3], const double earth_pos[3], double out[9]);
+/* OrbitalElements::compute::<Combined>, one orbit x one observer x n_epochs; out [9][n_epochs] */
+void oo_ephemeris_twobody(const oo_ephem_table *tab, const oo_elements *orbit, size_t n_epochs,
+                          const double *mjd_tt, const double *mjd_ut1, const double r_bf[3],
+                          double *out, int32_t *status);
+/* batch.rs:134-183 over a flat batch; out [9][n_epochs][n_orbits], status [n_epochs][n_orbits] */
+void oo_ephemeris_twobody_batch(const oo_ephem_table *tab, size_t n_orbits, const int32_t *kind,
+                                const double *epoch, const double *elem, size_t n_epochs,
+                                const double *mjd_tt, const double *mjd_ut1, const double r_bf[3],
+                                double *out, int32_t *status, int n_threads, int dedup_observer);
+
 #ifdef __cplusplus
 }
 #endif

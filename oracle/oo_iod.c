@@ -389,3 +389,82 @@ void oo_propagate_universal_batch(size_t n, const double *rv, const double *t0, 
   pu_ctx c = {n, rv, t0, t1, kind, convergency, out, status};
   parallel_for((long long)n, 4096, n_threads, pu_task, &c);
 }
+
+/* ---- FullOrbitResultExt::compute_ephemerides[_parallel] (ephemeris/batch.rs:134-183) over a flat
+ *      batch: one task per orbit (rayon par_iter over the result map), every (orbit, epoch) entry
+ *      recomputes the observer state like the reference unless dedup_observer != 0.
+ *      elem: [6][n_orbits] plane-major; out: [9][n_epochs][n_orbits]; status: [n_epochs][n_orbits] */
+typedef struct {
+  const oo_ephem_table *tab;
+  size_t n, n_epochs;
+  const int32_t *kind;
+  const double *epoch, *elem, *mjd_tt, *mjd_ut1, *r_bf;
+  const double *obs_pv; /* [9][n_epochs] precomputed observer state or NULL */
+  const int32_t *obs_st;
+  double *out;
+  int32_t *status;
+} eph_ctx;
+static void eph_task(long long lo, long long hi, void *vctx) {
+  eph_ctx *c = (eph_ctx *)vctx;
+  size_t n = c->n, E = c->n_epochs;
+  for (long long i = lo; i < hi; i++) {
+    oo_elements orb, equi;
+    orb.kind = c->kind[i];
+    orb.epoch = c->epoch[i];
+    for (int q = 0; q < 6; q++) orb.e[q] = c->elem[(size_t)q * n + i];
+    int rc = oo_to_equinoctial(&orb, &equi);
+    if (rc == OO_OK) {
+      double h = equi.e[1], k = equi.e[2];
+      if (sqrt(h * h + k * k) >= 1.0) rc = OO_ERR_INVALID_CONVERSION;
+    } else {
+      rc = OO_ERR_INVALID_CONVERSION;
+    }
+    for (size_t e = 0; e < E; e++) {
+      double o[9], op[3], ov[3], ep[3];
+      int st = rc;
+      if (st == OO_OK) {
+        if (c->obs_pv) {
+          st = c->obs_st[e];
+          for (int q = 0; q < 3; q++) {
+            op[q] = c->obs_pv[(size_t)q * E + e];
+            ov[q] = c->obs_pv[(size_t)(3 + q) * E + e];
+            ep[q] = c->obs_pv[(size_t)(6 + q) * E + e];
+          }
+        } else {
+          st = oo_ephemeris_observer_pv(c->tab, c->mjd_tt[e], c->mjd_ut1[e], c->r_bf, op, ov, ep);
+        }
+        if (st == OO_OK) st = oo_ephemeris_entry(&equi, c->mjd_tt[e], op, ov, ep, o);
+      }
+      if (st != OO_OK)
+        for (int q = 0; q < 9; q++) o[q] = NAN;
+      for (int q = 0; q < 9; q++) c->out[((size_t)q * E + e) * n + i] = o[q];
+      c->status[e * n + i] = st;
+    }
+  }
+}
+void oo_ephemeris_twobody_batch(const oo_ephem_table *tab, size_t n_orbits, const int32_t *kind,
+                                const double *epoch, const double *elem, size_t n_epochs,
+                                const double *mjd_tt, const double *mjd_ut1, const double r_bf[3],
+                                double *out, int32_t *status, int n_threads, int dedup_observer) {
+  eph_ctx c = {tab, n_orbits, n_epochs, kind, epoch, elem, mjd_tt, mjd_ut1, r_bf, NULL, NULL, out, status};
+  double *pv = NULL;
+  int32_t *st = NULL;
+  if (dedup_observer) {
+    pv = (double *)malloc(9 * n_epochs * sizeof(double));
+    st = (int32_t *)malloc(n_epochs * sizeof(int32_t));
+    for (size_t e = 0; e < n_epochs; e++) {
+      double op[3] = {NAN, NAN, NAN}, ov[3] = {NAN, NAN, NAN}, ep[3] = {NAN, NAN, NAN};
+      st[e] = oo_ephemeris_observer_pv(tab, mjd_tt[e], mjd_ut1[e], r_bf, op, ov, ep);
+      for (int q = 0; q < 3; q++) {
+        pv[(size_t)q * n_epochs + e] = op[q];
+        pv[(size_t)(3 + q) * n_epochs + e] = ov[q];
+        pv[(size_t)(6 + q) * n_epochs + e] = ep[q];
+      }
+    }
+    c.obs_pv = pv;
+    c.obs_st = st;
+  }
+  parallel_for((long long)n_orbits, 64, n_threads, eph_task, &c);
+  free(pv);
+  free(st);
+}

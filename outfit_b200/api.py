@@ -118,7 +118,7 @@ ABI_SYMBOLS = [
     "outfit_b200_observer_cache_device", "outfit_b200_propagate_universal",
     "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters", "outfit_b200_last_iod_phase_ms",
     "outfit_b200_set_work_counters", "outfit_b200_set_pass_streams",
-    "outfit_b200_measure_fp64_peak",
+    "outfit_b200_measure_fp64_peak", "outfit_b200_ephemeris_twobody", "outfit_b200_ephemeris_twobody_device",
 ]
 
 
@@ -159,6 +159,9 @@ def load_library():
     L.outfit_b200_set_pass_streams.argtypes = [vp, C.c_int]
     L.outfit_b200_last_iod_phase_ms.argtypes = [vp, C.POINTER(IodPhaseMs)]
     L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.outfit_b200_ephemeris_twobody.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, C.c_double * 3, vp, vp]
+    L.outfit_b200_ephemeris_twobody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp,
+                                                       C.c_double * 3, vp, vp, vp]
     _LIB = L
     return L
 
@@ -287,6 +290,26 @@ class OutfitB200:
         solver = solver or SolverType(kind=2)
         self._check(self._L.outfit_b200_propagate_universal_device(self._h, n, _p(rv), _p(t0), _p(t1), _p(psi_guess),
                                                                    C.byref(solver), _p(out), _p(status), stream))
+
+    # -- OrbitalElements::compute::<Combined>, two-body ------------------------------------------
+    EPHEMERIS_FIELDS = ("ra", "dec", "geocentric_dist", "heliocentric_dist", "phase_angle", "solar_elongation",
+                        "radial_velocity", "d_ra_dt", "d_dec_dt")
+
+    def ephemeris_twobody(self, kind, epoch, elem, mjd_tt, mjd_ut1, body_fixed):
+        """HOST arrays: kind (n,) int32, epoch (n,), elem (6, n), mjd_tt / mjd_ut1 (E,), body_fixed (3,)
+        -> out (9, E, n) in the order of EPHEMERIS_FIELDS, status (E, n)."""
+        n, E = int(kind.shape[0]), int(mjd_tt.shape[0])
+        out = np.empty((9, E, n), dtype=np.float64)
+        status = np.empty((E, n), dtype=np.int32)
+        bf = (C.c_double * 3)(*[float(x) for x in body_fixed])
+        self._check(self._L.outfit_b200_ephemeris_twobody(self._h, n, _p(kind), _p(epoch), _p(elem), E, _p(mjd_tt),
+                                                          _p(mjd_ut1), bf, out.ctypes.data, status.ctypes.data))
+        return out, status
+
+    def ephemeris_twobody_device(self, n, kind, epoch, elem, n_epochs, mjd_tt, mjd_ut1, body_fixed, out, status, stream=0):
+        bf = (C.c_double * 3)(*[float(x) for x in body_fixed])
+        self._check(self._L.outfit_b200_ephemeris_twobody_device(self._h, n, _p(kind), _p(epoch), _p(elem), n_epochs,
+                                                                 _p(mjd_tt), _p(mjd_ut1), bf, _p(out), _p(status), stream))
 
     def measure_fp64_peak(self):
         v = C.c_double()

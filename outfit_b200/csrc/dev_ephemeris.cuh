@@ -1,0 +1,295 @@
+// dev_ephemeris.cuh -- two-body `Combined` ephemeris (apparent RA/Dec, distances, phase angle, solar
+// elongation, radial velocity, angular rates) for many orbits x many epochs of one observer.
+//
+// Reference behaviour (/root/reference/src):
+//   OrbitalElements::compute::<Combined>   ephemeris/mod.rs:189-292, request.rs:181-205
+//   propagate / observer_pv                ephemeris/apparent_position.rs:135-160, 264-296
+//   assemble_apparent_position             ephemeris/apparent_position.rs:315-357
+//   compute_geometry                       ephemeris/geometry.rs:204-345
+//   PropagatorKind::TwoBody                propagator/mod.rs:84-91, 128-135
+//   propagate_twobody (equinoctial)        orbit_type/equinoctial_element.rs:326-348, 639-867
+//   HorizonRecord::interpolate (velocity)  jpl_ephem/horizon/horizon_records.rs:204-298
+//
+// Mapping.  The observer state depends on the epoch only, yet the reference recomputes it (pvobs +
+// six Chebyshev bodies) for every (orbit, epoch) entry: here `ephemeris_observer_kernel` evaluates it
+// once per epoch into a [9][E] table, and `ephemeris_twobody_kernel` runs one thread per orbit, hoists
+// everything of the propagation that does not depend on the epoch, and walks the epochs with the
+// table staged in shared memory by a bulk asynchronous copy (cp.async.bulk + mbarrier: the TMA engine
+// moves the tile while the threads convert their elements).  Outputs are plane-major
+// [quantity][epoch][orbit], so the 9 stores of a warp are 9 contiguous 256-byte segments.
+#pragma once
+#include "dev_geometry.cuh"
+
+namespace ofb {
+
+// Chebyshev position AND velocity of one body (km, km/day), HorizonRecord::interpolate
+__device__ __forceinline__ void cheb_posvel(const double *__restrict__ blk, unsigned off, unsigned nc, unsigned nsub,
+                                            double tau, double block_days, V3 &pos, V3 &vel) {
+  const double fs = floor(tau * (double)nsub);
+  const double mx = (double)nsub - 1.0;
+  const unsigned sub = (unsigned)(fs < mx ? fs : mx);
+  const double *cf = blk + off + (size_t)sub * nc * 3;
+  const double temp = (double)nsub * tau;
+  const double tc = 2.0 * (rem_euclid(temp, 1.0) + (double)(long long)tau) - 1.0;
+  const double twot = tc + tc;
+  const double vfac = (2.0 * (double)nsub) / block_days;
+  // T_0 = 1, T_1 = tc ; T'_0 = 0, T'_1 = 1, T'_2 = 4 tc, T'_i = 2tc T'_{i-1} + 2 T_{i-1} - T'_{i-2}
+  double tm2 = 1.0, tm1 = tc;
+  double dm2 = 1.0, dm1 = twot + twot;  // T'_1, T'_2
+  double x = __ldg(cf) * 1.0, y = __ldg(cf + nc) * 1.0, z = __ldg(cf + 2 * nc) * 1.0;
+  x += __ldg(cf + 1) * tc; y += __ldg(cf + nc + 1) * tc; z += __ldg(cf + 2 * nc + 1) * tc;
+  double vx = 0.0 + __ldg(cf) * 0.0, vy = 0.0 + __ldg(cf + nc) * 0.0, vz = 0.0 + __ldg(cf + 2 * nc) * 0.0;
+  vx += __ldg(cf + 1) * 1.0; vy += __ldg(cf + nc + 1) * 1.0; vz += __ldg(cf + 2 * nc + 1) * 1.0;
+  for (unsigned i = 2; i < nc; ++i) {
+    const double ti = twot * tm1 - tm2;
+    double di;
+    if (i == 2) di = dm1;
+    else di = twot * dm1 + 2.0 * tm1 - dm2;
+    const double cx = __ldg(cf + i), cy = __ldg(cf + nc + i), cz = __ldg(cf + 2 * nc + i);
+    x += cx * ti; y += cy * ti; z += cz * ti;
+    vx += cx * di; vy += cy * di; vz += cz * di;
+    tm2 = tm1; tm1 = ti;
+    if (i > 2) dm2 = dm1;
+    dm1 = di;
+  }
+  pos = V3{x, y, z};
+  vel = V3{vfac * vx, vfac * vy, vfac * vz};
+}
+
+// heliocentric Earth position + velocity (equatorial J2000, AU, AU/day): JPLEphem::earth_ephemeris(.., true)
+__device__ __forceinline__ bool earth_posvel(const EphemDev &E, double et, V3 &pos, V3 &vel) {
+  const double et_jd = 2400000.5 + trunc(et);
+  if (et_jd < E.jd_start || et_jd > E.jd_end) return false;
+  long long nr = (long long)floor((et_jd - E.jd_start) / E.block_days);
+  if (fabs(et_jd - E.jd_end) < 1e-10) nr -= 1;
+  if (nr < 0 || (size_t)nr >= E.n_blocks) return false;
+  const double interval_start = (double)nr * E.block_days + E.jd_start;
+  const double tau = ((et_jd - interval_start) + (et - trunc(et))) / E.block_days;
+  const double *blk = E.cheb + (size_t)nr * E.block_stride;
+  V3 pe, ve, pm, vm, ps, vs;
+  cheb_posvel(blk, E.ipt[0][0], E.ipt[0][1], E.ipt[0][2], tau, E.block_days, pe, ve);
+  cheb_posvel(blk, E.ipt[1][0], E.ipt[1][1], E.ipt[1][2], tau, E.block_days, pm, vm);
+  cheb_posvel(blk, E.ipt[2][0], E.ipt[2][1], E.ipt[2][2], tau, E.block_days, ps, vs);
+  const double dem = 1.0 + E.emrat;
+  pos = V3{((pe.x - pm.x / dem) - ps.x) / kAuKm, ((pe.y - pm.y / dem) - ps.y) / kAuKm, ((pe.z - pm.z / dem) - ps.z) / kAuKm};
+  vel = V3{((ve.x - vm.x / dem) - vs.x) / kAuKm, ((ve.y - vm.y / dem) - vs.y) / kAuKm, ((ve.z - vm.z / dem) - vs.z) / kAuKm};
+  return true;
+}
+
+// observer_pv (apparent_position.rs:264-296), one thread per epoch.
+// table: [9][e_stride] = obs_pos_equ xyz, obs_vel_equ xyz (= Earth velocity), earth_pos_equ xyz
+__global__ void __launch_bounds__(128)
+ephemeris_observer_kernel(EphemDev E, size_t n_epochs, size_t e_stride, const double *__restrict__ mjd_tt,
+                          const double *__restrict__ mjd_ut1, double bfx, double bfy, double bfz,
+                          double *__restrict__ table, int *__restrict__ status) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= e_stride) return;
+  double o[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) o[q] = NAN;
+  int st = 0;
+  if (e < n_epochs) {
+    const V3 geo = pvobs_position(mjd_tt[e], mjd_ut1[e], V3{bfx, bfy, bfz});
+    V3 ep, ev;
+    if (earth_posvel(E, mjd_tt[e], ep, ev)) {
+      const V3 op = ep + ecl_to_equ(geo);
+      o[0] = op.x; o[1] = op.y; o[2] = op.z; o[3] = ev.x; o[4] = ev.y; o[5] = ev.z; o[6] = ep.x; o[7] = ep.y; o[8] = ep.z;
+    } else {
+      st = 17;
+    }
+    status[e] = st;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) table[(size_t)q * e_stride + e] = o[q];
+}
+
+// ---- bulk asynchronous copy global -> shared, completion on an mbarrier (TMA engine, sm_90+) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kEphThreads = 128;
+constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 8 B = 9 KB
+
+// One thread per orbit.  kind: 0 Keplerian, 1 Equinoctial, 2 Cometary; elem [6][n_orbits].
+// out [9][n_epochs][n_orbits] = ra, dec, geocentric_dist, heliocentric_dist, phase_angle,
+// solar_elongation, radial_velocity, d_ra_dt, d_dec_dt; status [n_epochs][n_orbits].
+__global__ void __launch_bounds__(kEphThreads)
+ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const double *__restrict__ epoch,
+                         const double *__restrict__ elem, size_t n_epochs, size_t e_stride,
+                         const double *__restrict__ mjd_tt, const double *__restrict__ table,
+                         const int *__restrict__ obs_status, double *__restrict__ out, int *__restrict__ status) {
+  __shared__ __align__(16) double tile[9 * kEphTile];
+  __shared__ __align__(8) unsigned long long bar;
+  const size_t i = (size_t)blockIdx.x * kEphThreads + threadIdx.x;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  // first tile in flight while the threads convert their elements
+  const unsigned first = (unsigned)(n_epochs < (size_t)kEphTile ? ((n_epochs + 1) & ~(size_t)1) : kEphTile);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 9u * first * 8u);
+    for (int q = 0; q < 9; ++q) bulk_g2s(tile + q * kEphTile, table + (size_t)q * e_stride, first * 8u, &bar);
+  }
+  // ---- per-orbit constants (OrbitalElements::compute preamble + the epoch-independent part of
+  //      propagate_twobody) ----
+  int orbit_status = 0;
+  double a = 0, h = 0, k = 0, lambda = 0, t_ref = 0, n_mot = 0, lon_peri = 0, ch = 0, ck = 0, bhk = 0;
+  V3 fv = V3{0, 0, 0}, gv = V3{0, 0, 0};
+  if (i < n_orbits) {
+    Equinoctial eq;
+    const int kd = kind[i];
+    if (kd == 1) {
+      eq.epoch = epoch[i];
+      eq.a = elem[i]; eq.h = elem[n_orbits + i]; eq.k = elem[2 * n_orbits + i];
+      eq.p = elem[3 * n_orbits + i]; eq.q = elem[4 * n_orbits + i]; eq.lambda = elem[5 * n_orbits + i];
+    } else {
+      Orbit orb;
+      orb.kind = kd; orb.corrected = 0; orb.epoch = epoch[i];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) orb.e[q] = elem[(size_t)q * n_orbits + i];
+      if (to_equinoctial(orb, eq) != 0) orbit_status = 9;  // every entry: InvalidConversion (mod.rs:196-213)
+    }
+    if (orbit_status == 0) {
+      const double e2 = eq.h * eq.h + eq.k * eq.k;
+      if (sqrt(e2) >= 1.0) {
+        orbit_status = 9;  // check_elliptical_orbit, wrapped as InvalidConversion (mod.rs:219-240)
+      } else {
+        a = eq.a; h = eq.h; k = eq.k; lambda = eq.lambda; t_ref = eq.epoch;
+        n_mot = sqrt(kMu / ((a * a) * a));
+        lon_peri = (e2 > kEps * 1e2) ? rem_euclid(atan2(h, k), kTwoPi) : 0.0;
+        const double beta = 1.0 / (1.0 + sqrt(1.0 - e2));
+        bhk = beta * h * k;
+        ch = 1.0 - beta * (h * h);
+        ck = 1.0 - beta * (k * k);
+        const double u = 1.0 + eq.p * eq.p + eq.q * eq.q;
+        const double inv_u = 1.0 / u;
+        const double common = 2.0 * eq.p * eq.q * inv_u;
+        fv = V3{(1.0 - eq.p * eq.p + eq.q * eq.q) * inv_u, common, -2.0 * eq.p * inv_u};
+        gv = V3{common, (1.0 + eq.p * eq.p - eq.q * eq.q) * inv_u, 2.0 * eq.q * inv_u};
+      }
+    }
+  }
+  unsigned parity = 0;
+  for (size_t e0 = 0; e0 < n_epochs; e0 += kEphTile) {
+    const unsigned te = (unsigned)(n_epochs - e0 < (size_t)kEphTile ? n_epochs - e0 : kEphTile);
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
+    if (i < n_orbits) {
+#pragma unroll 1
+      for (unsigned j = 0; j < te; ++j) {
+        const size_t e = e0 + j;
+        double o[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) o[q] = NAN;
+        int st = orbit_status;
+        if (st == 0) st = __ldg(obs_status + e);
+        if (st == 0) {
+          const double t_obs = __ldg(mjd_tt + e);
+          const double dt = t_obs - t_ref;
+          double lam1 = rem_euclid(lambda + n_mot * (dt - 0.0), kTwoPi);
+          if (lam1 < lon_peri) lam1 += kTwoPi;
+          // generalised Kepler equation, roots 0.0.8 Newton (equinoctial_element.rs:326-348)
+          const double eps = kEps * 1e2;
+          double x = kPi + lon_peri, sF, cF;
+          int iter = 0;
+          bool last = false, ok = true;
+          for (;;) {
+            sincos(x, &sF, &cF);
+            if (last) break;
+            const double f = x - k * sF + h * cF - lam1;
+            const double d = 1.0 - k * cF - h * sF;
+            if (fabs(f) < eps) break;
+            if (fabs(d) < eps) {
+              if (iter == 0) { x = x + 1.0; iter = 1; continue; }
+              ok = false;
+              break;
+            }
+            const double x1 = x - f / d;
+            const bool conv = fabs(x - x1) < eps;
+            x = x1;
+            if (conv) { last = true; continue; }
+            if (++iter >= 25) { ok = false; break; }
+          }
+          if (!ok) {
+            st = 11;  // RootFindingError
+          } else {
+            const double xe = a * (ch * cF + bhk * sF - k);
+            const double ye = a * (ck * sF + bhk * cF - h);
+            const double vc = n_mot * (a * a) / sqrt(xe * xe + ye * ye);
+            const double vxe = vc * (bhk * cF - ch * sF);
+            const double vye = vc * (ck * cF - bhk * sF);
+            const V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
+            const V3 av = ecl_to_equ(vxe * fv + vye * gv);
+            const V3 op = V3{tile[j], tile[kEphTile + j], tile[2 * kEphTile + j]};
+            const V3 ov = V3{tile[3 * kEphTile + j], tile[4 * kEphTile + j], tile[5 * kEphTile + j]};
+            const V3 ep = V3{tile[6 * kEphTile + j], tile[7 * kEphTile + j], tile[8 * kEphTile + j]};
+            const double helio = norm(ap);
+            const double geo = norm(ap - ep);
+            const V3 raw = ap - op;
+            const double ltt = norm(raw) / kVlightAu;
+            const V3 topo = raw - ltt * av;
+            o[0] = rem_euclid(atan2(topo.y, topo.x), kTwoPi);
+            o[1] = atan2(topo.z, sqrt(topo.x * topo.x + topo.y * topo.y));
+            o[2] = geo;
+            o[3] = helio;
+            const double rho = norm(topo);
+            const double r_obs = norm(op);
+            o[4] = acos(clampd(dot(ap, topo) / (helio * rho), -1.0, 1.0));
+            o[5] = acos(clampd(-dot(op, topo) / (r_obs * rho), -1.0, 1.0));
+            const V3 vt = av - ov;
+            o[6] = dot(topo, vt) / rho;
+            const double dxy2 = topo.x * topo.x + topo.y * topo.y;
+            const double dxy = sqrt(dxy2);
+            if (dxy < kEps * rho) {
+              o[7] = 0.0; o[8] = 0.0;
+            } else {
+              o[7] = (-topo.y * vt.x + topo.x * vt.y) / dxy2;
+              o[8] = (-topo.z * topo.x * vt.x - topo.z * topo.y * vt.y + dxy2 * vt.z) / (rho * rho * dxy);
+            }
+          }
+        }
+        if (st != 0) {
+#pragma unroll
+          for (int q = 0; q < 9; ++q) o[q] = NAN;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) out[((size_t)q * n_epochs + e) * n_orbits + i] = o[q];
+        status[e * n_orbits + i] = st;
+      }
+    }
+    // next tile: every thread is done reading this one
+    __syncthreads();
+    const size_t en = e0 + kEphTile;
+    if (en < n_epochs && threadIdx.x == 0) {
+      const size_t left = n_epochs - en;
+      const unsigned nt = (unsigned)(left < (size_t)kEphTile ? ((left + 1) & ~(size_t)1) : kEphTile);
+      mbar_expect_tx(&bar, 9u * nt * 8u);
+      for (int q = 0; q < 9; ++q) bulk_g2s(tile + q * kEphTile, table + (size_t)q * e_stride + en, nt * 8u, &bar);
+    }
+  }
+}
+
+}  // namespace ofb

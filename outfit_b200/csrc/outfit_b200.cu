@@ -22,6 +22,7 @@
 #include "dev_iod.cuh"
 #include "dev_correct.cuh"
 #include "dev_geometry.cuh"
+#include "dev_ephemeris.cuh"
 
 using namespace ofb;
 
@@ -1141,6 +1142,73 @@ extern "C" int outfit_b200_propagate_universal(OutfitCtx *ctx, size_t n, const d
     if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n * sizeof(int), cudaMemcpyDeviceToHost, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_universal: D2H / kernel", e);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- two-body Combined ephemeris (ephemeris/mod.rs:189-292) -------------------------------------------
+extern "C" int outfit_b200_ephemeris_twobody_device(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind,
+                                                    const double *epoch, const double *elem, size_t n_epochs,
+                                                    const double *mjd_tt, const double *mjd_ut1,
+                                                    const double body_fixed[3], double *out, int32_t *status,
+                                                    void *cuda_stream) {
+  if (!ctx || !body_fixed) return OUTFIT_E_INVALID_ARGUMENT;
+  if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  CK(cudaSetDevice(ctx->device));
+  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  // observer table [9][e_stride] + status[e_stride] in the context scratch (rows 16-byte aligned)
+  const size_t e_stride = (n_epochs + 1) & ~(size_t)1;
+  int rc = ensure_scratch(ctx, 9 * e_stride * sizeof(double) + e_stride * sizeof(int) + 256);
+  if (rc) return rc;
+  double *d_table = reinterpret_cast<double *>(ctx->scratch);
+  int *d_ost = reinterpret_cast<int *>(d_table + 9 * e_stride);
+  ephemeris_observer_kernel<<<(unsigned)((e_stride + 127) / 128), 128, 0, stream>>>(
+      ctx->eph, n_epochs, e_stride, mjd_tt, mjd_ut1, body_fixed[0], body_fixed[1], body_fixed[2], d_table, d_ost);
+  ephemeris_twobody_kernel<<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
+      n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                             const double *elem, size_t n_epochs, const double *mjd_tt,
+                                             const double *mjd_ut1, const double body_fixed[3], double *out,
+                                             int32_t *status) {
+  if (!ctx || !body_fixed) return OUTFIT_E_INVALID_ARGUMENT;
+  if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
+  const size_t n_ent = n_orbits * n_epochs;
+  const size_t in_bytes = ((n_orbits * 4 + 255) & ~(size_t)255) + ((n_orbits * 8 + 255) & ~(size_t)255) +
+                          ((6 * n_orbits * 8 + 255) & ~(size_t)255) + 2 * ((n_epochs * 8 + 255) & ~(size_t)255);
+  unsigned char *d = nullptr;
+  if (cudaMalloc(&d, in_bytes + 9 * n_ent * 8 + n_ent * 4 + 1024) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(ephemeris)");
+  size_t off = 0;
+  cudaError_t e = cudaSuccess;
+  auto put = [&](const void *src, size_t nbytes) -> void * {
+    void *dst = d + off;
+    off += (nbytes + 255) & ~(size_t)255;
+    if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, 0);
+    return dst;
+  };
+  const int32_t *d_kind = (const int32_t *)put(kind, n_orbits * 4);
+  const double *d_epoch = (const double *)put(epoch, n_orbits * 8);
+  const double *d_elem = (const double *)put(elem, 6 * n_orbits * 8);
+  const double *d_tt = (const double *)put(mjd_tt, n_epochs * 8);
+  const double *d_ut1 = (const double *)put(mjd_ut1, n_epochs * 8);
+  double *d_out = (double *)put(nullptr, 9 * n_ent * 8);
+  int32_t *d_st = (int32_t *)put(nullptr, n_ent * 4);
+  int rc = e == cudaSuccess ? OUTFIT_OK : fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: H2D", e);
+  if (rc == OUTFIT_OK)
+    rc = outfit_b200_ephemeris_twobody_device(ctx, n_orbits, d_kind, d_epoch, d_elem, n_epochs, d_tt, d_ut1, body_fixed, d_out, d_st, nullptr);
+  if (rc == OUTFIT_OK) {
+    e = cudaMemcpyAsync(out, d_out, 9 * n_ent * 8, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n_ent * 4, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: D2H / kernel", e);
   }
   cudaFree(d);
   return rc;

@@ -290,3 +290,46 @@ def make_propagation_states(n, seed=20261018):
     dt *= np.where(rng.uniform(0, 1, n) < 0.3, -1.0, 1.0)
     t0 = np.full(n, 60000.0)
     return np.ascontiguousarray(out_rv), t0, t0 + dt
+
+
+# ------------------------------------------------------------------------------------------------
+# two-body ephemeris inputs (BASELINE configs[4]: orbits x daily epochs, one observer)
+# ------------------------------------------------------------------------------------------------
+def make_ephemeris_orbits(n, seed=20261018, epoch0=59000.0, mixed_kinds=False):
+    """n elliptic main-belt / NEO-like orbits as (kind, epoch, elem[6, n]) in the OutfitIodResult
+    convention: kind 0 Keplerian (a, e, i, Omega, omega, M).  With mixed_kinds a tenth of the orbits is
+    given as Equinoctial (kind 1), a few as hyperbolic Cometary (kind 2: rejected, e >= 1) and one as
+    parabolic Cometary (conversion error) to exercise the per-orbit error paths."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(1.2, 3.5, n)
+    e = rng.uniform(0.0, 0.4, n)
+    inc = np.abs(rng.rayleigh(np.radians(8.0), n)) % np.pi
+    node, argp, M = (rng.uniform(0, 2 * np.pi, n) for _ in range(3))
+    kind = np.zeros(n, dtype=np.int32)
+    epoch = epoch0 + rng.uniform(-50.0, 50.0, n)
+    elem = np.ascontiguousarray(np.stack([a, e, inc, node, argp, M]))
+    if mixed_kinds and n >= 40:
+        sel = np.arange(0, n, 10)
+        dig = node[sel] + argp[sel]
+        th = np.tan(inc[sel] / 2.0)
+        elem[:, sel] = np.stack([a[sel], e[sel] * np.sin(dig), e[sel] * np.cos(dig), th * np.sin(node[sel]),
+                                 th * np.cos(node[sel]), (dig + M[sel]) % (2 * np.pi)])
+        kind[sel] = 1
+        hyp = np.arange(5, n, 37)
+        elem[0, hyp] = rng.uniform(0.5, 2.0, hyp.size)      # q
+        elem[1, hyp] = rng.uniform(1.05, 2.5, hyp.size)     # e > 1
+        elem[5, hyp] = rng.uniform(-1.0, 1.0, hyp.size)     # nu
+        kind[hyp] = 2
+        elem[1, 7] = 1.0                                     # parabolic cometary: InvalidConversion
+        kind[7] = 2
+    return kind, np.ascontiguousarray(epoch), elem
+
+
+def make_ephemeris_epochs(n_epochs, mjd0=59000.25, step=1.0, site_idx=1):
+    """Daily epochs (MJD TT), the matching UT1 argument (dUT1 = 0: UT1 = TT - 69.184 s here) and the
+    Earth-fixed observer position (AU) of one of the synthetic sites."""
+    mjd_tt = mjd0 + step * np.arange(n_epochs, dtype=np.float64)
+    mjd_ut1 = mjd_tt - 69.184 / 86400.0
+    lon, rc, rs = SITES[site_idx]
+    body_fixed = np.array([ERAU * rc * np.cos(lon), ERAU * rc * np.sin(lon), ERAU * rs])
+    return np.ascontiguousarray(mjd_tt), np.ascontiguousarray(mjd_ut1), body_fixed
