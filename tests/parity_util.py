@@ -89,3 +89,20 @@ def assert_iod_parity(got, want, elem_floor=None, rms_floor=None, min_plain_frac
     return dict(n_ok=int(ok.sum()), elem_p50=float(np.median(ee)), elem_max=float(ee.max()),
                 rms_p50=float(np.median(er)), rms_max=float(er.max()),
                 plain_elem_fraction=float((ee <= ELEM_TOL).mean()), plain_rms_fraction=float((er <= RMS_TOL).mean()))
+
+
+def oracle_observer_cache(O, et, batch):
+    """OutfitCache::build with the ORACLE (pvobs + helio_position) for a body-fixed batch:
+    returns (helio_equ [n,3], geo_ecl [n,3]) as the oracle's fit_full_iod expects them."""
+    import ctypes as C
+    n = len(batch["ra"])
+    geo = np.zeros((n, 3))
+    hel = np.zeros((n, 3))
+    L = O.lib()
+    for i in range(n):
+        dx, dv, vb, h = O.D3(), O.D3(), O.D3(0, 0, 0), O.D3()
+        L.oo_pvobs(float(batch["mjd_tt"][i]), float(batch["mjd_ut1"][i]), O.d3(batch["body_fixed"][:, i]), vb, dx, dv)
+        geo[i] = list(dx)
+        assert L.oo_helio_position(C.byref(et), float(batch["mjd_tt"][i]), dx, h) == 0
+        hel[i] = list(h)
+    return np.ascontiguousarray(hel), np.ascontiguousarray(geo)

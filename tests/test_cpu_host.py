@@ -203,3 +203,19 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "full_iod_trajectories_per_s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["value"] > 0
+
+
+def test_cpp_host_header_compiles(tmp_path):
+    """outfit_b200/host/outfit_b200.hpp (the C++17 mirror of the reference interface) builds against the
+    C-ABI with g++ alone and its host-side logic works without a GPU: builder validation
+    (mod.rs:544-624), total_cmp time sort (obs_dataset_api.rs:222-223), SoA flattening, and the
+    no-device error (no CPU fallback)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_smoke")
+    libdir = os.path.join(root, "outfit_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(root, "tests", "cpp", "host_header_smoke.cpp"),
+                           "-o", exe, "-L" + libdir, "-loutfit_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "threw=1 sorted=1" in out.stdout
