@@ -339,12 +339,14 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       Rr = correction_side<COUNT>(p2, p1, mid, dt21, has_chi, chi21, P.kepler_eps, w);
     }
     if (!(L.ok && Rr.ok)) {
-      // nothing was updated: every remaining iteration would repeat this one exactly
-      if (!has_chi) {
-        if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
-        break;
-      }
-      continue;
+      // The reference `continue`s here with NOTHING updated (positions, velocity and the chi warm
+      // starts are only committed after both sides succeed), so every remaining iteration would
+      // repeat this one bit for bit and the loop would end after newton_max_it passes with the
+      // current state (gauss.rs:1310-1330).  Leaving now is exact -- and these are the candidates
+      // whose every Kepler solve exhausts its 50 Newton steps: left to repeat, a single one of them
+      // ran for 15 ms (clock64 probe, profiles/r01n_stragglers.log) and set the duration of the launch.
+      if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
+      break;
     }
     has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
     const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};

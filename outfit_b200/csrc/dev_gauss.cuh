@@ -110,20 +110,37 @@ __device__ __forceinline__ int aberth8(double c0, double c3, double c6, unsigned
                                        double (&zr)[8], double (&zi)[8], Work &w) {
   // Cauchy-type start radius: smallest integer r0 with S(r0) > 0, S(w) = w^8 - |c6| w^6 - |c3| w^3 - |c0|
   const double s0 = -fabs(c0), s3 = -fabs(c3), s6 = -fabs(c6);
-  double r0 = 1.0;
-  for (int guard = 0; guard < 100000; ++guard) {
+  // The crate walks r0 = 1, 2, 3, ... (at most 100000 steps).  S is negative below its single positive
+  // root and positive above it, and rounding can only blur the sign within ~1e-12 relative of that
+  // root, far less than the unit spacing of the candidates: the first integer with S > 0 is found by
+  // doubling + bisection in <= 34 evaluations instead of up to 1e5 (r0 reaches 1e4..1e5 on a few
+  // candidates per 100k trajectories; walked one by one they were the long pole of this kernel).
+  auto s_pos = [&](double rr) {
     double r = 0.0;
-    r = __dsub_rn(__fma_rn(r, r0, 1.0), 0.0);
-    r = __fma_rn(r, r0, -0.0);
-    r = __fma_rn(r, r0, s6);
-    r = __fma_rn(r, r0, -0.0);
-    r = __fma_rn(r, r0, -0.0);
-    r = __fma_rn(r, r0, s3);
-    r = __fma_rn(r, r0, -0.0);
-    r = __fma_rn(r, r0, -0.0);
-    r = __fma_rn(r, r0, s0);
-    if (r > 0.0) break;
-    r0 += 1.0;
+    r = __dsub_rn(__fma_rn(r, rr, 1.0), 0.0);
+    r = __fma_rn(r, rr, -0.0);
+    r = __fma_rn(r, rr, s6);
+    r = __fma_rn(r, rr, -0.0);
+    r = __fma_rn(r, rr, -0.0);
+    r = __fma_rn(r, rr, s3);
+    r = __fma_rn(r, rr, -0.0);
+    r = __fma_rn(r, rr, -0.0);
+    r = __fma_rn(r, rr, s0);
+    return r > 0.0;
+  };
+  double r0 = 1.0;
+  if (!s_pos(1.0)) {
+    double lo = 1.0, hi = 2.0;  // S(lo) <= 0
+    while (hi < 100000.0 && !s_pos(hi)) { lo = hi; hi = hi * 2.0; }
+    if (hi >= 100000.0) {
+      hi = 100000.0;
+      if (!s_pos(hi)) { lo = hi; hi = 100001.0; }  // the crate's walk ends at 100001 without a sign change
+    }
+    while (hi - lo > 1.0) {
+      const double mid = floor(0.5 * (lo + hi));
+      if (s_pos(mid)) hi = mid; else lo = mid;
+    }
+    r0 = hi;
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {

@@ -198,6 +198,9 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCorrectThreads + threadIdx.x;
   WorkC w;
   w.roots_accepted = 0; w.fg_iterations = 0; w.kepler_solves = 0; w.newton_steps = 0; w.sfunct_terms = 0;
+#ifdef OUTFIT_DEBUG_STRAGGLERS
+  const long long dbg_t0 = clock64();
+#endif
   unsigned long long tr;
   unsigned r, m;
   if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
@@ -278,6 +281,12 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
       }
     }
     S.state_kind[cid] = kind;
+#ifdef OUTFIT_DEBUG_STRAGGLERS
+    // slowest thread of the launch ((cycles >> 8) << 26 | cid) and the total thread time (cycles >> 8)
+    const unsigned long long dc = (unsigned long long)(clock64() - dbg_t0);
+    atomicMax(work_counters + 20, ((dc >> 8) << 26) | (cid & 0x3ffffffull));
+    atomicAdd(work_counters + 24, dc >> 8);
+#endif
   }
   if (COUNT) {
     Work wk;
@@ -1054,6 +1063,14 @@ extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *
   out->gauss_solves = h[1]; out->aberth_sweeps = h[2]; out->roots_accepted = h[3]; out->fg_iterations = h[4];
   out->kepler_universal_solves = h[5]; out->newton_steps = h[6]; out->sfunct_terms = h[7];
   out->scorer_evals = h[8]; out->scorer_newton_steps = h[9]; out->candidates = h[10];
+  return OUTFIT_OK;
+}
+
+// debug builds only (make EXTRA=-DOUTFIT_DEBUG_STRAGGLERS): the raw counter slots
+extern "C" int outfit_b200_debug_counters(OutfitCtx *ctx, unsigned long long *out32) {
+  if (!ctx || !out32) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out32, ctx->d_counters, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return OUTFIT_OK;
 }
 
