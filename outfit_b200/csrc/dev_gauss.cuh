@@ -77,9 +77,10 @@ __device__ __forceinline__ Cx cx_horner_step(Cx r, Cx x, double c) {
 
 // p(z) = z^8 + c6 z^6 + c3 z^3 + c0 and p'(z), dense Horner (zeros included: they round)
 __device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6, Cx &p, Cx &dp) {
-  Cx r = Cx{0.0, 0.0};
-  r = cx_horner_step(r, z, 1.0);
-  r = cx_horner_step(r, z, 0.0);
+  // The first two dense Horner steps are exact: (0*z + 1) = 1 and (1*z + 0) = z (resp. 8 and 8z for
+  // the derivative; scaling by 8 is exact), so the recurrences start from z and 8z.  (Only the sign of
+  // a zero component can differ, which no later operation observes; a non-finite z stays non-finite.)
+  Cx r = z;
   r = cx_horner_step(r, z, c6);
   r = cx_horner_step(r, z, 0.0);
   r = cx_horner_step(r, z, 0.0);
@@ -88,9 +89,7 @@ __device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6
   r = cx_horner_step(r, z, 0.0);
   r = cx_horner_step(r, z, c0);
   p = r;
-  Cx d = Cx{0.0, 0.0};
-  d = cx_horner_step(d, z, 8.0);
-  d = cx_horner_step(d, z, 0.0);
+  Cx d = Cx{__dmul_rn(8.0, z.re), __dmul_rn(8.0, z.im)};
   d = cx_horner_step(d, z, __dmul_rn(c6, 6.0));
   d = cx_horner_step(d, z, 0.0);
   d = cx_horner_step(d, z, 0.0);
@@ -100,14 +99,14 @@ __device__ __forceinline__ void poly8_eval(Cx z, double c0, double c3, double c6
   dp = d;
 }
 
-// returns 0 converged / 1 max-iter / 2 failed; the 8 iterates (index order k) are left in zr/zi.
+// returns 0 converged / 1 max-iter / 2 failed; the 8 iterates (index order k) are left in zsm.
 // One Jacobi sweep = (1) the 28 pair reciprocals 1/(z_i - z_k), i < k, each added to sum_i and
 // subtracted from sum_k -- IEEE negation is exact, and visiting the pairs in lexicographic order
 // delivers every sum its terms in increasing index order, so the sums are bit-identical to the
 // crate's 56-reciprocal double loop at half the divisions; (2) per root: dense Horner p, p',
 // w = p / (p * sum - p'), z += w.  Fully unrolled on registers (this kernel's code is small).
 __device__ __forceinline__ int aberth8(double c0, double c3, double c6, unsigned max_iter, double eps,
-                                       double (&zr)[8], double (&zi)[8], Work &w) {
+                                       volatile double *zsm, unsigned stride, Work &w) {
   // Cauchy-type start radius: smallest integer r0 with S(r0) > 0, S(w) = w^8 - |c6| w^6 - |c3| w^3 - |c0|
   const double s0 = -fabs(c0), s3 = -fabs(c3), s6 = -fabs(c6);
   // The crate walks r0 = 1, 2, 3, ... (at most 100000 steps).  S is negative below its single positive
@@ -142,39 +141,50 @@ __device__ __forceinline__ int aberth8(double c0, double c3, double c6, unsigned
     }
     r0 = hi;
   }
-#pragma unroll
+  // zsm: this thread's column of a [32][blockDim.x] shared array: z re (0-7), z im (8-15),
+  // sum re (16-23), sum im (24-31).  The 28-pair section is unrolled on registers; the per-root
+  // update is a ROLLED loop over shared memory: fully unrolled, one sweep was ~40 KB of SASS, more
+  // than the 32 KB instruction cache level, and 30 % of the issue slots stalled on instruction fetch
+  // (ncu r01q: stall_no_inst).
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) {
-    zr[k] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
-    zi[k] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
+    zsm[k * stride] = __dadd_rn(-0.0, __dmul_rn(r0, c_aberth_dir[2 * k]));
+    zsm[(8 + k) * stride] = __dmul_rn(r0, c_aberth_dir[2 * k + 1]);
   }
+#pragma unroll 1
   for (unsigned it = 0; it < max_iter; ++it) {
     ++w.aberth_sweeps;
-    double sr[8], si[8];
+    {
+      double zr[8], zi[8], sr[8], si[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { sr[k] = 0.0; si[k] = 0.0; }
+      for (int k = 0; k < 8; ++k) { zr[k] = zsm[k * stride]; zi[k] = zsm[(8 + k) * stride]; sr[k] = 0.0; si[k] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll
-      for (int k = i + 1; k < 8; ++k) {
-        const Cx rec = cx_recip(Cx{__dsub_rn(zr[i], zr[k]), __dsub_rn(zi[i], zi[k])});
-        sr[i] = __dadd_rn(sr[i], rec.re);
-        si[i] = __dadd_rn(si[i], rec.im);
-        sr[k] = __dadd_rn(sr[k], -rec.re);  // 1/(z_k - z_i) = -(1/(z_i - z_k)) exactly
-        si[k] = __dadd_rn(si[k], -rec.im);
+        for (int k = i + 1; k < 8; ++k) {
+          const Cx rec = cx_recip(Cx{__dsub_rn(zr[i], zr[k]), __dsub_rn(zi[i], zi[k])});
+          sr[i] = __dadd_rn(sr[i], rec.re);
+          si[i] = __dadd_rn(si[i], rec.im);
+          sr[k] = __dadd_rn(sr[k], -rec.re);  // 1/(z_k - z_i) = -(1/(z_i - z_k)) exactly
+          si[k] = __dadd_rn(si[k], -rec.im);
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { zsm[(16 + k) * stride] = sr[k]; zsm[(24 + k) * stride] = si[k]; }
     }
     bool converged = true;
     bool failed = false;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; ++i) {
-      const Cx z = Cx{zr[i], zi[i]};
+      const Cx z = Cx{zsm[i * stride], zsm[(8 + i) * stride]};
+      const Cx sum = Cx{zsm[(16 + i) * stride], zsm[(24 + i) * stride]};
       Cx p, dp;
       poly8_eval(z, c0, c3, c6, p, dp);
-      const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, Cx{sr[i], si[i]}), dp)));
+      const Cx nz = cx_add(z, cx_div(p, cx_sub(cx_mul(p, sum), dp)));
       if (!(isfinite(nz.re) && isfinite(nz.im))) failed = true;
       if (!(fabs(__dsub_rn(nz.re, z.re)) < eps && fabs(__dsub_rn(nz.im, z.im)) < eps)) converged = false;
-      zr[i] = nz.re;  // in place: no later root of this sweep reads z_i (the sums are complete)
-      zi[i] = nz.im;
+      zsm[i * stride] = nz.re;  // in place: no later root of this sweep reads z_i (the sums are complete)
+      zsm[(8 + i) * stride] = nz.im;
     }
     if (failed) return 2;  // the caller maps it to PolynomialRootFindingFailed
     if (converged) return 0;

@@ -144,9 +144,13 @@ __device__ __forceinline__ void load_triplet(const IodBatchDev &B, const IodDevP
 }
 
 // ---- P1: geometry + polynomial + Aberth ---------------------------------------------------------
-__global__ void __launch_bounds__(kCandThreads)
+#ifndef OUTFIT_ROOTS_BPS
+#define OUTFIT_ROOTS_BPS 4
+#endif
+__global__ void __launch_bounds__(kCandThreads, OUTFIT_ROOTS_BPS)
 roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  double zr[8], zi[8];
+  extern __shared__ __align__(16) double roots_sm[];  // [32][kCandThreads]: iterates + Aberth sums
+  volatile double *zsm = roots_sm + threadIdx.x;
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
   Work w;
   memset(&w, 0, sizeof w);
@@ -164,13 +168,13 @@ roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
     double c0, c3, c6;
     if (!gauss_geometry(g, gm)) code = OUTFIT_ST_SINGULAR_DIRECTION_MATRIX;
     else if (!gauss_polynomial(g, gm, c0, c3, c6)) code = OUTFIT_ST_GAUSS_NO_ROOTS;
-    else if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zr, zi, w) == 2) code = OUTFIT_ST_POLY_ROOT_FAILED;
+    else if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zsm, kCandThreads, w) == 2) code = OUTFIT_ST_POLY_ROOT_FAILED;
     else {
       // visit_real_positive_roots + plausibility window (gauss.rs:975-981, 1148), solver order kept
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; ++k) {
-        const double re = zr[k];
-        if (re > 0.0 && fabs(zi[k]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
+        const double re = zsm[k * kCandThreads];
+        if (re > 0.0 && fabs(zsm[(8 + k) * kCandThreads]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
           S.roots[(size_t)n * S.n_cand + cid] = re;
           ++n;
         }
@@ -896,7 +900,7 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
     triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
     mark();
-    roots_kernel<<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+    roots_kernel<<<cblocks, kCandThreads, 32 * kCandThreads * sizeof(double), stream>>>(B, P, S, ctx->d_counters + 1);
     mark();
     if (ctx->count_work) correct_kernel<true><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
     else correct_kernel<false><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
