@@ -6,6 +6,7 @@ import csv, io, os, re, subprocess, sys, tempfile
 from collections import Counter, defaultdict
 rep, kname, lib = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+sect = sys.argv[5] if len(sys.argv) > 5 else kname  # substring of the mangled section name (template instances)
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", kname],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
@@ -31,7 +32,7 @@ ins = []; cur = ("?", 0); take = False
 for line in dis:
     m = re.match(r"\s*//-+ \.text\.(\S+)", line)
     if m:
-        take = kname in m.group(1); continue
+        take = sect in m.group(1); continue
     if not take:
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
