@@ -175,10 +175,11 @@ series_done:
 
 // cold-start guess (first f-g iteration of a root only): scalars by value, no stack traffic in the caller
 __device__ __noinline__ double prelim_kepuni_v(double dt, double r0, double sig0, double alpha, double e0,
-                                               double convergency) {
+                                               double convergency, unsigned max_iter_prelim = 20,
+                                               int parabolic_newton = 0) {
   KepIn kp;
   kp.dt = dt; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
-  kp.convergency = convergency; kp.max_iter_prelim = 20; kp.parabolic_newton = 0;
+  kp.convergency = convergency; kp.max_iter_prelim = max_iter_prelim; kp.parabolic_newton = parabolic_newton;
   return prelim_kepuni(kp);
 }
 
@@ -186,7 +187,7 @@ __device__ __noinline__ double prelim_kepuni_v(double dt, double r0, double sig0
 // Returns ok; on success psi and (s2, s3) of the accepted evaluation.
 template <bool COUNT>
 __device__ __forceinline__ bool kepuni_newton_fast(double dt, double r0, double sig0, double alpha, double convergency,
-                                                   double &psi, double &s2, double &s3, WorkC &w) {
+                                                   double &psi, double &s2, double &s3, WorkC &w, double *s01 = nullptr) {
   const double sdt = kGaussK * dt;
   const double tol = 10.0 * kEps * (1.0 + fabs(sdt));
   bool final_eval = false;
@@ -200,6 +201,7 @@ __device__ __forceinline__ bool kepuni_newton_fast(double dt, double r0, double 
     }
     double s0, s1;
     s_funct_fast<COUNT>(psi, alpha, s0, s1, s2, s3, w.sfunct_terms);
+    if (s01) { s01[0] = s0; s01[1] = s1; }
     if (final_eval) return true;
     const double res = r0 * s1 + sig0 * s2 + s3 - sdt;
     const double der = r0 * s0 + sig0 * s1 + s2;

@@ -188,7 +188,8 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   const V3 cor = rel - ltt * vel;
   const double dec = atan2(cor.z, hypot(cor.x, cor.y));
   const double ra = rem_euclid(atan2(cor.y, cor.x), kTwoPi);
-  double da = fmod(ra_obs - ra, kTwoPi);
+  double da = ra_obs - ra;
+  if (!(fabs(da) < kTwoPi)) da = fmod(da, kTwoPi);  // |x| < m: fmod(x, m) == x exactly
   if (da > kPi) da -= kTwoPi;  // reference quirk: wraps only the > pi side
   const double a = cos_dec_obs * (da / sig_ra);
   const double b = (dec_obs - dec) / sig_dec;

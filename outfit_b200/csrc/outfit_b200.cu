@@ -503,8 +503,6 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
                            OutfitSolverType st, double *__restrict__ out, int *__restrict__ status) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Work w;
-  memset(&w, 0, sizeof w);
   const V3 r = V3{rv[i], rv[n + i], rv[2 * n + i]};
   const V3 v = V3{rv[3 * n + i], rv[4 * n + i], rv[5 * n + i]};
   double o[11];
@@ -521,30 +519,45 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
     const V3 h = cross(r, v);
     double e0 = sqrt(1.0 + alpha * dot(h, h) / kMu);
     e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
-    KepIn kp;
-    kp.dt = t1[i] - t0[i]; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
-    kp.convergency = st.convergency;
-    kp.max_iter_prelim = (unsigned)st.max_iter_prelim_kepuni;
-    kp.parabolic_newton = st.parabolic_method;
-    const double psi0 = psi_guess ? psi_guess[i] : prelim_kepuni(kp);
-    KepSol sol;
-    sol.ok = false;
-    if (st.kind == OUTFIT_SOLVER_NEWTON || st.kind == OUTFIT_SOLVER_AUTO) sol = solve_kepuni_newton(kp, psi0, w);
-    if (!sol.ok && st.kind != OUTFIT_SOLVER_NEWTON) sol = solve_kepuni_brent(kp, psi0, w);
-    if (!sol.ok) {
+    const double dt = t1[i] - t0[i];
+    // initial guess (prelim_kepler/*.rs) out of line, Newton (newton_solver.rs:240-352) inlined with the
+    // register-resident Stumpff series of dev_correct.cuh: same operations, same bits as dev_kepler.cuh
+    double psi = psi_guess ? psi_guess[i]
+                           : prelim_kepuni_v(dt, r0, sig0, alpha, e0, st.convergency, (unsigned)st.max_iter_prelim_kepuni,
+                                             st.parabolic_method);
+    const double psi0 = psi;
+    double s01[2] = {0.0, 0.0}, s2 = 0.0, s3 = 0.0;
+    WorkC wc;
+    wc.roots_accepted = 0; wc.fg_iterations = 0; wc.kepler_solves = 0; wc.newton_steps = 0; wc.sfunct_terms = 0;
+    bool ok = false;
+    if (st.kind == OUTFIT_SOLVER_NEWTON || st.kind == OUTFIT_SOLVER_AUTO)
+      ok = kepuni_newton_fast<false>(dt, r0, sig0, alpha, st.convergency, psi, s2, s3, wc, s01);
+    if (!ok && st.kind != OUTFIT_SOLVER_NEWTON) {  // Brent-Dekker (rare): the out-of-line reference statement
+      KepIn kp;
+      kp.dt = dt; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
+      kp.convergency = st.convergency;
+      kp.max_iter_prelim = (unsigned)st.max_iter_prelim_kepuni;
+      kp.parabolic_newton = st.parabolic_method;
+      Work w;
+      memset(&w, 0, sizeof w);
+      const KepSol sol = solve_kepuni_brent(kp, psi0, w);
+      ok = sol.ok;
+      psi = sol.psi; s01[0] = sol.s.s0; s01[1] = sol.s.s1; s2 = sol.s.s2; s3 = sol.s.s3;
+    }
+    if (!ok) {
       stt = st.kind == OUTFIT_SOLVER_NEWTON ? OUTFIT_ST_NEWTON_KEPLER : OUTFIT_ST_BRENT_KEPLER;
     } else {
-      const double r1 = r0 * sol.s.s0 + sig0 * sol.s.s1 + sol.s.s2;
+      const double r1 = r0 * s01[0] + sig0 * s01[1] + s2;
       if (r1 < kEps) {
         stt = OUTFIT_ST_DEGENERATE_STATE;
       } else {
-        const double fl = 1.0 - sol.s.s2 / r0;
-        const double gl = (r0 * sol.s.s1 + sig0 * sol.s.s2) / kGaussK;
-        const double fd = -(kGaussK / (r0 * r1)) * sol.s.s1;
-        const double gd = 1.0 - sol.s.s2 / r1;
+        const double fl = 1.0 - s2 / r0;
+        const double gl = (r0 * s01[1] + sig0 * s2) / kGaussK;
+        const double fd = -(kGaussK / (r0 * r1)) * s01[1];
+        const double gd = 1.0 - s2 / r1;
         o[0] = fl * r.x + gl * v.x; o[1] = fl * r.y + gl * v.y; o[2] = fl * r.z + gl * v.z;
         o[3] = fd * r.x + gd * v.x; o[4] = fd * r.y + gd * v.y; o[5] = fd * r.z + gd * v.z;
-        o[6] = fl; o[7] = gl; o[8] = fd; o[9] = gd; o[10] = sol.psi;
+        o[6] = fl; o[7] = gl; o[8] = fd; o[9] = gd; o[10] = psi;
       }
     }
   }
