@@ -350,18 +350,38 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
       break;
     }
+    // An iteration that ends in one of the `continue`s below commits only the chi warm starts.  If they
+    // come out bit-identical to the ones it started from, the next iteration has exactly the same
+    // inputs (positions, velocity, middle state, chi) and therefore the same outcome, and so on until
+    // newton_max_it: leaving now is exact.  This is the fate of ~45 % of the accepted roots (the new
+    // geocentric distance falls below min_rho2_au on the first or second pass and the warm-started
+    // Kepler solves return their guess), which the reference walks through all 50 iterations.
+    const bool same_chi = has_chi && L.chi == chi01 && Rr.chi == chi21;
     has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
     const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
     const double fl = L.f * Rr.g - Rr.f * L.g;
-    if (!isfinite(fl) || fabs(fl) < kEps) continue;
-    const double inv_f = 1.0 / fl;
+    bool stall = !isfinite(fl) || fabs(fl) < kEps;
     V3 n0, n1, n2;
-    double nep;
-    if (!positions_c(G, Rr.g * inv_f, -L.g * inv_f, P.min_rho2_au, n0, n1, n2, nep)) continue;
-    const MidC nm = middle_state(n1, nv, P.max_perihelion_au, P.max_ecc);
-    if (!nm.defined || !nm.accepted) return false;
-    const double denom = sqrt((dot(n0, n0) + dot(n1, n1)) + dot(n2, n2));
-    if (!isfinite(denom) || denom <= kEps) continue;
+    double nep = 0.0;
+    if (!stall) {
+      const double inv_f = 1.0 / fl;
+      stall = !positions_c(G, Rr.g * inv_f, -L.g * inv_f, P.min_rho2_au, n0, n1, n2, nep);
+    }
+    MidC nm;
+    double denom = 0.0;
+    if (!stall) {
+      nm = middle_state(n1, nv, P.max_perihelion_au, P.max_ecc);
+      if (!nm.defined || !nm.accepted) return false;
+      denom = sqrt((dot(n0, n0) + dot(n1, n1)) + dot(n2, n2));
+      stall = !isfinite(denom) || denom <= kEps;
+    }
+    if (stall) {
+      if (same_chi) {
+        if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
+        break;
+      }
+      continue;
+    }
     const V3 d0 = n0 - p0, d1 = n1 - p1, d2 = n2 - p2;
     const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
     p0 = n0; p1 = n1; p2 = n2;
