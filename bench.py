@@ -129,7 +129,17 @@ def oracle_rate(batch, table, kw, target_s=15.0, n_threads=0):
     return n / dt, n, dt, O.counters()
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print to fd 1 (NCCL's version banner) are sent
+    to stderr; returns a file object on the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -182,14 +192,14 @@ def main():
         dt = (time.perf_counter() - t0) / max(1, args.steps)
         v = per_step / dt
         sample = f"{per_step} trajectories of the same workload per step, all {cores} host threads (pthread pool, one task per trajectory)"
-        print(json.dumps({
+        print(file=out_stream, flush=True, *[json.dumps({
             "impl": "reference", "metric": "full_iod_trajectories_per_s", "value": v, "unit": "trajectories/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "C restatement of the reference's Rayon path (oracle/); the Rust reference cannot be built in this image"},
-            "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
         return
 
     # ------------------------------------------------------------------------------ our arm
@@ -349,9 +359,12 @@ def main():
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         if kep is not None:
-            kr = torch.tensor([kep["propagate_universal_per_s"]], dtype=torch.float64, device=dev)
+            kr = torch.tensor([kep["propagate_universal_per_s"], eph["entries_per_s"] if eph else 0.0],
+                              dtype=torch.float64, device=dev)
             dist.all_reduce(kr, op=dist.ReduceOp.SUM)
-            kep["propagate_universal_per_s"] = float(kr.item())
+            kep["propagate_universal_per_s"] = float(kr[0].item())
+            if eph:
+                eph["entries_per_s"] = float(kr[1].item())
     ms, e2e_ms, kernel_ms_max = (float(x) for x in tm.tolist())
 
     if rank == 0:
@@ -404,7 +417,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
                                    "sample": f"first {n} trajectories of the same batch, {dt:.1f} s wall on all {cores} host threads "
                                              "(C restatement of the reference's Rayon path; per-candidate Earth re-evaluation kept)"}
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
