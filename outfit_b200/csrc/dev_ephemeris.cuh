@@ -137,7 +137,10 @@ constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 
 // One thread per orbit.  kind: 0 Keplerian, 1 Equinoctial, 2 Cometary; elem [6][n_orbits].
 // out [9][n_epochs][n_orbits] = ra, dec, geocentric_dist, heliocentric_dist, phase_angle,
 // solar_elongation, radial_velocity, d_ra_dt, d_dec_dt; status [n_epochs][n_orbits].
-__global__ void __launch_bounds__(kEphThreads)
+#ifndef OUTFIT_EPH_BPS
+#define OUTFIT_EPH_BPS 5  // 96 registers, 20 warps per SM: 10.0 ms per 1e8 entries against 10.6 at 4 (r02b)
+#endif
+__global__ void __launch_bounds__(kEphThreads, OUTFIT_EPH_BPS)
 ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const double *__restrict__ epoch,
                          const double *__restrict__ elem, size_t n_epochs, size_t e_stride,
                          const double *__restrict__ mjd_tt, const double *__restrict__ table,

@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-for st in ""; do echo "stages [$st]"; OUTFIT_B200_LIB=outfit_b200/variants/lib_dbg.so OUTFIT_B200_FG_STAGES="$st" python tools/gpu_stragglers.py 2>&1 | tail -5; done | tee gpurun_out/r01z2_sections.log
+TAG=${1:-ab}
+python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.log
+OUTFIT_B200_STREAMS=1 PERF_PARITY=1 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB=|parity" | tee gpurun_out/${TAG}_ab.log
+python tools/gpu_perf_eph.py | tee -a gpurun_out/${TAG}_ab.log
