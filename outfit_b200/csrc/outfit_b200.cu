@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -588,6 +589,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters)
 // context + C-ABI
 // =================================================================================================
 struct OutfitCtx {
+  std::recursive_mutex mu;  // one call at a time per context (the scratch, arena and streams are per context)
   int device = 0;
   int sm_count = 0;
   std::string last_error;
@@ -714,6 +716,7 @@ extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
 
 extern "C" int outfit_b200_set_pass_streams(OutfitCtx *ctx, int n_streams) {
   if (!ctx || n_streams < 1 || n_streams > 8) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   ctx->n_streams = n_streams;
   return OUTFIT_OK;
 }
@@ -743,6 +746,7 @@ extern "C" int outfit_b200_load_ephemeris(OutfitCtx *ctx, const double *cheb, si
                                           size_t block_stride, double jd_start, double block_days,
                                           const uint32_t ipt[3][3], double emrat) {
   if (!ctx || !cheb || n_blocks == 0 || block_stride == 0 || !(block_days > 0.0)) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   for (int b = 0; b < 3; ++b) {
     if (ipt[b][1] < 3 || ipt[b][1] > kMaxCheb || ipt[b][2] == 0) return fail(ctx, OUTFIT_E_UNSUPPORTED, "ipt: n_coeff must be in [3, 18]");
     if ((size_t)ipt[b][0] + (size_t)ipt[b][1] * ipt[b][2] * 3 > block_stride) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "ipt exceeds block_stride");
@@ -943,6 +947,7 @@ extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodPa
                                                const OutfitObsBatch *batch, OutfitIodResult *out,
                                                void *cuda_stream) {
   if (!ctx || !params || !batch || (!out && batch->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   int rc = outfit_b200_iod_params_validate(params);
   if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
   CK(cudaSetDevice(ctx->device));
@@ -972,6 +977,7 @@ extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodPa
 extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *params,
                                         const OutfitObsBatch *hb, OutfitIodResult *out) {
   if (!ctx || !params || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   int rc = outfit_b200_iod_params_validate(params);
   if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
   if (hb->n_traj && (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec))
@@ -1076,6 +1082,7 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
 
 extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *out) {
   if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   unsigned long long h[32];
   CK(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
@@ -1096,12 +1103,14 @@ extern "C" int outfit_b200_debug_counters(OutfitCtx *ctx, unsigned long long *ou
 
 extern "C" int outfit_b200_set_work_counters(OutfitCtx *ctx, int enabled) {
   if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   ctx->count_work = enabled != 0;
   return OUTFIT_OK;
 }
 
 extern "C" int outfit_b200_last_iod_phase_ms(OutfitCtx *ctx, OutfitIodPhaseMs *out) {
   if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   memset(out, 0, sizeof *out);
   out->n_chunks = ctx->phase_chunks;
   out->kernel_launches = ctx->phase_chunks * 5u + ctx->phase_observer_kernels;
@@ -1132,6 +1141,7 @@ extern "C" int outfit_b200_observer_cache_device(OutfitCtx *ctx, size_t n, const
                                                  const double *mjd_ut1, const double *bf, double *geo_ecl,
                                                  double *helio_equ, int32_t *status, void *cuda_stream) {
   if (!ctx || (n && (!mjd_tt || !mjd_ut1 || !bf || !geo_ecl || !helio_equ))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return OUTFIT_OK;
@@ -1147,6 +1157,7 @@ extern "C" int outfit_b200_propagate_universal_device(OutfitCtx *ctx, size_t n, 
                                                       const OutfitSolverType *solver, double *out, int32_t *status,
                                                       void *cuda_stream) {
   if (!ctx || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return OUTFIT_OK;
   const int tpb = 128;
@@ -1160,6 +1171,7 @@ extern "C" int outfit_b200_propagate_universal(OutfitCtx *ctx, size_t n, const d
                                                const double *t1, const double *psi_guess,
                                                const OutfitSolverType *solver, double *out, int32_t *status) {
   if (!ctx || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return OUTFIT_OK;
   const size_t in_d = (8 + (psi_guess ? 1 : 0)) * n, out_d = 11 * n;
@@ -1191,6 +1203,7 @@ extern "C" int outfit_b200_ephemeris_twobody_device(OutfitCtx *ctx, size_t n_orb
                                                     const double body_fixed[3], double *out, int32_t *status,
                                                     void *cuda_stream) {
   if (!ctx || !body_fixed) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
   CK(cudaSetDevice(ctx->device));
@@ -1215,6 +1228,7 @@ extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, co
                                              const double *mjd_ut1, const double body_fixed[3], double *out,
                                              int32_t *status) {
   if (!ctx || !body_fixed) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
   if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
@@ -1253,6 +1267,7 @@ extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, co
 
 extern "C" int outfit_b200_measure_fp64_peak(OutfitCtx *ctx, double *flops_per_s) {
   if (!ctx || !flops_per_s) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   double *sink = nullptr;
   CK(cudaMalloc(&sink, 8));

@@ -324,3 +324,38 @@ def test_full_size_properties_100k(env):
     want = O.fit_full_iod(O.from_soa_batch(sl), env["et"], op, n_threads=0)
     ef, rf = oracle_floor(O, synth, sl, env["et"], op, want)
     assert_iod_parity(a[5000:5400], want, ef, rf)
+
+
+def test_passes_in_flight_and_entry_points_agree(env):
+    """Large batches run as 8 passes on 8 streams (and the host entry point slices its input copy behind
+    them): results are bit-identical to a single pass on one stream, and the host-buffer and
+    device-buffer entry points agree."""
+    import torch
+    from outfit_b200 import IODParams, RESULT_DTYPE
+    synth, ctx = env["synth"], env["ctx"]
+    T, K, nn = 9000, 6, 2
+    batch = synth.make_trajectories(T, 8, seed=131, table=env["table"], max_triplets=K, n_noise=nn)
+    params = IODParams.builder(n_noise_realizations=nn, max_triplets=K, noise_scale=1.0)
+    try:
+        ctx.set_pass_streams(1)
+        one = ctx.fit_full_iod(batch, params)
+        ctx.set_pass_streams(8)
+        many = ctx.fit_full_iod(batch, params)
+        dev = torch.device("cuda")
+        keys = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "noise_z"]
+        devb = {k: torch.from_numpy(batch[k].view(np.int64) if batch[k].dtype == np.uint64 else batch[k]).to(dev) for k in keys}
+        d_out = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        ctx.fit_full_iod_device(devb, params, d_out, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        on_dev = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    finally:
+        ctx.set_pass_streams(8)
+    assert one.tobytes() == many.tobytes()
+    assert one.tobytes() == on_dev.tobytes()
+    assert (one["status"] == 0).mean() > 0.8
+
+
+def test_parity_more_triplets_than_a_warp(env):
+    """max_triplets = 40 > 32 lanes, n_noise = 0: the best-K container beyond one warp-wide chunk."""
+    _, got, want, ef, rf = run_both(env, 300, 14, seed=132, K=40, nn=0)
+    assert_iod_parity(got, want, ef, rf)
