@@ -56,7 +56,11 @@ KERNEL_PHASE = {"roots_kernel": "roots_ms", "correct_kernel": "correct_ms", "sco
 
 
 def algorithmic_flops(counters, keys=None):
-    return sum(W_FLOP[k] * counters[k] for k in (keys or W_FLOP))
+    """EXECUTED work only: the f-g iterations the exact early exits skipped (the reference and the oracle
+    walk through them) are not counted."""
+    c = dict(counters)
+    c["fg_iterations"] = counters["fg_iterations"] - counters.get("fg_iterations_skipped", 0)
+    return sum(W_FLOP[k] * c[k] for k in (keys or W_FLOP))
 
 
 def libm_calls(counters):

@@ -94,7 +94,7 @@ class IodResult(C.Structure):
 class IodCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "gauss_solves", "aberth_sweeps", "roots_accepted", "fg_iterations", "kepler_universal_solves",
-        "newton_steps", "sfunct_terms", "scorer_evals", "scorer_newton_steps", "candidates")]
+        "newton_steps", "sfunct_terms", "scorer_evals", "scorer_newton_steps", "candidates", "fg_iterations_skipped")]
 
 
 class IodPhaseMs(C.Structure):

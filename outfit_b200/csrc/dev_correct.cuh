@@ -58,6 +58,7 @@ __constant__ double c_rcp[20] = {
 
 struct WorkC {
   unsigned roots_accepted, fg_iterations, kepler_solves, newton_steps, sfunct_terms;
+  unsigned fg_skipped;  // iterations of the reference's loop that the exact early exits did not execute
 };
 
 // ---- s_funct, |beta| >= 100 (rare): halving + duplication, as stumpff.rs:200-297 ----------------
@@ -347,7 +348,7 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       // current state (gauss.rs:1310-1330).  Leaving now is exact -- and these are the candidates
       // whose every Kepler solve exhausts its 50 Newton steps: left to repeat, a single one of them
       // ran for 15 ms (clock64 probe, profiles/r01n_stragglers.log) and set the duration of the launch.
-      if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
+      if (COUNT) { w.fg_iterations += P.newton_max_it - 1 - it; w.fg_skipped += P.newton_max_it - 1 - it; }
       break;
     }
     // An iteration that ends in one of the `continue`s below commits only the chi warm starts.  If they
@@ -377,7 +378,7 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
     }
     if (stall) {
       if (same_chi) {
-        if (COUNT) w.fg_iterations += P.newton_max_it - 1 - it;
+        if (COUNT) { w.fg_iterations += P.newton_max_it - 1 - it; w.fg_skipped += P.newton_max_it - 1 - it; }
         break;
       }
       continue;

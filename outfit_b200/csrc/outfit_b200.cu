@@ -202,7 +202,7 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
   double *my = geo_sm + threadIdx.x;
   const unsigned long long cid = (unsigned long long)blockIdx.x * kCorrectThreads + threadIdx.x;
   WorkC w;
-  w.roots_accepted = 0; w.fg_iterations = 0; w.kepler_solves = 0; w.newton_steps = 0; w.sfunct_terms = 0;
+  w.roots_accepted = 0; w.fg_iterations = 0; w.kepler_solves = 0; w.newton_steps = 0; w.sfunct_terms = 0; w.fg_skipped = 0;
 #ifdef OUTFIT_DEBUG_STRAGGLERS
   const long long dbg_t0 = clock64();
 #endif
@@ -297,7 +297,7 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
     Work wk;
     memset(&wk, 0, sizeof wk);
     wk.roots_accepted = w.roots_accepted; wk.fg_iterations = w.fg_iterations; wk.kepler_solves = w.kepler_solves;
-    wk.newton_steps = w.newton_steps; wk.sfunct_terms = w.sfunct_terms;
+    wk.newton_steps = w.newton_steps; wk.sfunct_terms = w.sfunct_terms; wk.fg_skipped = w.fg_skipped;
     flush_work(wk, work_counters);
   }
 }
@@ -532,7 +532,7 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
     const double psi0 = psi;
     double s01[2] = {0.0, 0.0}, s2 = 0.0, s3 = 0.0;
     WorkC wc;
-    wc.roots_accepted = 0; wc.fg_iterations = 0; wc.kepler_solves = 0; wc.newton_steps = 0; wc.sfunct_terms = 0;
+    wc.roots_accepted = 0; wc.fg_iterations = 0; wc.kepler_solves = 0; wc.newton_steps = 0; wc.sfunct_terms = 0; wc.fg_skipped = 0;
     bool ok = false;
     if (st.kind == OUTFIT_SOLVER_NEWTON || st.kind == OUTFIT_SOLVER_AUTO)
       ok = kepuni_newton_fast<false>(dt, r0, sig0, alpha, st.convergency, psi, s2, s3, wc, s01);
@@ -1090,6 +1090,7 @@ extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *
   out->gauss_solves = h[1]; out->aberth_sweeps = h[2]; out->roots_accepted = h[3]; out->fg_iterations = h[4];
   out->kepler_universal_solves = h[5]; out->newton_steps = h[6]; out->sfunct_terms = h[7];
   out->scorer_evals = h[8]; out->scorer_newton_steps = h[9]; out->candidates = h[10];
+  out->fg_iterations_skipped = h[11];
   return OUTFIT_OK;
 }
 
