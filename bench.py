@@ -296,6 +296,20 @@ def main():
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     launches += per_step_launches * (e2e_steps + 1)
+    # the same entry point with the deviates generated on the device from per-trajectory seeds
+    # (OutfitObsBatch.traj_seed; parity with rand's stream unpinned): 8 B instead of 14.4 kB per trajectory
+    seeded = {k: v for k, v in host_batch.items() if k != "noise_z"}
+    seeded["noise_z"] = None
+    seeded["traj_seed"] = torch.from_numpy((np.arange(T, dtype=np.int64) * 2654435761 + 20261018 + rank)).pin_memory().numpy().view(np.uint64)
+    ctx.fit_full_iod(seeded, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_seeded = ctx.fit_full_iod(seeded, params)
+    torch.cuda.synchronize()
+    e2e_seeded_s = (time.perf_counter() - t0) / e2e_steps
+    launches += (per_step_launches + 8) * (e2e_steps + 1)
+    seeded_h2d = h2d_bytes - int(pinned["noise_z"].numel() * 8) + T * 8
     clocks = sampler.stop()
 
     # Kepler leg: 10 M propagate_universal (BASELINE configs[1]), device-resident
@@ -359,7 +373,7 @@ def main():
         del d_eo, d_es
 
     # max over ranks
-    tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms, e2e_seeded_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         if kep is not None:
@@ -369,7 +383,7 @@ def main():
             kep["propagate_universal_per_s"] = float(kr[0].item())
             if eph:
                 eph["entries_per_s"] = float(kr[1].item())
-    ms, e2e_ms, kernel_ms_max = (float(x) for x in tm.tolist())
+    ms, e2e_ms, kernel_ms_max, e2e_seeded_ms = (float(x) for x in tm.tolist())
 
     if rank == 0:
         flops = algorithmic_flops(counters)
@@ -394,7 +408,11 @@ def main():
             "config": config,
             "e2e": {"value": T * world / (e2e_ms * 1e-3), "unit": "trajectories/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
-                    "api": "outfit_b200_fit_full_iod (host buffers, pinned)"},
+                    "api": "outfit_b200_fit_full_iod (host buffers, pinned; noise deviates drawn on the host)",
+                    "seeded": {"value": T * world / (e2e_seeded_ms * 1e-3), "ms_per_step": e2e_seeded_ms,
+                               "h2d_bytes_per_step": seeded_h2d,
+                               "note": "same entry, deviates generated on the device from per-trajectory seeds (traj_seed)",
+                               "selected_ok_fraction": float((res_seeded["status"] == 0).mean())}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",

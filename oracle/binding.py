@@ -197,6 +197,16 @@ def _declare(L):
                                   C.c_int]
     L.oo_fit_full_iod.restype = None
     L.oo_counters_reset.restype = None
+    L.oo_draw_noise.argtypes = [C.c_uint64, C.c_size_t, C.c_void_p]
+    L.oo_draw_noise.restype = None
+    L.oo_splitmix64_next.argtypes = [C.POINTER(C.c_uint64)]
+    L.oo_splitmix64_next.restype = C.c_uint64
+    L.oo_xoshiro_next.argtypes = [C.c_uint64 * 4]
+    L.oo_xoshiro_next.restype = C.c_uint64
+    L.oo_xoshiro_seed_from_u64.argtypes = [C.c_uint64, C.c_uint64 * 4]
+    L.oo_xoshiro_seed_from_u64.restype = None
+    L.oo_ziggurat_tables.argtypes = [C.c_double * 257, C.c_double * 257]
+    L.oo_ziggurat_tables.restype = None
     L.oo_ephemeris_twobody_batch.argtypes = [C.POINTER(EphemTable), C.c_size_t, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, D3,
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -296,6 +306,14 @@ def ephemeris_twobody_batch(table, kind, epoch, elem, mjd_tt, mjd_ut1, body_fixe
                                      ptr(mjd_ut1), d3(body_fixed), ptr(out), ptr(status), n_threads,
                                      1 if dedup_observer else 0)
     return out, status
+
+
+def draw_noise(seeds, per_traj):
+    """Deviates of SmallRng::seed_from_u64(seed) + StandardNormal for every seed: (len(seeds), per_traj)."""
+    out = np.empty((len(seeds), per_traj), dtype=np.float64)
+    for t, sd in enumerate(seeds):
+        lib().oo_draw_noise(int(sd), per_traj, out[t].ctypes.data)
+    return out
 
 
 def counters():

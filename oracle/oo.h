@@ -286,6 +286,14 @@ void oo_fit_full_iod(size_t n_traj, const uint64_t *traj_offset, const double *m
                      const uint64_t *noise_offset, oo_iod_result *out, int n_threads,
                      int dedup_earth);
 
+/* ---- noise deviates (oo_rng.c; rand / rand_distr restated, parity unpinned) ------------------ */
+uint64_t oo_splitmix64_next(uint64_t *x);
+void oo_xoshiro_seed_from_u64(uint64_t seed, uint64_t s[4]);   /* SmallRng::seed_from_u64 */
+uint64_t oo_xoshiro_next(uint64_t s[4]);                        /* Xoshiro256++ */
+void oo_ziggurat_tables(double x[257], double f[257]);
+double oo_standard_normal(uint64_t s[4]);                       /* rand_distr::StandardNormal */
+void oo_draw_noise(uint64_t seed, size_t n, double *out);       /* n deviates in draw order */
+
 /* ---- two-body `Combined` ephemeris (ephemeris/mod.rs:189-292; oo_ephemeris.c) -------------- */
 /* apparent_position.rs:264-296 : observer position / velocity (= Earth velocity) / Earth position,
    equatorial mean J2000, AU and AU/day */

@@ -80,7 +80,8 @@ class ObsBatch(C.Structure):
                 ("mjd_tt", C.c_void_p), ("ra", C.c_void_p), ("dec", C.c_void_p),
                 ("sigma_ra", C.c_void_p), ("sigma_dec", C.c_void_p), ("obs_helio_equ", C.c_void_p),
                 ("obs_geo_ecl", C.c_void_p), ("observer_body_fixed", C.c_void_p),
-                ("mjd_ut1", C.c_void_p), ("noise_z", C.c_void_p), ("max_obs_per_traj", C.c_uint64)]
+                ("mjd_ut1", C.c_void_p), ("noise_z", C.c_void_p), ("max_obs_per_traj", C.c_uint64),
+                ("traj_seed", C.c_void_p)]
 
 
 class IodResult(C.Structure):
@@ -232,6 +233,7 @@ class OutfitB200:
             b.obs_helio_equ = _p(batch["helio_equ"])
             b.obs_geo_ecl = _p(batch["geo_ecl"])
         b.noise_z = _p(batch.get("noise_z"))
+        b.traj_seed = _p(batch.get("traj_seed"))
         b.max_obs_per_traj = int(batch.get("max_obs_per_traj", 0))
         return b
 

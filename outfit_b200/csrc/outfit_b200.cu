@@ -24,6 +24,7 @@
 #include "dev_correct.cuh"
 #include "dev_geometry.cuh"
 #include "dev_ephemeris.cuh"
+#include "dev_rng.cuh"
 
 using namespace ofb;
 
@@ -608,6 +609,7 @@ struct OutfitCtx {
   size_t arena_bytes = 0;
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   std::vector<cudaEvent_t> copy_ev;
+  double *d_zig = nullptr;  // ziggurat tables x[257], f[257] of the on-device StandardNormal (dev_rng.cuh)
   int n_streams = 8;  // passes in flight (outfit_b200_set_pass_streams; 1 = one pass on the caller's stream)
   cudaStream_t aux_stream[7] = {};  // extra compute streams (pass overlap)
   cudaEvent_t fork_ev = nullptr, join_ev[7] = {};
@@ -706,6 +708,25 @@ extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
     rcp[2 * j + 1] = 1.0 / ((d + 1.0) * (d + 2.0));
   }
   if (cudaMemcpyToSymbol(c_series_rcp, rcp, sizeof rcp) != cudaSuccess) { cudaFree(ctx->d_counters); delete ctx; return OUTFIT_E_CUDA; }
+  {
+    // ziggurat tables from the published recurrence (rand_distr's ziggurat_tables.py): x[0] = V / f(R),
+    // x[1] = R, x[i] = f^-1(V / x[i-1] + f(x[i-1])), x[256] = 0; f(x) = exp(-x^2 / 2)
+    double zig[2 * (kZigN + 1)];
+    double *xt = zig, *ft = zig + kZigN + 1;
+    xt[0] = kZigV / exp(-kZigR * kZigR / 2.0);
+    xt[1] = kZigR;
+    for (int i = 2; i < kZigN; ++i) {
+      const double last = xt[i - 1];
+      xt[i] = sqrt(-2.0 * log(kZigV / last + exp(-last * last / 2.0)));
+    }
+    xt[kZigN] = 0.0;
+    for (int i = 0; i <= kZigN; ++i) ft[i] = exp(-xt[i] * xt[i] / 2.0);
+    if (cudaMalloc(&ctx->d_zig, sizeof zig) != cudaSuccess || cudaMemcpy(ctx->d_zig, zig, sizeof zig, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(ctx->d_counters);
+      delete ctx;
+      return OUTFIT_E_ALLOC;
+    }
+  }
   if (const char *ev = getenv("OUTFIT_B200_STREAMS")) {
     const int v = atoi(ev);
     if (v >= 1 && v <= 8) ctx->n_streams = v;
@@ -726,6 +747,7 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_cheb) cudaFree(ctx->d_cheb);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_zig) cudaFree(ctx->d_zig);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->iod_scratch) cudaFree(ctx->iod_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
@@ -819,7 +841,9 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
   if (max_obs > kMaxObsPerTraj) return fail(ctx, OUTFIT_E_UNSUPPORTED, "trajectory longer than 448 observations");
   if (params->max_triplets > kMaxTriplets) return fail(ctx, OUTFIT_E_UNSUPPORTED, "max_triplets > 1024");
-  if (params->n_noise_realizations > 0 && !b->noise_z) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "noise_z is NULL but n_noise_realizations > 0");
+  if (params->n_noise_realizations > 0 && !b->noise_z && !b->traj_seed)
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "n_noise_realizations > 0 needs noise_z (host-drawn deviates) or traj_seed (on-device generator)");
+  const bool device_noise = params->n_noise_realizations > 0 && !b->noise_z;
   if (params->n_noise_realizations > 65535) return fail(ctx, OUTFIT_E_UNSUPPORTED, "n_noise_realizations > 65535");
   const size_t n = b->n_obs;
   const bool have_cache = b->obs_helio_equ && b->obs_geo_ecl;
@@ -862,7 +886,8 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   const unsigned long long cand_per_traj = (unsigned long long)P.max_triplets * M;
   // per-candidate scratch (bytes): code 4 + nroots 1 + roots 64 + state_kind 4 + state 56 + score 20
   const size_t per_cand = 4 + 1 + 64 + 4 + 56 + 4 + 4 + 8 + 4;
-  const size_t per_traj = (size_t)cand_per_traj * per_cand + (size_t)P.max_triplets * 4 + 4;
+  const size_t per_traj = (size_t)cand_per_traj * per_cand + (size_t)P.max_triplets * 4 + 4 +
+                          (device_noise ? (size_t)P.max_triplets * P.n_noise * 48 : 0);
   const size_t budget = (size_t)6 << 30;  // candidate scratch per chunk
   unsigned long long chunk = b->n_traj;
   if (per_traj * chunk > budget) chunk = budget / per_traj ? budget / per_traj : 1;
@@ -916,6 +941,13 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     S.trip = (unsigned *)take(tn * P.max_triplets * 4);
     S.ktraj = (unsigned *)take(tn * 4);
     S.nroots = (unsigned char *)take(S.n_cand);
+    if (device_noise) {
+      // this pass's deviates, generated on the device in draw order (dev_rng.cuh)
+      double *nz = (double *)take((size_t)tn * P.max_triplets * P.n_noise * 48);
+      noise_kernel<<<(unsigned)((tn + 127) / 128), 128, 0, stream>>>(tn, reinterpret_cast<const unsigned long long *>(b->traj_seed) + t0,
+                                                                   ctx->d_zig, P.max_triplets * P.n_noise, nz);
+      B.noise_z = nz;
+    }
     const unsigned tblocks = (unsigned)((tn + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
     triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
@@ -997,7 +1029,7 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
   if (!have_cache && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_helio_equ+obs_geo_ecl or observer_body_fixed+mjd_ut1");
   const size_t n_noise_doubles = hb->noise_z ? T * (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
   // one cached device arena for the inputs and the results (every sub-buffer 256-B aligned)
-  const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 +
+  const size_t bytes = (T + 1) * 8 + T * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 +
                        T * sizeof(OutfitIodResult) + 16 * 256;
   if (ctx->arena_bytes < bytes) {
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
@@ -1046,7 +1078,8 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->copy_ev.push_back(e);
   }
-  CK(cudaEventRecord(ctx->copy_ev[0], cs));  // observation arrays are in flight up to here
+  db.traj_seed = (!n_noise_doubles && hb->traj_seed) ? (const uint64_t *)put(hb->traj_seed, T * 8) : nullptr;
+  CK(cudaEventRecord(ctx->copy_ev[0], cs));  // observation arrays (and seeds) are in flight up to here
   double *d_noise = nullptr;
   if (n_noise_doubles) {
     d_noise = (double *)put(nullptr, n_noise_doubles * 8);

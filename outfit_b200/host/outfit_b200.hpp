@@ -73,6 +73,8 @@ class ObsBatchBuilder {
   }
   // noise_z: [n_traj][max_triplets][n_noise][6] standard normal deviates in draw order, or empty
   void set_noise(std::vector<double> z) { noise_ = std::move(z); }
+  // per-trajectory SmallRng seeds (base_seed ^ traj_id.stable_hash()): deviates generated on the device
+  void set_seeds(std::vector<uint64_t> seeds) { seeds_ = std::move(seeds); }
   size_t n_traj() const { return offsets_.size() - 1; }
   size_t n_obs() const { return rows_.size(); }
   // The returned struct points into this builder: keep it alive during the call.
@@ -92,6 +94,7 @@ class ObsBatchBuilder {
     b.mjd_tt = mjd_.data(); b.ra = ra_.data(); b.dec = dec_.data(); b.sigma_ra = sra_.data(); b.sigma_dec = sdec_.data();
     b.observer_body_fixed = bf_.data(); b.mjd_ut1 = ut1_.data();
     b.noise_z = noise_.empty() ? nullptr : noise_.data();
+    b.traj_seed = seeds_.empty() ? nullptr : seeds_.data();
     b.max_obs_per_traj = longest;
     return b;
   }
@@ -104,7 +107,7 @@ class ObsBatchBuilder {
     return x < y;
   }
   std::vector<Observation> rows_;
-  std::vector<uint64_t> offsets_{0};
+  std::vector<uint64_t> offsets_{0}, seeds_;
   std::vector<double> mjd_, ra_, dec_, sra_, sdec_, ut1_, bf_, noise_;
 };
 

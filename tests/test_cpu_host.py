@@ -51,7 +51,7 @@ def test_c_abi_exports_every_declared_symbol(lib):
     assert sorted(ABI_SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.outfit_b200_abi_version() == 1
+    assert lib.outfit_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_the_oracle_and_numpy_views(lib, oracle):
@@ -62,7 +62,7 @@ def test_struct_layouts_match_the_oracle_and_numpy_views(lib, oracle):
     assert C.sizeof(api.IodResult) == C.sizeof(oracle.IodResult) == api.RESULT_DTYPE.itemsize == 128
     for name, _ in api.IodResult._fields_:
         assert getattr(api.IodResult, name).offset == api.RESULT_DTYPE.fields[name][1]
-    assert C.sizeof(api.ObsBatch) == 14 * 8
+    assert C.sizeof(api.ObsBatch) == 15 * 8  # ABI v2: + traj_seed
 
 
 def test_iod_params_default_and_validation(lib, oracle):
