@@ -1,8 +1,6 @@
 // dev_correct.cuh -- the f-g correction phase (P2) as one register-resident loop per candidate.
 //
-// Reference behaviour restated here (same operations, same order, same bits as dev_gauss.cuh /
-// dev_kepler.cuh, which remain the readable statement of the algorithm and serve the bulk
-// propagator):
+// Reference behaviour restated here:
 //   accept_root / positions / Gibbs          gauss.rs:702-870
 //   pos_and_vel_correction                   gauss.rs:1284-1418
 //   velocity_correction_with_guess           kepler/velocity.rs:94-211
@@ -10,7 +8,7 @@
 //   s_funct                                  kepler/stumpff.rs:78-297
 //   eccentricity_control                     orb_elem.rs:257-301
 //
-// Why a second statement: ncu (profiles/r01d) showed the first version of this phase bound by
+// Why it looks like this: ncu (profiles/r01d) showed the first version of this phase bound by
 // fixed-latency dependency stalls (37 %) and local-memory round trips (12.7 % of the warp
 // instructions were LDL/STL: structs handed by reference to un-inlined functions), with FP64
 // instructions only 44 % of the instruction stream.  Here

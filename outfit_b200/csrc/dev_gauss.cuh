@@ -210,24 +210,6 @@ struct GaussGeom {
   double a0, a2, b0, b2;
 };
 
-// R*c with nalgebra's accumulation order, then rho, positions and light-time epoch (gauss.rs:702)
-__device__ __noinline__ bool positions_from_c(const Triplet &g, const GaussGeom &gm, double c0,
-                                                 double c1, double c2, double min_rho2, V3 (&pos)[3],
-                                                 double &epoch) {
-  const V3 gc = V3{(g.R[0].x * c0 + g.R[1].x * c1) + g.R[2].x * c2,
-                   (g.R[0].y * c0 + g.R[1].y * c1) + g.R[2].y * c2,
-                   (g.R[0].z * c0 + g.R[1].z * c1) + g.R[2].z * c2};
-  const double rho0 = -(dot(gm.SiR[0], gc) / c0);
-  const double rho1 = -(dot(gm.SiR[1], gc) / c1);
-  const double rho2 = -(dot(gm.SiR[2], gc) / c2);
-  if (rho1 < min_rho2) return false;
-  pos[0] = g.R[0] + rho0 * gm.S[0];
-  pos[1] = g.R[1] + rho1 * gm.S[1];
-  pos[2] = g.R[2] + rho2 * gm.S[2];
-  epoch = g.t[1] - rho1 / kVlightAu;
-  return true;
-}
-
 __device__ __forceinline__ V3 gibbs_velocity(const V3 (&pos)[3], double tau1, double tau3) {
   const double tau13 = tau3 - tau1;
   const double n1 = norm(pos[0]), n2 = norm(pos[1]), n3 = norm(pos[2]);
@@ -239,53 +221,6 @@ __device__ __forceinline__ V3 gibbs_velocity(const V3 (&pos)[3], double tau1, do
   return V3{kGaussK * ((pos[0].x * e1 + pos[1].x * d2) + pos[2].x * d3),
             kGaussK * ((pos[0].y * e1 + pos[1].y * d2) + pos[2].y * d3),
             kGaussK * ((pos[0].z * e1 + pos[1].z * d2) + pos[2].z * d3)};
-}
-
-// Iterative two-sided Lagrange f-g refinement (gauss.rs:1284-1418).  Returns false <=> None.
-// `ec0` = eccentricity_control of the incoming (pos[1], vel) (accept_root computed it with the same
-// limits); the control evaluated on a committed update is the one the next iteration's velocity
-// corrections would recompute, so it is carried instead.
-__device__ __noinline__ bool pos_and_vel_correction(const Triplet &g, const GaussGeom &gm,
-                                                    const IodDevParams &P, V3 (&pos)[3], V3 &vel,
-                                                    const EccCtl &ec0, double &epoch, Work &w) {
-  const double dt01 = g.t[0] - g.t[1], dt21 = g.t[2] - g.t[1];
-  double ep = 0.0;
-  if (fabs(dt01) <= kEps || fabs(dt21) <= kEps) return false;
-  bool has_chi = false;
-  double chi01 = 0.0, chi21 = 0.0;
-  MidState mid = mid_state(pos[1], vel, ec0);
-  for (unsigned it = 0; it < P.newton_max_it; ++it) {
-    ++w.fg_iterations;
-    const VelCor L = velocity_correction_side(pos[0], pos[1], mid, dt01, has_chi, chi01, P.kepler_eps, w);
-    const VelCor Rr = velocity_correction_side(pos[2], pos[1], mid, dt21, has_chi, chi21, P.kepler_eps, w);
-    if (!(L.ok && Rr.ok)) {
-      // nothing was updated: every remaining iteration would repeat this one exactly
-      if (!has_chi) { w.fg_iterations += P.newton_max_it - 1 - it; break; }
-      continue;
-    }
-    has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
-    if (!isfinite(L.g) || !isfinite(Rr.g)) continue;
-    const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
-    const double fl = L.f * Rr.g - Rr.f * L.g;
-    if (!isfinite(fl) || fabs(fl) < kEps) continue;
-    const double inv_f = 1.0 / fl;
-    V3 np[3];
-    double nep;
-    if (!positions_from_c(g, gm, Rr.g * inv_f, -1.0, -L.g * inv_f, P.min_rho2_au, np, nep)) continue;
-    const EccCtl ec = eccentricity_control(np[1], nv, P.max_perihelion_au, P.max_ecc);
-    if (!ec.defined || !ec.accepted) return false;
-    const double denom = sqrt((dot(np[0], np[0]) + dot(np[1], np[1])) + dot(np[2], np[2]));
-    if (!isfinite(denom) || denom <= kEps) continue;
-    const V3 d0 = np[0] - pos[0], d1 = np[1] - pos[1], d2 = np[2] - pos[2];
-    const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
-    pos[0] = np[0]; pos[1] = np[1]; pos[2] = np[2];
-    vel = nv;
-    ep = nep;
-    mid = mid_state(pos[1], vel, ec);
-    if (rel <= P.newton_eps) break;
-  }
-  epoch = ep;
-  return true;
 }
 
 }  // namespace ofb

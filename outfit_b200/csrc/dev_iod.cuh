@@ -207,23 +207,4 @@ __device__ __forceinline__ bool gauss_polynomial(const Triplet &g, const GaussGe
   return count != 0;
 }
 
-// One admissible root -> accept_root (gauss.rs:816-870) -> f-g correction (gauss.rs:1284).
-// returns 0 rejected, 1 PrelimOrbit state, 2 CorrectedOrbit state; state = r(t2), v(t2), epoch
-__device__ __forceinline__ int solve_root(const Triplet &g, const GaussGeom &gm, const IodDevParams &P, double r2,
-                                          V3 &r_out, V3 &v_out, double &epoch_out, Work &w) {
-  const double r2m3 = 1.0 / ((r2 * r2) * r2);
-  V3 pos[3];
-  double epoch;
-  if (!positions_from_c(g, gm, gm.a0 + gm.b0 * r2m3, -1.0, gm.a2 + gm.b2 * r2m3, P.min_rho2_au, pos, epoch)) return 0;
-  V3 vel = gibbs_velocity(pos, gm.tau1, gm.tau3);
-  const EccCtl ec = eccentricity_control(pos[1], vel, P.max_perihelion_au, P.max_ecc);
-  if (!ec.defined || !ec.accepted) return 0;
-  ++w.roots_accepted;
-  r_out = pos[1]; v_out = vel; epoch_out = epoch;
-  double cepoch;
-  if (!pos_and_vel_correction(g, gm, P, pos, vel, ec, cepoch, w)) return 1;
-  r_out = pos[1]; v_out = vel; epoch_out = cepoch;
-  return 2;
-}
-
 }  // namespace ofb
