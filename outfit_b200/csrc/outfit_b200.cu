@@ -888,7 +888,8 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   const size_t per_cand = 4 + 1 + 64 + 4 + 56 + 4 + 4 + 8 + 4;
   const size_t per_traj = (size_t)cand_per_traj * per_cand + (size_t)P.max_triplets * 4 + 4 +
                           (device_noise ? (size_t)P.max_triplets * P.n_noise * 48 : 0);
-  const size_t budget = (size_t)6 << 30;  // candidate scratch per chunk
+  // candidate scratch per pass: 6 GB for a single stream, 2 GB per stream (16 GB in total) with 8 in flight
+  const size_t budget = n_streams > 1 ? (size_t)2 << 30 : (size_t)6 << 30;
   unsigned long long chunk = b->n_traj;
   if (per_traj * chunk > budget) chunk = budget / per_traj ? budget / per_traj : 1;
   if (max_chunk && chunk > max_chunk) chunk = max_chunk;

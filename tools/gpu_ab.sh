@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-python bench.py --steps 3 --warmup 3 > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/r02i_bench.err
-python -c "
-import json;d=json.load(open('gpurun_out/r02i_bench.json'));print(d['value'],d['e2e']['value'],d['e2e']['ms_per_step']);print(d['e2e']['seeded'])"
+for v in "" outfit_b200/variants/lib_bps3.so outfit_b200/variants/lib_bps5.so outfit_b200/variants/lib_bps6.so; do OUTFIT_B200_LIB=$v OUTFIT_B200_STREAMS=1 PERF_PARITY=0 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB="; done | tee gpurun_out/r02k_ab.log
