@@ -55,6 +55,16 @@ KERNEL_EVENTS = {
 KERNEL_PHASE = {"roots_kernel": "roots_ms", "correct_kernel": "correct_ms", "score_kernel": "score_ms"}
 
 
+# One `ncu` capture of a single-pass launch of THIS workload (100 k trajectories x 12 observations),
+# profiles/r02l_ncu_metrics_100k.csv: DRAM bytes per launch (read + write), FP64 pipe utilisation, issue
+# slot utilisation, active threads per warp instruction.  Static evidence, not re-measured by bench.py.
+NCU_R02L = {
+    "roots_kernel": {"dram_bytes": 1556186880 + 1034213632, "fp64_pipe_pct": 69.74, "issue_pct": 54.48, "threads_per_inst": 31.10},
+    "correct_kernel": {"dram_bytes": 2048618496 + 1953743360, "fp64_pipe_pct": 56.07, "issue_pct": 52.01, "threads_per_inst": 24.79},
+    "score_kernel": {"dram_bytes": 2201879808 + 675036160, "fp64_pipe_pct": 55.32, "issue_pct": 77.24, "threads_per_inst": 29.59},
+}
+
+
 def algorithmic_flops(counters, keys=None):
     """EXECUTED work only: the f-g iterations the exact early exits skipped (the reference and the oracle
     walk through them) are not counted."""
@@ -394,6 +404,8 @@ def main():
             kfl = algorithmic_flops(counters, ev)
             kernels[kname] = {"ms": kms, "share_of_step": kms / kernel_ms, "algorithmic_flop": kfl,
                               "tflops": kfl / (kms * 1e-3) / 1e12, "frac_fp64_peak": kfl / (kms * 1e-3) / fp64_peak}
+            if args.workload == "c3_100k_x12":
+                kernels[kname]["ncu_r02l"] = NCU_R02L[kname]
         for kname, key in (("scorer_observer_kernel", "observer_ms"), ("triplets_kernel", "triplets_ms"),
                            ("select_kernel", "select_ms")):
             kernels[kname] = {"ms": phases[key], "share_of_step": phases[key] / kernel_ms}
@@ -416,7 +428,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": kernels[dom]["frac_fp64_peak"], "traffic": None, "kernel": dom,
+                         "frac": kernels[dom]["frac_fp64_peak"],
+                         "traffic": NCU_R02L[dom]["dram_bytes"] if args.workload == "c3_100k_x12" else None, "kernel": dom,
                          "kernel_ms": kernels[dom]["ms"], "algorithmic_flop_per_launch": kernels[dom]["algorithmic_flop"],
                          "step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / fp64_peak, "ms": ms,
                                   "single_pass_ms": kernel_ms, "single_pass_frac": achieved / fp64_peak,
