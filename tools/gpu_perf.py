@@ -31,6 +31,8 @@ try:
 except Exception as e:
     print("   phases: n/a (two-stream passes)")
 print(f"LIB={os.environ.get('OUTFIT_B200_LIB','default')} T={T} {ms:.1f} ms  {T/ms*1e3:.0f} traj/s  ok={np.mean(res['status']==0):.4f}")
+if os.environ.get("PERF_COUNT", "0") == "1":
+    print("   counters:", ctx.last_iod_counters())
 if os.environ.get("PERF_E2E", "0") == "1":
     pinned = {k: torch.from_numpy(batch[k].view(np.int64) if batch[k].dtype == np.uint64 else batch[k]).pin_memory() for k in keys}
     hb = {k: (pinned[k].numpy().view(np.uint64) if k == "traj_offset" else pinned[k].numpy()) for k in keys}
