@@ -359,3 +359,13 @@ def test_parity_more_triplets_than_a_warp(env):
     """max_triplets = 40 > 32 lanes, n_noise = 0: the best-K container beyond one warp-wide chunk."""
     _, got, want, ef, rf = run_both(env, 300, 14, seed=132, K=40, nn=0)
     assert_iod_parity(got, want, ef, rf)
+
+
+def test_parity_at_scale_20k(env):
+    """20 000 trajectories x 12 observations with the example parameters (6.6 M candidates): every
+    integer / index field equal to the oracle's, floats within the rule of parity_util.  Guards the
+    exact early exits of the f-g loop and of the Aberth start radius at a scale where their rare
+    branches (a few per 10^5 candidates) are all exercised."""
+    _, got, want, ef, rf = run_both(env, 20000, 12, seed=161, K=30, nn=10)
+    st = assert_iod_parity(got, want, ef, rf, min_plain_fraction=0.90, max_outlier_fraction=1e-3)
+    assert st["n_ok"] > 19000
