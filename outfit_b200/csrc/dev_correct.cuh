@@ -31,8 +31,10 @@ constexpr int kCorrectThreads = 128;
 // shared-memory slots per thread (doubles)
 enum {
   SL_R0 = 0, SL_R1 = 3, SL_R2 = 6, SL_S0 = 9, SL_S1 = 12, SL_S2 = 15, SL_I0 = 18, SL_I1 = 21, SL_I2 = 24,
-  SL_TAU1 = 27, SL_TAU3 = 28, SL_A0 = 29, SL_A2 = 30, SL_B0 = 31, SL_B2 = 32, SL_T0 = 33, SL_T1 = 34, SL_T2 = 35,
-  SL_COUNT = 36
+  SL_T0 = 27, SL_T1 = 28, SL_T2 = 29,
+  // loop state that is idle during the Kepler solves: the outer positions, the first side's result
+  SL_P0 = 30, SL_P2 = 33, SL_LF = 36, SL_LG = 37, SL_LCHI = 38, SL_LV = 39,
+  SL_COUNT = 42
 };
 constexpr size_t kCorrectSmemBytes = (size_t)SL_COUNT * kCorrectThreads * sizeof(double);
 
@@ -245,14 +247,25 @@ __device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double
   return m;
 }
 
+// shared-memory view of this thread's loop-invariant geometry
+// (volatile: keeps the compiler from hoisting these loop-invariant loads into registers, which is
+// exactly the register pressure -- and the spills -- the staging exists to avoid)
+struct GeoSm {
+  volatile double *p;  // &smem[threadIdx.x]
+  __device__ __forceinline__ double at(int slot) const { return p[slot * kCorrectThreads]; }
+  __device__ __forceinline__ V3 v3(int slot) const { return V3{at(slot), at(slot + 1), at(slot + 2)}; }
+  __device__ __forceinline__ void put(int slot, double v) const { p[slot * kCorrectThreads] = v; }
+  __device__ __forceinline__ void put3(int slot, V3 v) const { put(slot, v.x); put(slot + 1, v.y); put(slot + 2, v.z); }
+};
+
 struct SideC {
   bool ok;
   V3 v;
   double f, g, chi;
 };
 template <bool COUNT>
-__device__ __forceinline__ SideC correction_side(V3 x1, V3 x2, const MidC &m, double dt, bool has_guess, double chi_guess,
-                                                 double eps, WorkC &w) {
+__device__ __forceinline__ SideC correction_side(const GeoSm &G, int x1_slot, V3 x2, const MidC &m, double dt, bool has_guess,
+                                                 double chi_guess, double eps, WorkC &w) {
   SideC o;
   o.ok = false;
   if (COUNT) ++w.kepler_solves;
@@ -263,6 +276,7 @@ __device__ __forceinline__ SideC correction_side(V3 x1, V3 x2, const MidC &m, do
   const double g = dt - div_mk(s3, kGaussK, c_rcp[RC_GAUSSK]);
   const double ga = fabs(g);
   if (!isfinite(ga) || ga < 100.0 * kEps * (1.0 + fabs(dt))) return o;
+  const V3 x1 = G.v3(x1_slot);
   const double nx = (-f) * x2.x + x1.x, ny = (-f) * x2.y + x1.y, nz = (-f) * x2.z + x1.z;
   if (mk_ok(g)) {
     const double yg = 1.0 / g;
@@ -274,15 +288,6 @@ __device__ __forceinline__ SideC correction_side(V3 x1, V3 x2, const MidC &m, do
   o.ok = true;
   return o;
 }
-
-// shared-memory view of this thread's loop-invariant geometry
-// (volatile: keeps the compiler from hoisting these loop-invariant loads into registers, which is
-// exactly the register pressure -- and the spills -- the staging exists to avoid)
-struct GeoSm {
-  const volatile double *p;  // &smem[threadIdx.x]
-  __device__ __forceinline__ double at(int slot) const { return p[slot * kCorrectThreads]; }
-  __device__ __forceinline__ V3 v3(int slot) const { return V3{at(slot), at(slot + 1), at(slot + 2)}; }
-};
 
 // positions_from_c with c1 = -1 (gauss.rs:702): -(x / -1) == x exactly, so rho1 = S^-1 row 1 . gc
 __device__ __forceinline__ bool positions_c(const GeoSm &G, double c0, double c2, double min_rho2, V3 &p0, V3 &p1,
@@ -302,27 +307,41 @@ __device__ __forceinline__ bool positions_c(const GeoSm &G, double c0, double c2
 }
 
 // accept_root (gauss.rs:816-870): positions, light-time epoch, Gibbs velocity, acceptability.
+// tau / a / b of gauss_prelim (gauss.rs:464-500) are rebuilt from the three epochs (a handful of
+// operations per root) instead of occupying six shared-memory slots.  On success the outer positions
+// are parked in shared memory (SL_P0, SL_P2); the caller keeps p1, vel, mid in registers.
 template <bool COUNT>
-__device__ __forceinline__ bool accept_root_fast(const GeoSm &G, const IodDevParams &P, double root, V3 &p0, V3 &p1,
-                                                 V3 &p2, V3 &vel, double &epoch, MidC &mid, WorkC &w) {
+__device__ __forceinline__ bool accept_root_fast(const GeoSm &G, const IodDevParams &P, double root, V3 &p1, V3 &vel,
+                                                 double &epoch, MidC &mid, WorkC &w) {
+  const double t0 = G.at(SL_T0), t1 = G.at(SL_T1), t2 = G.at(SL_T2);
+  const double tau1 = kGaussK * (t0 - t1), tau3 = kGaussK * (t2 - t1);
+  const double tau13 = tau3 - tau1;
+  const double a0 = tau3 / tau13, a2 = -(tau1 / tau13);
+  const double b0 = a0 * (tau13 * tau13 - tau3 * tau3) / 6.0;
+  const double b2 = a2 * (tau13 * tau13 - tau1 * tau1) / 6.0;
   const double r2m3 = 1.0 / ((root * root) * root);
-  if (!positions_c(G, G.at(SL_A0) + G.at(SL_B0) * r2m3, G.at(SL_A2) + G.at(SL_B2) * r2m3, P.min_rho2_au, p0, p1, p2, epoch))
-    return false;
+  V3 p0, p2;
+  if (!positions_c(G, a0 + b0 * r2m3, a2 + b2 * r2m3, P.min_rho2_au, p0, p1, p2, epoch)) return false;
   {
     const V3 pos[3] = {p0, p1, p2};
-    vel = gibbs_velocity(pos, G.at(SL_TAU1), G.at(SL_TAU3));
+    vel = gibbs_velocity(pos, tau1, tau3);
   }
   mid = middle_state(p1, vel, P.max_perihelion_au, P.max_ecc);
   if (!mid.defined || !mid.accepted) return false;
   if (COUNT) ++w.roots_accepted;
+  G.put3(SL_P0, p0);
+  G.put3(SL_P2, p2);
   return true;
 }
 
 // pos_and_vel_correction (gauss.rs:1284-1418) on an accepted root.  false <=> None (the caller keeps
 // the accepted state as a PrelimOrbit); true: (p1, vel, ep) hold the corrected state.
+// Register diet: the outer positions and the first side's result are idle while a Kepler solve runs,
+// so they live in shared memory; what stays in registers across the solves is p1, vel, the middle
+// state and the two chi warm starts.
 template <bool COUNT>
-__device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevParams &P, V3 &p0, V3 &p1, V3 &p2,
-                                                   V3 &vel, MidC &mid, double &ep, WorkC &w) {
+__device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevParams &P, V3 &p1, V3 &vel, MidC &mid,
+                                                   double &ep, WorkC &w) {
   const double dt01 = G.at(SL_T0) - G.at(SL_T1), dt21 = G.at(SL_T2) - G.at(SL_T1);
   if (fabs(dt01) <= kEps || fabs(dt21) <= kEps) return false;
   ep = 0.0;
@@ -333,13 +352,17 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
     if (COUNT) ++w.fg_iterations;
     // velocity_correction_with_guess guards (velocity.rs:105-123), identical for both sides
     const bool sides_ok = isfinite(mid.hn) && !(mid.hn <= 1e6 * kEps) && mid.defined;
-    SideC L, Rr;
-    L.ok = false; Rr.ok = false;
+    bool both = false;
+    SideC Rr;
+    Rr.ok = false;
     if (sides_ok) {
-      L = correction_side<COUNT>(p0, p1, mid, dt01, has_chi, chi01, P.kepler_eps, w);
-      Rr = correction_side<COUNT>(p2, p1, mid, dt21, has_chi, chi21, P.kepler_eps, w);
+      const SideC L = correction_side<COUNT>(G, SL_P0, p1, mid, G.at(SL_T0) - G.at(SL_T1), has_chi, chi01, P.kepler_eps, w);
+      if (L.ok) { G.put(SL_LF, L.f); G.put(SL_LG, L.g); G.put(SL_LCHI, L.chi); G.put3(SL_LV, L.v); }
+      const bool l_ok = L.ok;
+      Rr = correction_side<COUNT>(G, SL_P2, p1, mid, G.at(SL_T2) - G.at(SL_T1), has_chi, chi21, P.kepler_eps, w);
+      both = l_ok && Rr.ok;
     }
-    if (!(L.ok && Rr.ok)) {
+    if (!both) {
       // The reference `continue`s here with NOTHING updated (positions, velocity and the chi warm
       // starts are only committed after both sides succeed), so every remaining iteration would
       // repeat this one bit for bit and the loop would end after newton_max_it passes with the
@@ -349,22 +372,24 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       if (COUNT) { w.fg_iterations += P.newton_max_it - 1 - it; w.fg_skipped += P.newton_max_it - 1 - it; }
       break;
     }
+    const double Lf = G.at(SL_LF), Lg = G.at(SL_LG), Lchi = G.at(SL_LCHI);
     // An iteration that ends in one of the `continue`s below commits only the chi warm starts.  If they
     // come out bit-identical to the ones it started from, the next iteration has exactly the same
     // inputs (positions, velocity, middle state, chi) and therefore the same outcome, and so on until
     // newton_max_it: leaving now is exact.  This is the fate of ~45 % of the accepted roots (the new
     // geocentric distance falls below min_rho2_au on the first or second pass and the warm-started
     // Kepler solves return their guess), which the reference walks through all 50 iterations.
-    const bool same_chi = has_chi && L.chi == chi01 && Rr.chi == chi21;
-    has_chi = true; chi01 = L.chi; chi21 = Rr.chi;
-    const V3 nv = V3{(L.v.x + Rr.v.x) * 0.5, (L.v.y + Rr.v.y) * 0.5, (L.v.z + Rr.v.z) * 0.5};
-    const double fl = L.f * Rr.g - Rr.f * L.g;
+    const bool same_chi = has_chi && Lchi == chi01 && Rr.chi == chi21;
+    has_chi = true; chi01 = Lchi; chi21 = Rr.chi;
+    const V3 Lv = G.v3(SL_LV);
+    const V3 nv = V3{(Lv.x + Rr.v.x) * 0.5, (Lv.y + Rr.v.y) * 0.5, (Lv.z + Rr.v.z) * 0.5};
+    const double fl = Lf * Rr.g - Rr.f * Lg;
     bool stall = !isfinite(fl) || fabs(fl) < kEps;
     V3 n0, n1, n2;
     double nep = 0.0;
     if (!stall) {
       const double inv_f = 1.0 / fl;
-      stall = !positions_c(G, Rr.g * inv_f, -L.g * inv_f, P.min_rho2_au, n0, n1, n2, nep);
+      stall = !positions_c(G, Rr.g * inv_f, -Lg * inv_f, P.min_rho2_au, n0, n1, n2, nep);
     }
     MidC nm;
     double denom = 0.0;
@@ -381,9 +406,11 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       }
       continue;
     }
-    const V3 d0 = n0 - p0, d1 = n1 - p1, d2 = n2 - p2;
+    const V3 d0 = n0 - G.v3(SL_P0), d1 = n1 - p1, d2 = n2 - G.v3(SL_P2);
     const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
-    p0 = n0; p1 = n1; p2 = n2;
+    G.put3(SL_P0, n0);
+    G.put3(SL_P2, n2);
+    p1 = n1;
     vel = nv;
     ep = nep;
     mid = nm;

@@ -239,16 +239,6 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
       const GeoSm G{my};
       {
         // gauss_prelim (gauss.rs:464-549): tau, a, b, cofactor inverse (rows of S^-1)
-        const double t0 = G.at(SL_T0), t1 = G.at(SL_T1), t2 = G.at(SL_T2);
-        const double tau1 = kGaussK * (t0 - t1), tau3 = kGaussK * (t2 - t1);
-        const double tau13 = tau3 - tau1;
-        const double a0 = tau3 / tau13, a2 = -(tau1 / tau13);
-        my[SL_TAU1 * kCorrectThreads] = tau1;
-        my[SL_TAU3 * kCorrectThreads] = tau3;
-        my[SL_A0 * kCorrectThreads] = a0;
-        my[SL_A2 * kCorrectThreads] = a2;
-        my[SL_B0 * kCorrectThreads] = a0 * (tau13 * tau13 - tau3 * tau3) / 6.0;
-        my[SL_B2 * kCorrectThreads] = a2 * (tau13 * tau13 - tau1 * tau1) / 6.0;
         const V3 S0 = G.v3(SL_S0), S1 = G.v3(SL_S1), S2 = G.v3(SL_S2);
         const double m11 = S0.x, m12 = S1.x, m13 = S2.x, m21 = S0.y, m22 = S1.y, m23 = S2.y, m31 = S0.z, m32 = S1.z, m33 = S2.z;
         const double mi1 = m22 * m33 - m32 * m23, mi2 = m21 * m33 - m31 * m23, mi3 = m21 * m32 - m31 * m22;
@@ -263,10 +253,10 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
       unsigned n_solutions = 0;
 #pragma unroll 1
       for (unsigned k = 0; k < n; ++k) {
-        V3 p0, p1, p2, vel;
+        V3 p1, vel;
         double ep;
         MidC mid;
-        if (!accept_root_fast<COUNT>(G, P, S.roots[(size_t)k * S.n_cand + cid], p0, p1, p2, vel, ep, mid, w)) continue;
+        if (!accept_root_fast<COUNT>(G, P, S.roots[(size_t)k * S.n_cand + cid], p1, vel, ep, mid, w)) continue;
         ++n_solutions;
         // prelim_orbit (gauss.rs:1238-1247): first CorrectedOrbit in discovery order, else first pushed
         const bool first = kind == 0;
@@ -276,7 +266,7 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
           S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
           S.state[6 * S.n_cand + cid] = ep;
         }
-        if (fg_correction_fast<COUNT>(G, P, p0, p1, p2, vel, mid, ep, w)) {
+        if (fg_correction_fast<COUNT>(G, P, p1, vel, mid, ep, w)) {
           kind = 2;
           S.state[0 * S.n_cand + cid] = p1.x; S.state[1 * S.n_cand + cid] = p1.y; S.state[2 * S.n_cand + cid] = p1.z;
           S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
