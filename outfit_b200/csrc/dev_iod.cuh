@@ -147,6 +147,95 @@ __device__ __noinline__ unsigned select_triplets(const TrajSmem &sm, unsigned n_
   return heap_len;
 }
 
+// ---- the same selection, one THREAD per trajectory ---------------------------------------------------
+// The std::BinaryHeap replica is inherently serial; run by lane 0 of a warp it issues ~30 k warp
+// instructions per trajectory with one lane active (ncu r02l: 5.3 of 32 threads per instruction, issue
+// slots 74 % busy).  With a thread per trajectory the same instructions serve 32 trajectories at once.
+// The heap is a column of a [slot][thread] shared array (bank = thread, whatever the slot), the epochs
+// are read through the read-only cache.  Identical operations on identical values: identical output.
+struct HeapCol {
+  double *w;     // &heap_w[threadIdx.x], stride = threads per block
+  unsigned *x;   // &heap_x[threadIdx.x]
+  unsigned stride;
+  __device__ __forceinline__ double &W(unsigned i) const { return w[i * stride]; }
+  __device__ __forceinline__ unsigned &X(unsigned i) const { return x[i * stride]; }
+};
+__device__ __forceinline__ void heapc_sift_up(const HeapCol &h, unsigned pos) {
+  const double w = h.W(pos);
+  const unsigned x = h.X(pos);
+  while (pos > 0) {
+    const unsigned parent = (pos - 1) >> 1;
+    if (heap_le(w, h.W(parent))) break;
+    h.W(pos) = h.W(parent); h.X(pos) = h.X(parent);
+    pos = parent;
+  }
+  h.W(pos) = w; h.X(pos) = x;
+}
+__device__ __forceinline__ void heapc_sift_down_to_bottom(const HeapCol &h, unsigned end) {
+  const double w = h.W(0);
+  const unsigned x = h.X(0);
+  unsigned pos = 0, child = 1;
+  while (end >= 2 && child <= end - 2) {
+    if (heap_le(h.W(child), h.W(child + 1))) child += 1;
+    h.W(pos) = h.W(child); h.X(pos) = h.X(child);
+    pos = child;
+    child = 2 * pos + 1;
+  }
+  if (end >= 1 && child == end - 1) {
+    h.W(pos) = h.W(child); h.X(pos) = h.X(child);
+    pos = child;
+  }
+  h.W(pos) = w; h.X(pos) = x;
+  heapc_sift_up(h, pos);
+}
+// returns the number found; leaves them, ascending, in the heap column
+__device__ __forceinline__ unsigned select_triplets_thread(const HeapCol &h, const double *__restrict__ T, unsigned n_obs,
+                                                           const IodDevParams &P) {
+  if (P.max_triplets == 0 || n_obs < 3) return 0;
+  const unsigned nr = P.max_obs_for_triplets >= n_obs ? n_obs : (P.max_obs_for_triplets <= 3 ? 3u : P.max_obs_for_triplets);
+  const unsigned K = P.max_triplets;
+  unsigned heap_len = 0;
+  for (unsigned i = 0; i + 2 < nr; ++i) {
+    const double ti = __ldg(T + keep_index(i, n_obs, P.max_obs_for_triplets));
+    for (unsigned j = i + 1; j + 1 < nr; ++j) {
+      const double tj = __ldg(T + keep_index(j, n_obs, P.max_obs_for_triplets));
+      const double gap1 = s_gap(tj - ti, P.inv_optimal_interval);
+      for (unsigned k = j + 1; k < nr; ++k) {
+        const double tk = __ldg(T + keep_index(k, n_obs, P.max_obs_for_triplets));
+        const double span = tk - ti;
+        if (!(span >= P.dt_min && span <= P.dt_max_triplet)) continue;
+        const double wgt = gap1 + s_gap(tk - tj, P.inv_optimal_interval);
+        if (!isfinite(wgt)) continue;
+        const unsigned packed = (i << 20) | (j << 10) | k;
+        if (heap_len < K) {
+          h.W(heap_len) = wgt; h.X(heap_len) = packed;
+          heapc_sift_up(h, heap_len);
+          ++heap_len;
+        } else if (wgt < h.W(0)) {
+          // BinaryHeap::pop then push
+          --heap_len;
+          if (heap_len > 0) {
+            h.W(0) = h.W(heap_len); h.X(0) = h.X(heap_len);
+            heapc_sift_down_to_bottom(h, heap_len);
+          }
+          h.W(heap_len) = wgt; h.X(heap_len) = packed;
+          heapc_sift_up(h, heap_len);
+          ++heap_len;
+        }
+      }
+    }
+  }
+  // heap.into_vec() then insertion sort by weight (stable)
+  for (unsigned a = 1; a < heap_len; ++a) {
+    const double w = h.W(a);
+    const unsigned x = h.X(a);
+    unsigned b = a;
+    while (b > 0 && w < h.W(b - 1)) { h.W(b) = h.W(b - 1); h.X(b) = h.X(b - 1); --b; }
+    h.W(b) = w; h.X(b) = x;
+  }
+  return heap_len;
+}
+
 // ---- candidate geometry: gauss_prelim + unit matrix + cofactor inverse (gauss.rs:464-549) -------
 // false <=> SingularDirectionMatrix
 __device__ __noinline__ bool gauss_geometry(const Triplet &g, GaussGeom &gm) {

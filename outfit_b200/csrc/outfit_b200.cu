@@ -105,6 +105,23 @@ triplets_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned n_obs_cap)
   if (lane == 0) S.ktraj[tr] = K;
 }
 
+// P0, one thread per trajectory (dev_iod.cuh: select_triplets_thread); dynamic shared memory =
+// blockDim.x * max_triplets * 12 bytes
+__global__ void __launch_bounds__(128)
+triplets_thread_kernel(IodBatchDev B, IodDevParams P, IodScratch S) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *hw = reinterpret_cast<double *>(smem_raw);
+  unsigned *hx = reinterpret_cast<unsigned *>(hw + (size_t)P.max_triplets * blockDim.x);
+  const unsigned long long tr = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tr >= B.n_traj) return;
+  const unsigned long long o0 = B.traj_offset[tr];
+  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+  const HeapCol h{hw + threadIdx.x, hx + threadIdx.x, blockDim.x};
+  const unsigned K = select_triplets_thread(h, B.mjd_tt + o0, n_obs, P);
+  for (unsigned a = 0; a < K; ++a) S.trip[tr * P.max_triplets + a] = h.X(a);
+  S.ktraj[tr] = K;
+}
+
 // candidate id -> (trajectory, triplet rank, realization); false when the slot is unused
 __device__ __forceinline__ bool decode_candidate(unsigned long long cid, const IodDevParams &P, const IodScratch &S,
                                                  unsigned long long &tr, unsigned &r, unsigned &m) {
@@ -600,6 +617,7 @@ struct OutfitCtx {
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   std::vector<cudaEvent_t> copy_ev;
   double *d_zig = nullptr;  // ziggurat tables x[257], f[257] of the on-device StandardNormal (dev_rng.cuh)
+  bool triplets_per_thread = true;  // OUTFIT_B200_TRIPLETS_WARP=1: the warp-per-trajectory selection kernel
   int n_streams = 8;  // passes in flight (outfit_b200_set_pass_streams; 1 = one pass on the caller's stream)
   cudaStream_t aux_stream[7] = {};  // extra compute streams (pass overlap)
   cudaEvent_t fork_ev = nullptr, join_ev[7] = {};
@@ -717,6 +735,7 @@ extern "C" int outfit_b200_init(int device, OutfitCtx **out) {
       return OUTFIT_E_ALLOC;
     }
   }
+  if (const char *ev = getenv("OUTFIT_B200_TRIPLETS_WARP")) ctx->triplets_per_thread = atoi(ev) == 0;
   if (const char *ev = getenv("OUTFIT_B200_STREAMS")) {
     const int v = atoi(ev);
     if (v >= 1 && v <= 8) ctx->n_streams = v;
@@ -941,7 +960,15 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     }
     const unsigned tblocks = (unsigned)((tn + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
-    triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+    // thread per trajectory while a 128-thread block's heap columns fit in shared memory (K <= ~1300),
+    // else the warp-per-trajectory kernel
+    if ((size_t)P.max_triplets * 12 * 128 <= 160 * 1024 && ctx->triplets_per_thread) {
+      const size_t tsm = (size_t)P.max_triplets * 12 * 128;
+      if (tsm > 48 * 1024) CK(cudaFuncSetAttribute(triplets_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      triplets_thread_kernel<<<(unsigned)((tn + 127) / 128), 128, tsm, stream>>>(B, P, S);
+    } else {
+      triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+    }
     mark();
     roots_kernel<<<cblocks, kCandThreads, 32 * kCandThreads * sizeof(double), stream>>>(B, P, S, ctx->d_counters + 1);
     mark();

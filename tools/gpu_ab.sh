@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-for v in outfit_b200/variants/lib_base.so "" outfit_b200/variants/lib_bps5.so outfit_b200/variants/lib_bps6.so; do OUTFIT_B200_LIB=$v OUTFIT_B200_STREAMS=1 PERF_PARITY=1 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB=|parity"; done | tee gpurun_out/r02r_ab.log
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r02t_pytest.log
+OUTFIT_B200_STREAMS=1 PERF_PARITY=0 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB=" | tee gpurun_out/r02t_ab.log
+OUTFIT_B200_STREAMS=1 PERF_RAGGED=1 PERF_PARITY=0 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB=" | tee -a gpurun_out/r02t_ab.log
