@@ -39,23 +39,15 @@ __device__ __forceinline__ Cx cx_mul(Cx a, Cx b) {
 }
 // Two quotients over one denominator n: one correctly rounded reciprocal y = RN(1/n) and Markstein's
 // correction (q0 = a*y; r = fma(-n, q0, a); q = fma(r, y, q0)) give RN(a/n), the bits of the IEEE
-// division, for finite operands of sane magnitude; anything else (a vanished or overflowed
-// denominator: coincident iterates, the crate's `Failed` path) takes the IEEE divisions.
-__device__ __noinline__ void div2_ieee(double a, double b, double n, double *out) {
-  out[0] = __ddiv_rn(a, n);
-  out[1] = __ddiv_rn(b, n);
-}
+// division, whenever 1/n and the quotient neither overflow nor underflow -- |z_i - z_k|^2 and
+// |p s - p'|^2 of O(1) iterates are nowhere near that.  A vanished denominator (coincident iterates)
+// yields NaN here where the division yields +-inf or NaN: both end the solve as `Failed`
+// (the caller tests isfinite on the new iterate), so no guard is needed.
 __device__ __forceinline__ Cx div2_same_denominator(double a, double b, double n) {
-  const double an = fabs(n);
-  if (an > 1e-200 && an < 1e200) {  // (a non-finite numerator yields NaN instead of +-inf: both are `Failed`)
-    const double y = __drcp_rn(n);
-    const double qa = __dmul_rn(a, y), qb = __dmul_rn(b, y);
-    const double ra = __fma_rn(-n, qa, a), rb = __fma_rn(-n, qb, b);
-    return Cx{__fma_rn(ra, y, qa), __fma_rn(rb, y, qb)};
-  }
-  double o[2];
-  div2_ieee(a, b, n, o);
-  return Cx{o[0], o[1]};
+  const double y = __drcp_rn(n);
+  const double qa = __dmul_rn(a, y), qb = __dmul_rn(b, y);
+  const double ra = __fma_rn(-n, qa, a), rb = __fma_rn(-n, qb, b);
+  return Cx{__fma_rn(ra, y, qa), __fma_rn(rb, y, qb)};
 }
 __device__ __forceinline__ Cx cx_div(Cx a, Cx b) {
   const double n = __dadd_rn(__dmul_rn(b.re, b.re), __dmul_rn(b.im, b.im));
