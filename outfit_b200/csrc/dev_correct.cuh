@@ -38,16 +38,15 @@ enum {
 };
 constexpr size_t kCorrectSmemBytes = (size_t)SL_COUNT * kCorrectThreads * sizeof(double);
 
-// RN(a / n) from y = RN(1 / n) (Markstein); a and n must be finite, n != 0, no over/underflow
+// RN(a / n) from y = RN(1 / n) (Markstein) for finite operands whose reciprocal and quotient neither
+// overflow nor underflow -- AU / day scale quantities here.  For a non-finite or vanished n it yields
+// NaN where the division may yield 0 or inf; every use below is followed by the reference's own
+// finiteness / acceptability tests, which reject both.
 __device__ __forceinline__ double div_mk(double a, double n, double y) {
   const double q0 = __dmul_rn(a, y);
   const double r = __fma_rn(-n, q0, a);
   return __fma_rn(r, y, q0);
 }
-// true when the Markstein form may replace a division by n (sane magnitude; everything on this path
-// is AU / day scale, the guard only routes pathological values to the IEEE division)
-__device__ __forceinline__ bool mk_ok(double n) { return fabs(n) > 1e-100 && fabs(n) < 1e100; }
-
 // Correctly rounded reciprocals of the compile-time denominators, in the constant bank: an FP64
 // instruction takes c[bank][offset] as a direct operand, whereas a 64-bit literal costs two UMOVs.
 enum { RC_3 = 16, RC_GAUSSK = 17, RC_MU = 18, RC_VLIGHT = 19 };
@@ -238,7 +237,7 @@ __device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double
   const V3 lenz = V3{vxh.x * inv_mu - r.x * inv_d, vxh.y * inv_mu - r.y * inv_d, vxh.z * inv_mu - r.z * inv_d};
   m.ecc = norm(lenz);
   const double peri = h2 / (kMu * (1.0 + m.ecc));
-  const double energy = v2 / 2.0 - (mk_ok(dist) ? div_mk(kMu, dist, inv_d) : kMu / dist);
+  const double energy = v2 / 2.0 - div_mk(kMu, dist, inv_d);
   m.accepted = (m.ecc < ecc_max) && (peri < peri_max);
   m.r2 = dist;
   m.inv_r2 = inv_d;
@@ -272,18 +271,14 @@ __device__ __forceinline__ SideC correction_side(const GeoSm &G, int x1_slot, V3
   double psi = has_guess ? chi_guess : prelim_kepuni_v(dt, m.r2, m.sig0, m.alpha, m.ecc, eps);
   double s2, s3;
   if (!kepuni_newton_fast<COUNT>(dt, m.r2, m.sig0, m.alpha, eps, psi, s2, s3, w)) return o;
-  const double f = 1.0 - (mk_ok(m.r2) ? div_mk(s2, m.r2, m.inv_r2) : s2 / m.r2);
+  const double f = 1.0 - div_mk(s2, m.r2, m.inv_r2);
   const double g = dt - div_mk(s3, kGaussK, c_rcp[RC_GAUSSK]);
   const double ga = fabs(g);
   if (!isfinite(ga) || ga < 100.0 * kEps * (1.0 + fabs(dt))) return o;
   const V3 x1 = G.v3(x1_slot);
   const double nx = (-f) * x2.x + x1.x, ny = (-f) * x2.y + x1.y, nz = (-f) * x2.z + x1.z;
-  if (mk_ok(g)) {
-    const double yg = 1.0 / g;
-    o.v = V3{div_mk(nx, g, yg), div_mk(ny, g, yg), div_mk(nz, g, yg)};
-  } else {
-    o.v = V3{nx / g, ny / g, nz / g};
-  }
+  const double yg = 1.0 / g;  // |g| >= 100 eps (1 + |dt|), finite: checked above
+  o.v = V3{div_mk(nx, g, yg), div_mk(ny, g, yg), div_mk(nz, g, yg)};
   o.f = f; o.g = g; o.chi = psi;
   o.ok = true;
   return o;

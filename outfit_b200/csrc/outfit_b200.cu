@@ -262,10 +262,11 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
         const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;  // != 0: P1 accepted this candidate
         const double num[9] = {mi1, m13 * m32 - m33 * m12, m12 * m23 - m22 * m13, -mi2, m11 * m33 - m31 * m13,
                                m13 * m21 - m23 * m11, mi3, m12 * m31 - m32 * m11, m11 * m22 - m21 * m12};
-        const bool mk = mk_ok(det);
+        // det != 0 and P1 found admissible roots with this very matrix: a |det| small enough to break the
+        // reciprocal form (< 1e-290) would have sent the roots out of the plausibility window
         const double yd = 1.0 / det;
 #pragma unroll
-        for (int q = 0; q < 9; ++q) my[(SL_I0 + q) * kCorrectThreads] = mk ? div_mk(num[q], det, yd) : num[q] / det;
+        for (int q = 0; q < 9; ++q) my[(SL_I0 + q) * kCorrectThreads] = div_mk(num[q], det, yd);
       }
       unsigned n_solutions = 0;
 #pragma unroll 1
