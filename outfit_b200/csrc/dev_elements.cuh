@@ -184,7 +184,7 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   const V3 pos = xe * s.F + ye * s.G;
   const V3 vel = vxe * s.F + vye * s.G;
   const V3 rel = pos - obs_equ;
-  const double ltt = norm(rel) / kVlightAu;
+  const double ltt = div_by_const(norm(rel), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
   const V3 cor = rel - ltt * vel;
   const double dec = atan2(cor.z, hypot(cor.x, cor.y));
   const double ra = rem_euclid(atan2(cor.y, cor.x), kTwoPi);

@@ -252,7 +252,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
             const double helio = norm(ap);
             const double geo = norm(ap - ep);
             const V3 raw = ap - op;
-            const double ltt = norm(raw) / kVlightAu;
+            const double ltt = div_by_const(norm(raw), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
             const V3 topo = raw - ltt * av;
             o[0] = rem_euclid(atan2(topo.y, topo.x), kTwoPi);
             o[1] = atan2(topo.z, sqrt(topo.x * topo.x + topo.y * topo.y));
