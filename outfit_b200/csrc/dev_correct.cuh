@@ -208,7 +208,7 @@ __device__ __forceinline__ bool kepuni_newton_fast(double dt, double r0, double 
     if (fabs(res) <= tol) return true;
     if (!isfinite(der) || fabs(der) < 10.0 * kEps) { psi *= 0.5; continue; }
     const double mx = 2.0 * (1.0 + fabs(psi));
-    const double step = clampd(-res / der, -mx, mx);
+    const double step = clampd(bf_div(-res, der), -mx, mx);
     double cand = psi + step;
     if (cand * psi < 0.0) cand = 0.5 * psi;
     psi = cand;
@@ -226,17 +226,17 @@ struct MidC {
 __device__ __forceinline__ MidC middle_state(V3 r, V3 v, double peri_max, double ecc_max) {
   MidC m;
   const double v2 = dot(v, v);
-  const double dist = norm(r);
+  const double dist = bf_sqrt(dot(r, r));
   const V3 h = cross(r, v);
   const double h2 = dot(h, h);
-  m.hn = sqrt(h2);
+  m.hn = bf_sqrt(h2);
   m.defined = !(m.hn == 0.0);
   const V3 vxh = cross(v, h);
   const double inv_mu = c_rcp[RC_MU];
-  const double inv_d = 1.0 / dist;
+  const double inv_d = bf_rcp(dist);
   const V3 lenz = V3{vxh.x * inv_mu - r.x * inv_d, vxh.y * inv_mu - r.y * inv_d, vxh.z * inv_mu - r.z * inv_d};
-  m.ecc = norm(lenz);
-  const double peri = h2 / (kMu * (1.0 + m.ecc));
+  m.ecc = bf_sqrt(dot(lenz, lenz));
+  const double peri = bf_div(h2, kMu * (1.0 + m.ecc));
   const double energy = v2 / 2.0 - div_mk(kMu, dist, inv_d);
   m.accepted = (m.ecc < ecc_max) && (peri < peri_max);
   m.r2 = dist;
@@ -277,7 +277,7 @@ __device__ __forceinline__ SideC correction_side(const GeoSm &G, int x1_slot, V3
   if (!isfinite(ga) || ga < 100.0 * kEps * (1.0 + fabs(dt))) return o;
   const V3 x1 = G.v3(x1_slot);
   const double nx = (-f) * x2.x + x1.x, ny = (-f) * x2.y + x1.y, nz = (-f) * x2.z + x1.z;
-  const double yg = 1.0 / g;  // |g| >= 100 eps (1 + |dt|), finite: checked above
+  const double yg = bf_rcp(g);  // |g| >= 100 eps (1 + |dt|), finite: checked above
   o.v = V3{div_mk(nx, g, yg), div_mk(ny, g, yg), div_mk(nz, g, yg)};
   o.f = f; o.g = g; o.chi = psi;
   o.ok = true;
@@ -290,9 +290,9 @@ __device__ __forceinline__ bool positions_c(const GeoSm &G, double c0, double c2
   const V3 R0 = G.v3(SL_R0), R1 = G.v3(SL_R1), R2 = G.v3(SL_R2);
   const V3 gc = V3{(R0.x * c0 + R1.x * -1.0) + R2.x * c2, (R0.y * c0 + R1.y * -1.0) + R2.y * c2,
                    (R0.z * c0 + R1.z * -1.0) + R2.z * c2};
-  const double rho0 = -(dot(G.v3(SL_I0), gc) / c0);
+  const double rho0 = -bf_div(dot(G.v3(SL_I0), gc), c0);
   const double rho1 = dot(G.v3(SL_I1), gc);
-  const double rho2 = -(dot(G.v3(SL_I2), gc) / c2);
+  const double rho2 = -bf_div(dot(G.v3(SL_I2), gc), c2);
   if (rho1 < min_rho2) return false;
   p0 = R0 + rho0 * G.v3(SL_S0);
   p1 = R1 + rho1 * G.v3(SL_S1);
@@ -383,7 +383,7 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
     V3 n0, n1, n2;
     double nep = 0.0;
     if (!stall) {
-      const double inv_f = 1.0 / fl;
+      const double inv_f = bf_rcp(fl);
       stall = !positions_c(G, Rr.g * inv_f, -Lg * inv_f, P.min_rho2_au, n0, n1, n2, nep);
     }
     MidC nm;
@@ -391,7 +391,7 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
     if (!stall) {
       nm = middle_state(n1, nv, P.max_perihelion_au, P.max_ecc);
       if (!nm.defined || !nm.accepted) return false;
-      denom = sqrt((dot(n0, n0) + dot(n1, n1)) + dot(n2, n2));
+      denom = bf_sqrt((dot(n0, n0) + dot(n1, n1)) + dot(n2, n2));
       stall = !isfinite(denom) || denom <= kEps;
     }
     if (stall) {
@@ -402,7 +402,7 @@ __device__ __forceinline__ bool fg_correction_fast(const GeoSm &G, const IodDevP
       continue;
     }
     const V3 d0 = n0 - G.v3(SL_P0), d1 = n1 - p1, d2 = n2 - G.v3(SL_P2);
-    const double rel = sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)) / denom;
+    const double rel = bf_div(bf_sqrt((dot(d0, d0) + dot(d1, d1)) + dot(d2, d2)), denom);
     G.put3(SL_P0, n0);
     G.put3(SL_P2, n2);
     p1 = n1;

@@ -170,7 +170,7 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
       if (iter == 0) { x = x + 1.0; iter = 1; continue; }
       return false;
     }
-    const double x1 = x - f / d;
+    const double x1 = x - bf_div(f, d);
     const bool conv = fabs(x - x1) < eps;
     x = x1;
     if (conv) { last = true; continue; }
@@ -178,21 +178,21 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   }
   const double xe = s.a * (s.ch * cF + s.bhk * sF - s.k);
   const double ye = s.a * (s.ck * sF + s.bhk * cF - s.h);
-  const double vc = s.n * (s.a * s.a) / sqrt(xe * xe + ye * ye);
+  const double vc = bf_div(s.n * (s.a * s.a), bf_sqrt(xe * xe + ye * ye));
   const double vxe = vc * (s.bhk * cF - s.ch * sF);
   const double vye = vc * (s.ck * cF - s.bhk * sF);
   const V3 pos = xe * s.F + ye * s.G;
   const V3 vel = vxe * s.F + vye * s.G;
   const V3 rel = pos - obs_equ;
-  const double ltt = div_by_const(norm(rel), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
+  const double ltt = div_by_const(bf_sqrt(dot(rel, rel)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
   const V3 cor = rel - ltt * vel;
   const double dec = atan2(cor.z, hypot(cor.x, cor.y));
   const double ra = rem_euclid(atan2(cor.y, cor.x), kTwoPi);
   double da = ra_obs - ra;
   if (!(fabs(da) < kTwoPi)) da = fmod(da, kTwoPi);  // |x| < m: fmod(x, m) == x exactly
   if (da > kPi) da -= kTwoPi;  // reference quirk: wraps only the > pi side
-  const double a = cos_dec_obs * (da / sig_ra);
-  const double b = (dec_obs - dec) / sig_dec;
+  const double a = cos_dec_obs * bf_div(da, sig_ra);
+  const double b = bf_div(dec_obs - dec, sig_dec);
   chi2 = a * a + b * b;
   return true;
 }

@@ -44,7 +44,7 @@ __device__ __forceinline__ Cx cx_mul(Cx a, Cx b) {
 // yields NaN here where the division yields +-inf or NaN: both end the solve as `Failed`
 // (the caller tests isfinite on the new iterate), so no guard is needed.
 __device__ __forceinline__ Cx div2_same_denominator(double a, double b, double n) {
-  const double y = __drcp_rn(n);
+  const double y = bf_rcp(n);
   const double qa = __dmul_rn(a, y), qb = __dmul_rn(b, y);
   const double ra = __fma_rn(-n, qa, a), rb = __fma_rn(-n, qb, b);
   return Cx{__fma_rn(ra, y, qa), __fma_rn(rb, y, qb)};

@@ -580,6 +580,30 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
 }
 
 // =================================================================================================
+// self-test of the branch-free arithmetic (dev_kepler.cuh: bf_rcp / bf_div / bf_sqrt) against the intrinsics
+// =================================================================================================
+__global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long n, unsigned long long seed, int exp_range,
+                                                            unsigned long long *__restrict__ mismatches) {
+  unsigned long long bad_r = 0, bad_d = 0, bad_s = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long st = seed + 0x9e3779b97f4a7c15ull * i;
+    const unsigned long long u = splitmix64_next(st), v = splitmix64_next(st), e = splitmix64_next(st);
+    const long long ea = 1023 - exp_range + (long long)(e % (unsigned long long)(2 * exp_range));
+    const long long eb = 1023 - exp_range + (long long)((e >> 32) % (unsigned long long)(2 * exp_range));
+    const double a = __longlong_as_double((long long)((u & 0x800fffffffffffffull) | ((unsigned long long)ea << 52)));
+    const double b = __longlong_as_double((long long)((v & 0x800fffffffffffffull) | ((unsigned long long)eb << 52)));
+    if (__double_as_longlong(bf_rcp(b)) != __double_as_longlong(__drcp_rn(b))) ++bad_r;
+    if (__double_as_longlong(bf_div(a, b)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_d;
+    const double p = fabs(a);
+    if (__double_as_longlong(bf_sqrt(p)) != __double_as_longlong(__dsqrt_rn(p))) ++bad_s;
+  }
+  if (bad_r) atomicAdd(mismatches + 0, bad_r);
+  if (bad_d) atomicAdd(mismatches + 1, bad_d);
+  if (bad_s) atomicAdd(mismatches + 2, bad_s);
+}
+
+// =================================================================================================
 // FP64 pipe probe
 // =================================================================================================
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters) {
@@ -1316,6 +1340,22 @@ extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, co
   }
   cudaFree(d);
   return rc;
+}
+
+extern "C" int outfit_b200_selftest_arith(OutfitCtx *ctx, unsigned long long n, unsigned long long seed, int exp_range,
+                                          unsigned long long out3[3]) {
+  if (!ctx || !out3 || exp_range < 1 || exp_range > 500) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr;
+  CK(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+  selftest_arith_kernel<<<ctx->sm_count * 8, 256>>>(n, seed, exp_range, d);
+  cudaError_t e = cudaMemcpy(out3, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  // zero / special values: bf_sqrt(0) must be exactly 0
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "selftest_arith", e);
+  return OUTFIT_OK;
 }
 
 extern "C" int outfit_b200_measure_fp64_peak(OutfitCtx *ctx, double *flops_per_s) {

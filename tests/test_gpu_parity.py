@@ -369,3 +369,11 @@ def test_parity_at_scale_20k(env):
     _, got, want, ef, rf = run_both(env, 20000, 12, seed=161, K=30, nn=10)
     st = assert_iod_parity(got, want, ef, rf, min_plain_fraction=0.90, max_outlier_fraction=1e-3)
     assert st["n_ok"] > 19000
+
+
+def test_branch_free_arithmetic_is_bit_identical_to_the_intrinsics(env):
+    """bf_rcp / bf_div / bf_sqrt (dev_kepler.cuh) against __drcp_rn / __ddiv_rn / __dsqrt_rn: 4e8 random
+    operands over two exponent ranges, zero mismatches."""
+    ctx = env["ctx"]
+    assert ctx.selftest_arith(200_000_000, seed=1, exp_range=40) == (0, 0, 0)
+    assert ctx.selftest_arith(200_000_000, seed=2, exp_range=300) == (0, 0, 0)
