@@ -230,7 +230,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
               ok = false;
               break;
             }
-            const double x1 = x - f / d;
+            const double x1 = x - bf_div(f, d);
             const bool conv = fabs(x - x1) < eps;
             x = x1;
             if (conv) { last = true; continue; }
@@ -241,7 +241,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
           } else {
             const double xe = a * (ch * cF + bhk * sF - k);
             const double ye = a * (ck * sF + bhk * cF - h);
-            const double vc = n_mot * (a * a) / sqrt(xe * xe + ye * ye);
+            const double vc = bf_div(n_mot * (a * a), bf_sqrt(xe * xe + ye * ye));
             const double vxe = vc * (bhk * cF - ch * sF);
             const double vye = vc * (ck * cF - bhk * sF);
             const V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
@@ -249,28 +249,29 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
             const V3 op = V3{tile[j], tile[kEphTile + j], tile[2 * kEphTile + j]};
             const V3 ov = V3{tile[3 * kEphTile + j], tile[4 * kEphTile + j], tile[5 * kEphTile + j]};
             const V3 ep = V3{tile[6 * kEphTile + j], tile[7 * kEphTile + j], tile[8 * kEphTile + j]};
-            const double helio = norm(ap);
-            const double geo = norm(ap - ep);
+            const double helio = bf_sqrt(dot(ap, ap));
+            const V3 dgeo = ap - ep;
+            const double geo = bf_sqrt(dot(dgeo, dgeo));
             const V3 raw = ap - op;
-            const double ltt = div_by_const(norm(raw), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
+            const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
             const V3 topo = raw - ltt * av;
             o[0] = rem_euclid(atan2(topo.y, topo.x), kTwoPi);
-            o[1] = atan2(topo.z, sqrt(topo.x * topo.x + topo.y * topo.y));
+            o[1] = atan2(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
             o[2] = geo;
             o[3] = helio;
-            const double rho = norm(topo);
-            const double r_obs = norm(op);
-            o[4] = acos(clampd(dot(ap, topo) / (helio * rho), -1.0, 1.0));
-            o[5] = acos(clampd(-dot(op, topo) / (r_obs * rho), -1.0, 1.0));
+            const double rho = bf_sqrt(dot(topo, topo));
+            const double r_obs = bf_sqrt(dot(op, op));
+            o[4] = acos(clampd(bf_div(dot(ap, topo), helio * rho), -1.0, 1.0));
+            o[5] = acos(clampd(bf_div(-dot(op, topo), r_obs * rho), -1.0, 1.0));
             const V3 vt = av - ov;
-            o[6] = dot(topo, vt) / rho;
+            o[6] = bf_div(dot(topo, vt), rho);
             const double dxy2 = topo.x * topo.x + topo.y * topo.y;
-            const double dxy = sqrt(dxy2);
+            const double dxy = bf_sqrt(dxy2);
             if (dxy < kEps * rho) {
               o[7] = 0.0; o[8] = 0.0;
             } else {
-              o[7] = (-topo.y * vt.x + topo.x * vt.y) / dxy2;
-              o[8] = (-topo.z * topo.x * vt.x - topo.z * topo.y * vt.y + dxy2 * vt.z) / (rho * rho * dxy);
+              o[7] = bf_div(-topo.y * vt.x + topo.x * vt.y, dxy2);
+              o[8] = bf_div(-topo.z * topo.x * vt.x - topo.z * topo.y * vt.y + dxy2 * vt.z, rho * rho * dxy);
             }
           }
         }

@@ -522,15 +522,15 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
 #pragma unroll
   for (int q = 0; q < 11; ++q) o[q] = NAN;
   int stt = OUTFIT_ST_OK;
-  const double r0 = norm(r);
+  const double r0 = bf_sqrt(dot(r, r));
   if (r0 < kEps) {
     stt = OUTFIT_ST_DEGENERATE_STATE;
   } else {
     const double v2 = dot(v, v);
-    const double sig0 = dot(r, v) / kGaussK;
-    const double alpha = (v2 - 2.0 * kMu / r0) / kMu;
+    const double sig0 = bf_div(dot(r, v), kGaussK);
+    const double alpha = bf_div(v2 - bf_div(2.0 * kMu, r0), kMu);
     const V3 h = cross(r, v);
-    double e0 = sqrt(1.0 + alpha * dot(h, h) / kMu);
+    double e0 = bf_sqrt(1.0 + bf_div(alpha * dot(h, h), kMu));
     e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
     const double dt = t1[i] - t0[i];
     // initial guess (prelim_kepler/*.rs) out of line, Newton (newton_solver.rs:240-352) inlined with the
@@ -564,10 +564,10 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
       if (r1 < kEps) {
         stt = OUTFIT_ST_DEGENERATE_STATE;
       } else {
-        const double fl = 1.0 - s2 / r0;
-        const double gl = (r0 * s01[1] + sig0 * s2) / kGaussK;
-        const double fd = -(kGaussK / (r0 * r1)) * s01[1];
-        const double gd = 1.0 - s2 / r1;
+        const double fl = 1.0 - bf_div(s2, r0);
+        const double gl = bf_div(r0 * s01[1] + sig0 * s2, kGaussK);
+        const double fd = -bf_div(kGaussK, r0 * r1) * s01[1];
+        const double gd = 1.0 - bf_div(s2, r1);
         o[0] = fl * r.x + gl * v.x; o[1] = fl * r.y + gl * v.y; o[2] = fl * r.z + gl * v.z;
         o[3] = fd * r.x + gd * v.x; o[4] = fd * r.y + gd * v.y; o[5] = fd * r.z + gd * v.z;
         o[6] = fl; o[7] = gl; o[8] = fd; o[9] = gd; o[10] = psi;
