@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r02x_pytest.log
-python tools/gpu_perf_eph.py | tee gpurun_out/r02x_ab.log
-python tools/gpu_perf_kepler.py | tee -a gpurun_out/r02x_ab.log
+for v in "" outfit_b200/variants/lib_ung.so; do OUTFIT_B200_LIB=$v OUTFIT_B200_STREAMS=1 PERF_PARITY=0 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB="; OUTFIT_B200_LIB=$v python tools/gpu_perf_eph.py; done | tee gpurun_out/r03a_ab.log
