@@ -56,12 +56,12 @@ KERNEL_PHASE = {"roots_kernel": "roots_ms", "correct_kernel": "correct_ms", "sco
 
 
 # One `ncu` capture of a single-pass launch of THIS workload (100 k trajectories x 12 observations),
-# profiles/r02l_ncu_metrics_100k.csv: DRAM bytes per launch (read + write), FP64 pipe utilisation, issue
+# profiles/r03c_ncu_metrics_100k.csv: DRAM bytes per launch (read + write), FP64 pipe utilisation, issue
 # slot utilisation, active threads per warp instruction.  Static evidence, not re-measured by bench.py.
-NCU_R02L = {
-    "roots_kernel": {"dram_bytes": 1556186880 + 1034213632, "fp64_pipe_pct": 69.74, "issue_pct": 54.48, "threads_per_inst": 31.10},
-    "correct_kernel": {"dram_bytes": 2048618496 + 1953743360, "fp64_pipe_pct": 56.07, "issue_pct": 52.01, "threads_per_inst": 24.79},
-    "score_kernel": {"dram_bytes": 2201879808 + 675036160, "fp64_pipe_pct": 55.32, "issue_pct": 77.24, "threads_per_inst": 29.59},
+NCU_R03C = {
+    "roots_kernel": {"dram_bytes": 1556703488 + 1037716480, "fp64_pipe_pct": 81.28, "issue_pct": 53.05, "threads_per_inst": 31.07},
+    "correct_kernel": {"dram_bytes": 2045758208 + 1946571520, "fp64_pipe_pct": 63.89, "issue_pct": 54.51, "threads_per_inst": 24.83},
+    "score_kernel": {"dram_bytes": 2200741888 + 652708608, "fp64_pipe_pct": 57.96, "issue_pct": 77.93, "threads_per_inst": 29.59},
 }
 
 
@@ -405,7 +405,7 @@ def main():
             kernels[kname] = {"ms": kms, "share_of_step": kms / kernel_ms, "algorithmic_flop": kfl,
                               "tflops": kfl / (kms * 1e-3) / 1e12, "frac_fp64_peak": kfl / (kms * 1e-3) / fp64_peak}
             if args.workload == "c3_100k_x12":
-                kernels[kname]["ncu_r02l"] = NCU_R02L[kname]
+                kernels[kname]["ncu_r03c"] = NCU_R03C[kname]
         for kname, key in (("scorer_observer_kernel", "observer_ms"), ("triplets_kernel", "triplets_ms"),
                            ("select_kernel", "select_ms")):
             kernels[kname] = {"ms": phases[key], "share_of_step": phases[key] / kernel_ms}
@@ -429,7 +429,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": kernels[dom]["frac_fp64_peak"],
-                         "traffic": NCU_R02L[dom]["dram_bytes"] if args.workload == "c3_100k_x12" else None, "kernel": dom,
+                         "traffic": NCU_R03C[dom]["dram_bytes"] if args.workload == "c3_100k_x12" else None, "kernel": dom,
                          "kernel_ms": kernels[dom]["ms"], "algorithmic_flop_per_launch": kernels[dom]["algorithmic_flop"],
                          "step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / fp64_peak, "ms": ms,
                                   "single_pass_ms": kernel_ms, "single_pass_frac": achieved / fp64_peak,
