@@ -160,7 +160,7 @@ def load_library():
     L.outfit_b200_set_pass_streams.argtypes = [vp, C.c_int]
     L.outfit_b200_last_iod_phase_ms.argtypes = [vp, C.POINTER(IodPhaseMs)]
     L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
-    L.outfit_b200_selftest_arith.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64 * 3]
+    L.outfit_b200_selftest_arith.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64 * 4]
     L.outfit_b200_ephemeris_twobody.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, C.c_double * 3, vp, vp]
     L.outfit_b200_ephemeris_twobody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp,
                                                        C.c_double * 3, vp, vp, vp]
@@ -315,8 +315,8 @@ class OutfitB200:
                                                                  _p(mjd_tt), _p(mjd_ut1), bf, _p(out), _p(status), stream))
 
     def selftest_arith(self, n, seed=1, exp_range=60):
-        """Mismatch counts (rcp, div, sqrt) of the branch-free arithmetic against the CUDA intrinsics."""
-        out = (C.c_uint64 * 3)()
+        """Mismatch counts (rcp, div, sqrt, sincos) of the library's own arithmetic against CUDA's."""
+        out = (C.c_uint64 * 4)()
         self._check(self._L.outfit_b200_selftest_arith(self._h, int(n), int(seed), int(exp_range), out))
         return tuple(int(x) for x in out)
 

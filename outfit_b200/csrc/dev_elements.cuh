@@ -160,7 +160,7 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   int iter = 0;
   bool last = false;
   for (;;) {
-    sincos(x, &sF, &cF);  // the only sincos site: also evaluates at the accepted root
+    sincos_angle(x, &sF, &cF);  // the only sincos site: also evaluates at the accepted root
     if (last) break;
     if (COUNT) ++w.scorer_newton;
     const double f = x - s.k * sF + s.h * cF - lam1;

@@ -220,7 +220,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
           int iter = 0;
           bool last = false, ok = true;
           for (;;) {
-            sincos(x, &sF, &cF);
+            sincos_angle(x, &sF, &cF);
             if (last) break;
             const double f = x - k * sF + h * cF - lam1;
             const double d = 1.0 - k * cF - h * sF;

@@ -584,7 +584,7 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
 // =================================================================================================
 __global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long n, unsigned long long seed, int exp_range,
                                                             unsigned long long *__restrict__ mismatches) {
-  unsigned long long bad_r = 0, bad_d = 0, bad_s = 0;
+  unsigned long long bad_r = 0, bad_d = 0, bad_s = 0, bad_t = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     unsigned long long st = seed + 0x9e3779b97f4a7c15ull * i;
@@ -597,7 +597,16 @@ __global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long 
     if (__double_as_longlong(bf_div(a, b)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_d;
     const double p = fabs(a);
     if (__double_as_longlong(bf_sqrt(p)) != __double_as_longlong(__dsqrt_rn(p))) ++bad_s;
+    // angles: uniform in (-64, 64) from one draw, magnitudes down to 2^-40 from the other
+    const double ang = ((double)(long long)(u >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 128.0;
+    const double small = __longlong_as_double((long long)((v & 0x800fffffffffffffull) | ((unsigned long long)(1023 - (e % 40)) << 52)));
+    double s0, c0, s1, c1;
+    sincos(ang, &s0, &c0); sincos_angle(ang, &s1, &c1);
+    if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
+    sincos(small, &s0, &c0); sincos_angle(small, &s1, &c1);
+    if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
   }
+  if (bad_t) atomicAdd(mismatches + 3, bad_t);
   if (bad_r) atomicAdd(mismatches + 0, bad_r);
   if (bad_d) atomicAdd(mismatches + 1, bad_d);
   if (bad_s) atomicAdd(mismatches + 2, bad_s);
@@ -1343,15 +1352,15 @@ extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, co
 }
 
 extern "C" int outfit_b200_selftest_arith(OutfitCtx *ctx, unsigned long long n, unsigned long long seed, int exp_range,
-                                          unsigned long long out3[3]) {
-  if (!ctx || !out3 || exp_range < 1 || exp_range > 500) return OUTFIT_E_INVALID_ARGUMENT;
+                                          unsigned long long out4[4]) {
+  if (!ctx || !out4 || exp_range < 1 || exp_range > 500) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   unsigned long long *d = nullptr;
-  CK(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
-  CK(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
   selftest_arith_kernel<<<ctx->sm_count * 8, 256>>>(n, seed, exp_range, d);
-  cudaError_t e = cudaMemcpy(out3, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   // zero / special values: bf_sqrt(0) must be exactly 0
   cudaFree(d);
   if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "selftest_arith", e);

@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-OUTFIT_B200_STREAMS=1 PERF_T=100000 PERF_PARITY=0 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:'roots_kernel|correct_kernel|score_kernel|triplets_thread_kernel|select_kernel' --launch-skip 5 -c 5 --csv --log-file gpurun_out/r03c_ncu_metrics_100k.csv python tools/gpu_perf.py > gpurun_out/r03c_ncu.log 2>&1; echo "rc=$?"
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee gpurun_out/r03d_pytest.log
+OUTFIT_B200_STREAMS=1 PERF_PARITY=1 python tools/gpu_perf.py 2>&1 | grep -E "phases|LIB=|parity" | tee gpurun_out/r03d_ab.log
+python tools/gpu_perf_eph.py | tee -a gpurun_out/r03d_ab.log
