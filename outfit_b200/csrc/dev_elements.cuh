@@ -186,8 +186,8 @@ __device__ __forceinline__ bool ephemeris_error(const ScoreOrbit &s, double t_ob
   const V3 rel = pos - obs_equ;
   const double ltt = div_by_const(bf_sqrt(dot(rel, rel)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
   const V3 cor = rel - ltt * vel;
-  const double dec = atan2(cor.z, hypot(cor.x, cor.y));
-  const double ra = rem_euclid(atan2(cor.y, cor.x), kTwoPi);
+  const double dec = atan2_finite(cor.z, hypot(cor.x, cor.y));
+  const double ra = rem_euclid(atan2_finite(cor.y, cor.x), kTwoPi);
   double da = ra_obs - ra;
   if (!(fabs(da) < kTwoPi)) da = fmod(da, kTwoPi);  // |x| < m: fmod(x, m) == x exactly
   if (da > kPi) da -= kTwoPi;  // reference quirk: wraps only the > pi side

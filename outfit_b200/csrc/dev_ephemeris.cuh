@@ -255,8 +255,8 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
             const V3 raw = ap - op;
             const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
             const V3 topo = raw - ltt * av;
-            o[0] = rem_euclid(atan2(topo.y, topo.x), kTwoPi);
-            o[1] = atan2(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
+            o[0] = rem_euclid(atan2_finite(topo.y, topo.x), kTwoPi);
+            o[1] = atan2_finite(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
             o[2] = geo;
             o[3] = helio;
             const double rho = bf_sqrt(dot(topo, topo));

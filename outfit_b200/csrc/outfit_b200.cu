@@ -605,6 +605,13 @@ __global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long 
     if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
     sincos(small, &s0, &c0); sincos_angle(small, &s1, &c1);
     if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
+    // atan2: the operand pair (a, b) of the division test (ratios over +-2 exp_range binades, all
+    // quadrants) and a pair of comparable magnitudes
+    if (__double_as_longlong(atan2(a, b)) != __double_as_longlong(atan2_finite(a, b))) ++bad_t;
+    if (__double_as_longlong(atan2(ang, small)) != __double_as_longlong(atan2_finite(ang, small))) ++bad_t;
+    if (__double_as_longlong(atan2(small, ang)) != __double_as_longlong(atan2_finite(small, ang))) ++bad_t;
+    const double c2 = ang * 0.37 + small;
+    if (__double_as_longlong(atan2(ang, c2)) != __double_as_longlong(atan2_finite(ang, c2))) ++bad_t;
   }
   if (bad_t) atomicAdd(mismatches + 3, bad_t);
   if (bad_r) atomicAdd(mismatches + 0, bad_r);
