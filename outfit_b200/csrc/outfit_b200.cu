@@ -375,7 +375,7 @@ score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
             const unsigned long long gI = o0 + ii;
             const double dec_o = __ldg(B.dec + gI);
             double v;
-            if (!ephemeris_error<COUNT>(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos(dec_o), __ldg(B.sigma_ra + gI),
+            if (!ephemeris_error<COUNT>(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos_angle(dec_o), __ldg(B.sigma_ra + gI),
                                  __ldg(B.sigma_dec + gI),
                                  V3{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)},
                                  v, w)) {
@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long 
     double s0, c0, s1, c1;
     sincos(ang, &s0, &c0); sincos_angle(ang, &s1, &c1);
     if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
+    if (__double_as_longlong(cos(ang)) != __double_as_longlong(c1)) ++bad_t;  // cos() alone == the cosine of sincos()
     sincos(small, &s0, &c0); sincos_angle(small, &s1, &c1);
     if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
     // atan2: the operand pair (a, b) of the division test (ratios over +-2 exp_range binades, all
