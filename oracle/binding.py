@@ -320,3 +320,70 @@ def counters():
     c = Counters()
     lib().oo_counters_get(C.byref(c))
     return {n: getattr(c, n) for n, _ in Counters._fields_}
+
+
+# ---- differential orbit correction (oo_lsq.c) ---------------------------------------------------
+class LsqConfig(C.Structure):
+    _fields_ = [("max_newton_iterations", C.c_uint64), ("max_outlier_rejection_passes", C.c_uint64),
+                ("convergence_threshold", C.c_double), ("convergence_before_rejection_threshold", C.c_double),
+                ("rms_stagnation_ratio", C.c_double), ("rms_divergence_ratio", C.c_double),
+                ("max_stagnation_iterations", C.c_uint64), ("enable_outlier_rejection", C.c_int32),
+                ("chi2_rejection_threshold", C.c_double), ("chi2_recovery_threshold", C.c_double),
+                ("eccentricity_limit", C.c_double), ("min_semi_major_axis", C.c_double),
+                ("max_semi_major_axis", C.c_double), ("min_periapsis_distance", C.c_double),
+                ("max_apoapsis_distance", C.c_double), ("free_elements", C.c_int32 * 6)]
+
+
+OBS_EQUATION_DTYPE = np.dtype([("d_ra", "<f8", (6,)), ("d_dec", "<f8", (6,)), ("residual_ra", "<f8"),
+                               ("residual_dec", "<f8"), ("weight_ra", "<f8"), ("weight_dec", "<f8"),
+                               ("weight_cross", "<f8"), ("active", "<i4")], align=True)
+OBS_FIT_DTYPE = np.dtype([("sigma_ra", "<f8"), ("sigma_dec", "<f8"), ("bias_ra", "<f8"), ("bias_dec", "<f8"),
+                          ("residual_ra", "<f8"), ("residual_dec", "<f8"), ("chi", "<f8"),
+                          ("selection", "<i4")], align=True)
+LSQ_SOLUTION_DTYPE = np.dtype([("correction", "<f8", (6,)), ("normal_matrix", "<f8", (36,)),
+                               ("covariance", "<f8", (36,)), ("normalised_rms", "<f8"),
+                               ("num_measurements", "<u8"), ("inversion_succeeded", "<i4")], align=True)
+LSQ_RESULT_DTYPE = np.dtype([("status", "<i4"), ("kind", "<i4"), ("fallback_cause", "<i4"), ("epoch", "<f8"),
+                             ("elem", "<f8", (6,)), ("sigma", "<f8", (6,)), ("normal_matrix", "<f8", (36,)),
+                             ("covariance", "<f8", (36,)), ("normalised_rms", "<f8"),
+                             ("total_newton_iterations", "<u8"), ("num_measurements", "<u8")], align=True)
+
+
+def default_lsq_config(**kw):
+    c = LsqConfig()
+    lib().oo_lsq_config_default(C.byref(c))
+    for k, v in kw.items():
+        if k == "free_elements":
+            c.free_elements = (C.c_int32 * 6)(*[int(x) for x in v])
+        else:
+            setattr(c, k, v)
+    return c
+
+
+def solve_weighted_least_squares(eqs, free=(1, 1, 1, 1, 1, 1)):
+    out = np.zeros(1, dtype=LSQ_SOLUTION_DTYPE)
+    fr = (C.c_int32 * 6)(*[int(x) for x in free])
+    lib().oo_solve_weighted_least_squares(C.c_size_t(len(eqs)), ptr(eqs), fr, ptr(out))
+    return out[0]
+
+
+def update_observation_selection(fit, eqs, covariance, chi2_reject=25.0, chi2_recover=9.0):
+    fit = fit.copy()
+    cov = np.ascontiguousarray(covariance, dtype=np.float64)
+    L = lib()
+    L.oo_update_observation_selection.restype = C.c_size_t
+    n = L.oo_update_observation_selection(C.c_size_t(len(fit)), ptr(fit), ptr(eqs), ptr(cov),
+                                          C.c_double(chi2_reject), C.c_double(chi2_recover))
+    return fit, int(n)
+
+
+def fit_lsq(batch, table, cfg, iod, n_threads=0):
+    """batch as for fit_full_iod (AoS geo_ecl); iod: IOD_RESULT_DTYPE array -> (results, per-obs fit data)."""
+    T = len(batch["traj_offset"]) - 1
+    out = np.zeros(T, dtype=LSQ_RESULT_DTYPE)
+    fit = np.zeros(len(batch["mjd_tt"]), dtype=OBS_FIT_DTYPE)
+    iod = np.ascontiguousarray(iod)
+    lib().oo_fit_lsq(C.c_size_t(T), ptr(batch["traj_offset"]), ptr(batch["mjd_tt"]), ptr(batch["ra"]),
+                     ptr(batch["dec"]), ptr(batch["sigma_ra"]), ptr(batch["sigma_dec"]), ptr(batch["geo_ecl"]),
+                     C.byref(table), C.byref(cfg), ptr(iod), ptr(out), ptr(fit), n_threads)
+    return out, fit

@@ -314,6 +314,79 @@ void oo_ephemeris_twobody_batch(const oo_ephem_table *tab, size_t n_orbits, cons
                                 const double *mjd_tt, const double *mjd_ut1, const double r_bf[3],
                                 double *out, int32_t *status, int n_threads, int dedup_observer);
 
+/* ---- differential orbit correction (differential_orbit_correction/; oo_lsq.c) --------------- */
+enum { OO_ERR_LSQ_INVERSION = 18,   /* DifferentialCorrectionFailed (normal-equation inversion) */
+       OO_ERR_LSQ_BIZARRE = 19,     /* BizarreOrbit */
+       OO_ERR_LSQ_DIVERGED = 20 };  /* DifferentialCorrectionDiverged */
+enum { OO_LSQ_KIND_NONE = 0,          /* no orbit: `status` holds the IOD / conversion error */
+       OO_LSQ_KIND_CORRECTED = 1,     /* FitOrbitResult::DifferentialCorrection */
+       OO_LSQ_KIND_IOD_FALLBACK = 2 };/* the loop failed: the IOD result is returned (mod.rs:113) */
+typedef struct {                    /* DifferentialCorrectionConfig, diff_cor.rs:100-192 */
+  uint64_t max_newton_iterations, max_outlier_rejection_passes;
+  double convergence_threshold, convergence_before_rejection_threshold;
+  double rms_stagnation_ratio, rms_divergence_ratio;
+  uint64_t max_stagnation_iterations;
+  int32_t enable_outlier_rejection;
+  double chi2_rejection_threshold, chi2_recovery_threshold;     /* OutlierRejectionConfig */
+  double eccentricity_limit, min_semi_major_axis, max_semi_major_axis, min_periapsis_distance,
+      max_apoapsis_distance;                                     /* EquinoctialLimits */
+  int32_t free_elements[6];
+} oo_lsq_config;
+typedef struct {                    /* ObservationEquation, least_square.rs:60-101 */
+  double d_ra[6], d_dec[6], residual_ra, residual_dec, weight_ra, weight_dec, weight_cross;
+  int32_t active;
+} oo_obs_equation;
+typedef struct {                    /* ObsFitData, obs_fit_data.rs:60-116 ; selection 0/1/2 */
+  double sigma_ra, sigma_dec, bias_ra, bias_dec, residual_ra, residual_dec, chi;
+  int32_t selection;
+} oo_obs_fit_data;
+typedef struct {                    /* DifferentialCorrectionResult; matrices column-major 6x6 */
+  double correction[6], normal_matrix[36], covariance[36], normalised_rms;
+  uint64_t num_measurements;
+  int32_t inversion_succeeded;
+} oo_lsq_solution;
+typedef struct {
+  int32_t status;                   /* OO_OK or the error that left no orbit */
+  int32_t kind;                     /* OO_LSQ_KIND_* */
+  int32_t fallback_cause;           /* OO_ERR_LSQ_* when kind == IOD_FALLBACK */
+  double epoch, elem[6];            /* CORRECTED: equinoctial (a,h,k,p,q,lambda); FALLBACK: the IOD elements */
+  double sigma[6];                  /* EquinoctialUncertainty::from_covariance */
+  double normal_matrix[36], covariance[36];
+  double normalised_rms;            /* FALLBACK: the IOD rms */
+  uint64_t total_newton_iterations, num_measurements;
+} oo_lsq_result;
+void oo_lsq_config_default(oo_lsq_config *c);
+int oo_is_bizarre(const double eq[6], const oo_lsq_config *c);
+void oo_compute_derivative(const double eq[6], double t0, double t1, double n, double lam1, double F,
+                           double inv_u, double beta, double sF, double cF, double xe, double ye,
+                           double vxe, double vye, const double fv[3], const double gv[3],
+                           const double pos[3], const double vel[3], double dpos[18], double dvel[18]);
+int oo_propagate_twobody_partials(const oo_elements *eq, double t0, double t1, double pos[3],
+                                  double vel[3], double dpos[18], double dvel[18]);
+int oo_obs_and_partials(const oo_traj_view *tv, size_t i, const oo_ephem_table *tab,
+                        const oo_elements *equi, double *ra, double *dec, double d_ra[6],
+                        double d_dec[6]);
+double oo_angular_diff(double a, double b);
+int oo_invert_normal_matrix(const double m[36], double inv[36]);
+void oo_solve_weighted_least_squares(size_t n, const oo_obs_equation *eqs, const int32_t free_elements[6],
+                                     oo_lsq_solution *out);
+void oo_rescale_covariance(double normal_matrix[36], double covariance[36], size_t num_free,
+                           size_t num_measurements, double normalised_rms);
+size_t oo_update_observation_selection(size_t n, oo_obs_fit_data *fit, const oo_obs_equation *eqs,
+                                       const double covariance[36], double chi2_reject,
+                                       double chi2_recover);
+int oo_run_differential_correction(const oo_traj_view *tv, const oo_ephem_table *tab,
+                                   const oo_elements *initial, const oo_lsq_config *cfg,
+                                   oo_obs_fit_data *fit, oo_lsq_result *out);
+void oo_differential_correction(const oo_traj_view *tv, const oo_ephem_table *tab, const oo_iod_result *iod,
+                                const oo_lsq_config *cfg, oo_lsq_result *out, oo_obs_fit_data *fit);
+/* FitLSQ::fit_lsq (obs_dataset_api.rs:113-190) with initial_orbits = Some(IOD results), over a flat
+   batch, one task per trajectory.  fit: [sum n] per-observation fit data (final state). */
+void oo_fit_lsq(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,
+                const double *dec, const double *sigma_ra, const double *sigma_dec,
+                const double *geo_ecl, const oo_ephem_table *tab, const oo_lsq_config *cfg,
+                const oo_iod_result *iod, oo_lsq_result *out, oo_obs_fit_data *fit, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -468,3 +468,34 @@ void oo_ephemeris_twobody_batch(const oo_ephem_table *tab, size_t n_orbits, cons
   free(pv);
   free(st);
 }
+
+/* FitLSQ::fit_lsq (differential_orbit_correction/obs_dataset_api.rs:113-190) over a flat SoA batch */
+typedef struct {
+  const uint64_t *traj_offset;
+  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec, *geo_ecl;
+  const oo_ephem_table *tab;
+  const oo_lsq_config *cfg;
+  const oo_iod_result *iod;
+  oo_lsq_result *out;
+  oo_obs_fit_data *fit;
+} lsq_ctx;
+static void lsq_task(long long lo, long long hi, void *vctx) {
+  lsq_ctx *c = (lsq_ctx *)vctx;
+  for (long long t = lo; t < hi; t++) {
+    size_t o = (size_t)c->traj_offset[t], n = (size_t)(c->traj_offset[t + 1] - c->traj_offset[t]);
+    oo_traj_view tv;
+    tv.n = n;
+    tv.mjd_tt = c->mjd_tt + o; tv.ra = c->ra + o; tv.dec = c->dec + o;
+    tv.sigma_ra = c->sigma_ra + o; tv.sigma_dec = c->sigma_dec + o;
+    tv.helio_equ = NULL; tv.geo_ecl = c->geo_ecl + 3 * o;
+    tv.scorer_obs_equ = NULL;
+    oo_differential_correction(&tv, c->tab, &c->iod[t], c->cfg, &c->out[t], c->fit + o);
+  }
+}
+void oo_fit_lsq(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,
+                const double *dec, const double *sigma_ra, const double *sigma_dec,
+                const double *geo_ecl, const oo_ephem_table *tab, const oo_lsq_config *cfg,
+                const oo_iod_result *iod, oo_lsq_result *out, oo_obs_fit_data *fit, int n_threads) {
+  lsq_ctx c = {traj_offset, mjd_tt, ra, dec, sigma_ra, sigma_dec, geo_ecl, tab, cfg, iod, out, fit};
+  parallel_for((long long)n_traj, 1, n_threads, lsq_task, &c);
+}

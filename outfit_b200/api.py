@@ -21,7 +21,8 @@ STATUS_NAMES = {
     4: "SpuriousRootDetected", 5: "VelocityCorrectionError", 6: "NewtonRaphsonKeplerConvergence",
     7: "BrentDekkerKeplerConvergence", 8: "DegenerateState", 9: "InvalidConversion", 10: "InvalidOrbit",
     11: "RootFindingError", 12: "NonFiniteScore", 13: "NoFeasibleTriplets", 14: "NoViableOrbit",
-    15: "ObservationNotFound", 17: "EphemerisOutOfRange",
+    15: "ObservationNotFound", 17: "EphemerisOutOfRange", 18: "DifferentialCorrectionFailed", 19: "BizarreOrbit",
+    20: "DifferentialCorrectionDiverged",
 }
 
 
@@ -111,6 +112,39 @@ RESULT_DTYPE = np.dtype([
     align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(IodResult)
 
+class DifferentialCorrectionConfig(C.Structure):
+    """DifferentialCorrectionConfig (diff_cor.rs:100-192) + OutlierRejectionConfig + EquinoctialLimits."""
+    _fields_ = [("max_newton_iterations", C.c_uint64), ("max_outlier_rejection_passes", C.c_uint64),
+                ("convergence_threshold", C.c_double), ("convergence_before_rejection_threshold", C.c_double),
+                ("rms_stagnation_ratio", C.c_double), ("rms_divergence_ratio", C.c_double),
+                ("max_stagnation_iterations", C.c_uint64), ("enable_outlier_rejection", C.c_int32),
+                ("_pad0", C.c_int32), ("chi2_rejection_threshold", C.c_double),
+                ("chi2_recovery_threshold", C.c_double), ("eccentricity_limit", C.c_double),
+                ("min_semi_major_axis", C.c_double), ("max_semi_major_axis", C.c_double),
+                ("min_periapsis_distance", C.c_double), ("max_apoapsis_distance", C.c_double),
+                ("free_elements", C.c_int32 * 6)]
+
+    @classmethod
+    def default(cls, **kw):
+        c = cls()
+        load_library().outfit_b200_lsq_config_default(C.byref(c))
+        for k, v in kw.items():
+            if k.startswith("_") or not hasattr(c, k):
+                raise AttributeError(f"DifferentialCorrectionConfig has no field {k!r}")
+            if k == "free_elements":
+                v = (C.c_int32 * 6)(*[int(x) for x in v])
+            setattr(c, k, v)
+        return c
+
+
+LSQ_RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("kind", "<i4"), ("fallback_cause", "<i4"), ("_pad0", "<i4"), ("epoch", "<f8"),
+    ("elem", "<f8", (6,)), ("sigma", "<f8", (6,)), ("normal_matrix", "<f8", (36,)), ("covariance", "<f8", (36,)),
+    ("normalised_rms", "<f8"), ("total_newton_iterations", "<u8"), ("num_measurements", "<u8")], align=True)
+OBS_FIT_DTYPE = np.dtype([("residual_ra", "<f8"), ("residual_dec", "<f8"), ("chi", "<f8"), ("selection", "<i4"),
+                          ("_pad0", "<i4")], align=True)
+assert LSQ_RESULT_DTYPE.itemsize == 8 * (2 + 1 + 6 + 6 + 72 + 3) and OBS_FIT_DTYPE.itemsize == 32
+
 ABI_SYMBOLS = [
     "outfit_b200_abi_version", "outfit_b200_strerror", "outfit_b200_last_error",
     "outfit_b200_iod_params_default", "outfit_b200_iod_params_validate",
@@ -120,6 +154,7 @@ ABI_SYMBOLS = [
     "outfit_b200_propagate_universal_device", "outfit_b200_last_iod_counters", "outfit_b200_last_iod_phase_ms",
     "outfit_b200_set_work_counters", "outfit_b200_set_pass_streams",
     "outfit_b200_measure_fp64_peak", "outfit_b200_selftest_arith", "outfit_b200_ephemeris_twobody", "outfit_b200_ephemeris_twobody_device",
+    "outfit_b200_lsq_config_default", "outfit_b200_fit_lsq", "outfit_b200_fit_lsq_device",
 ]
 
 
@@ -160,6 +195,12 @@ def load_library():
     L.outfit_b200_set_pass_streams.argtypes = [vp, C.c_int]
     L.outfit_b200_last_iod_phase_ms.argtypes = [vp, C.POINTER(IodPhaseMs)]
     L.outfit_b200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.outfit_b200_lsq_config_default.argtypes = [C.POINTER(DifferentialCorrectionConfig)]
+    L.outfit_b200_lsq_config_default.restype = None
+    L.outfit_b200_fit_lsq.argtypes = [vp, C.POINTER(IODParams), C.POINTER(DifferentialCorrectionConfig),
+                                      C.POINTER(ObsBatch), vp, vp, vp]
+    L.outfit_b200_fit_lsq_device.argtypes = [vp, C.POINTER(DifferentialCorrectionConfig), C.POINTER(ObsBatch), vp, vp,
+                                             vp, vp]
     L.outfit_b200_selftest_arith.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64 * 4]
     L.outfit_b200_ephemeris_twobody.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, C.c_double * 3, vp, vp]
     L.outfit_b200_ephemeris_twobody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp,
@@ -253,6 +294,33 @@ class OutfitB200:
         if params.n_noise_realizations == 0:
             b.noise_z = None
         self._check(self._L.outfit_b200_fit_full_iod_device(self._h, C.byref(params), C.byref(b), _p(out_ptr), stream))
+
+    # -- FitLSQ::fit_lsq (differential_orbit_correction/obs_dataset_api.rs:113-190) ----------------
+    def fit_lsq(self, batch, iod_params, cfg=None, initial_orbits=None, use_body_fixed=False):
+        """HOST buffers.  initial_orbits: the RESULT_DTYPE array of fit_full_iod on the same batch, or None
+        to run the IOD first (like the reference with `initial_orbits = None`).
+        Returns (LSQ_RESULT_DTYPE[n_traj], OBS_FIT_DTYPE[n_obs])."""
+        cfg = cfg or DifferentialCorrectionConfig.default()
+        b = self._batch_struct(batch, use_body_fixed)
+        if iod_params is None or iod_params.n_noise_realizations == 0:
+            b.noise_z = None
+        out = np.zeros(int(b.n_traj), dtype=LSQ_RESULT_DTYPE)
+        fit = np.zeros(int(b.n_obs), dtype=OBS_FIT_DTYPE)
+        io = None
+        if initial_orbits is not None:
+            io = np.ascontiguousarray(initial_orbits, dtype=RESULT_DTYPE)
+            assert io.shape[0] == int(b.n_traj)
+        self._check(self._L.outfit_b200_fit_lsq(self._h, C.byref(iod_params) if iod_params is not None else None,
+                                                C.byref(cfg), C.byref(b), io.ctypes.data if io is not None else None,
+                                                out.ctypes.data, fit.ctypes.data))
+        return out, fit
+
+    def fit_lsq_device(self, dev_batch, cfg, iod_ptr, out_ptr, fit_ptr, stream=0, use_body_fixed=False):
+        """DEVICE-resident buffers; enqueues, does not sync."""
+        b = self._batch_struct(dev_batch, use_body_fixed)
+        b.noise_z = None
+        self._check(self._L.outfit_b200_fit_lsq_device(self._h, C.byref(cfg), C.byref(b), _p(iod_ptr), _p(out_ptr),
+                                                       _p(fit_ptr), stream))
 
     def last_iod_counters(self):
         c = IodCounters()

@@ -1,0 +1,267 @@
+// dev_lsq.cuh -- differential orbit correction (weighted least-squares Newton-Raphson on equinoctial
+// elements with outlier rejection), one thread per trajectory.
+//
+// Reference: differential_orbit_correction/{mod.rs:60-115, diff_cor.rs:282-442,
+// single_iteration.rs:140-317, least_square.rs:188-405, outlier_rejection.rs:118-235},
+// orbit_type/equinoctial_element.rs:258-270,442-637,639-867, ephemeris/observation_ephemeris.rs:204-258,
+// 418-450; the 6x6 Cholesky / Householder-QR inverses follow the published algorithms of nalgebra 0.34
+// (column axpy factorisation, column-by-column substitution, sequential dots).
+//
+// The arithmetic keeps the reference's operation order (no FMA contraction: the file is compiled with
+// -fmad=false), so against a CPU restatement only the libm calls differ (<= 1 ulp each).
+// What is NOT kept is the reference's data flow: `last_equations` (12 partials per observation, cloned
+// every Newton step) is not stored -- the rejection step re-evaluates the partials at the elements the
+// last accepted step was linearised at, which reproduces them bit for bit from 7 doubles of state.
+#pragma once
+#include "dev_elements.cuh"
+
+namespace ofb {
+
+struct LsqCfgDev {
+  unsigned long long max_newton_iterations, max_outlier_rejection_passes, max_stagnation_iterations;
+  double convergence_threshold, convergence_before_rejection_threshold, rms_stagnation_ratio, rms_divergence_ratio;
+  double chi2_reject, chi2_recover;
+  double ecc_limit, min_a, max_a, min_q, max_Q;
+  int enable_outlier_rejection;
+  int free_el[6];
+};
+
+#define OFB_M6(m, r, c) ((m)[6 * (c) + (r)])
+
+// equinoctial_element.rs:258-270
+__device__ __forceinline__ bool lsq_is_bizarre(const double *e, const LsqCfgDev &c) {
+  const double ecc = sqrt(e[1] * e[1] + e[2] * e[2]);
+  const double peri = e[0] * (1.0 - ecc);
+  const double apo = e[0] * (1.0 + ecc);
+  return ecc > c.ecc_limit || e[0] < c.min_a || e[0] > c.max_a || peri < c.min_q || apo > c.max_Q;
+}
+
+// compute_obs_and_partials_2body (observation_ephemeris.rs:418-450): predicted (ra, dec) of the orbit
+// `el` = (epoch, a, h, k, p, q, lambda) at one observation and d(ra, dec)/d(elements).
+// false <=> the reference returns Err (e >= 1, Kepler equation not converged).
+__device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs, V3 obs_equ, double &ra,
+                                                  double &dec, double *d_ra, double *d_dec) {
+  const double epoch = el[0], a = el[1], h = el[2], k = el[3], p = el[4], q = el[5];
+  const double e2 = h * h + k * k;
+  if (sqrt(e2) >= 1.0) return false;  // check_elliptical_orbit
+  // propagate_twobody(0.0, dt, true) (equinoctial_element.rs:809-867)
+  const double t0 = 0.0, t1 = t_obs - epoch;
+  const double n = sqrt(kMu / ((a * a) * a));
+  double lam1 = el[6] + n * (t1 - t0);
+  double lon_peri = 0.0;
+  if (e2 > kEps * 1e2) lon_peri = rem_euclid(atan2(h, k), kTwoPi);
+  lam1 = rem_euclid(lam1, kTwoPi);
+  if (lam1 < lon_peri) lam1 += kTwoPi;
+  // solve_kepler_equation (:326-348; roots 0.0.8 Newton, eps 100 ulp, 25 iterations)
+  const double eps = kEps * 1e2;
+  double F = kPi + lon_peri;
+  int iter = 0;
+  for (;;) {
+    double sx, cx;
+    sincos(F, &sx, &cx);
+    const double f = F - k * sx + h * cx - lam1;
+    const double d = 1.0 - k * cx - h * sx;
+    if (fabs(f) < eps) break;
+    if (fabs(d) < eps) {
+      if (iter == 0) { F = F + 1.0; iter = 1; continue; }
+      return false;
+    }
+    const double x1 = F - f / d;
+    if (fabs(F - x1) < eps) { F = x1; break; }
+    F = x1;
+    if (++iter >= 25) return false;
+  }
+  // compute_cartesian_position_and_velocity (:639-759)
+  const double beta = 1.0 / (1.0 + sqrt(1.0 - e2));
+  const double bhk = beta * h * k;
+  double sF, cF;
+  sincos(F, &sF, &cF);
+  const double xe = a * ((1.0 - beta * (h * h)) * cF + bhk * sF - k);
+  const double ye = a * ((1.0 - beta * (k * k)) * sF + bhk * cF - h);
+  const double u = 1.0 + p * p + q * q;
+  const double inv_u = 1.0 / u;
+  const double common = 2.0 * p * q * inv_u;
+  const V3 fv{(1.0 - p * p + q * q) * inv_u, common, -2.0 * p * inv_u};
+  const V3 gv{common, (1.0 + p * p - q * q) * inv_u, 2.0 * q * inv_u};
+  const V3 pos = xe * fv + ye * gv;
+  const double vconst = n * (a * a) / sqrt(xe * xe + ye * ye);
+  const double vxe = vconst * (bhk * cF - (1.0 - beta * (h * h)) * sF);
+  const double vye = vconst * ((1.0 - beta * (k * k)) * cF - bhk * sF);
+  const V3 vel = vxe * fv + vye * gv;
+  // compute_derivative (:442-637), position block only (the velocity block is unused on this path)
+  const V3 wv{2.0 * p * inv_u, -2.0 * q * inv_u, (1.0 - p * p - q * q) * inv_u};
+  const double r = sqrt(xe * xe + ye * ye);
+  const double inv_r = 1.0 / r;
+  const double inv_1_beta = 1.0 / (1.0 - beta);
+  const double b3 = (beta * beta) * beta;
+  const double tmp1 = lam1 - F;
+  const double tmp2 = beta + (h * h) * b3 * inv_1_beta;
+  const double tmp3 = h * k * b3 * inv_1_beta;
+  const double tmp4 = beta * h - sF;
+  const double tmp5 = beta * k - cF;
+  const double tmp6 = beta + (k * k) * b3 * inv_1_beta;
+  const double dt = t1 - t0;
+  V3 col[6];
+  col[0] = V3{(pos.x - 3.0 * vel.x * dt / 2.0) / a, (pos.y - 3.0 * vel.y * dt / 2.0) / a,
+              (pos.z - 3.0 * vel.z * dt / 2.0) / a};
+  const double dx1de2 = -a * (tmp1 * tmp2 + a * cF * tmp4 * inv_r);
+  const double dx2de2 = a * (tmp1 * tmp3 - 1.0 + a * cF * tmp5 * inv_r);
+  col[1] = dx1de2 * fv + dx2de2 * gv;
+  const double dx1de3 = -a * (tmp1 * tmp3 + 1.0 - a * sF * tmp4 * inv_r);
+  const double dx2de3 = a * (tmp1 * tmp6 - a * sF * tmp5 * inv_r);
+  col[2] = dx1de3 * fv + dx2de3 * gv;
+  {
+    const V3 t = q * (ye * fv - xe * gv) - xe * wv;
+    col[3] = V3{2.0 * t.x * inv_u, 2.0 * t.y * inv_u, 2.0 * t.z * inv_u};
+    const V3 s = p * ((-ye) * fv + xe * gv) + ye * wv;
+    col[4] = V3{2.0 * s.x * inv_u, 2.0 * s.y * inv_u, 2.0 * s.z * inv_u};
+  }
+  col[5] = V3{vel.x / n, vel.y / n, vel.z / n};
+  // topocentric_radec_and_partials (observation_ephemeris.rs:204-258)
+  const V3 ap = ecl_to_equ(pos), av = ecl_to_equ(vel);
+  const V3 rel = ap - obs_equ;
+  const double ltt = norm(rel) / kVlightAu;
+  const V3 cor = rel - ltt * av;
+  const double x = cor.x, y = cor.y, z = cor.z;
+  const double rho = norm(cor);
+  const double rho_xy = hypot(x, y);
+  const double rho_xy_sq = rho_xy * rho_xy;
+  dec = atan2(z, rho_xy);
+  ra = rem_euclid(atan2(y, x), kTwoPi);
+  const double rho_sq = rho * rho;
+  const V3 gra{-y / rho_xy_sq, x / rho_xy_sq, 0.0};
+  const V3 gdec{-z * x / (rho_xy * rho_sq), -z * y / (rho_xy * rho_sq), rho_xy / rho_sq};
+  const double rel_norm = norm(rel);
+  const double aberr = 1.0 / (rel_norm * kVlightAu);
+  const double sra = dot(gra, av) * aberr, sdec = dot(gdec, av) * aberr;
+  const V3 drp = gra - sra * rel;
+  const V3 ddp = gdec - sdec * rel;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const V3 dq = ecl_to_equ(col[j]);
+    d_ra[j] = dot(drp, dq);
+    d_dec[j] = dot(ddp, dq);
+  }
+  return true;
+}
+
+// ecl_to_equ above is (kCos*y - kSin*z, kSin*y + kCos*z); the reference multiplies by the full 3x3
+// matrix, (0*x + c*y) + (-s)*z: the zero products and the sign placement do not change any rounding.
+
+// nalgebra Cholesky::new: in-place lower factor; false <=> not positive definite
+__device__ __noinline__ bool lsq_cholesky6(double *m) {
+  for (int j = 0; j < 6; ++j) {
+    for (int k = 0; k < j; ++k) {
+      const double factor = -OFB_M6(m, j, k);
+      for (int i = j; i < 6; ++i) OFB_M6(m, i, j) = factor * OFB_M6(m, i, k) + OFB_M6(m, i, j);
+    }
+    const double diag = OFB_M6(m, j, j);
+    if (diag == 0.0 || !(diag >= 0.0)) return false;
+    const double denom = sqrt(diag);
+    OFB_M6(m, j, j) = denom;
+    for (int i = j + 1; i < 6; ++i) OFB_M6(m, i, j) = OFB_M6(m, i, j) / denom;
+  }
+  return true;
+}
+// Cholesky::inverse: L then L^T substitution on the identity, column by column
+__device__ __noinline__ void lsq_cholesky6_inverse(const double *l, double *inv) {
+  for (int c = 0; c < 6; ++c) {
+    double b[6] = {0, 0, 0, 0, 0, 0};
+    b[c] = 1.0;
+    for (int i = 0; i < 5; ++i) {
+      const double coeff = b[i] / OFB_M6(l, i, i);
+      b[i] = coeff;
+      for (int r = i + 1; r < 6; ++r) b[r] = -coeff * OFB_M6(l, r, i) + b[r];
+    }
+    b[5] = b[5] / OFB_M6(l, 5, 5);
+    for (int i = 5; i >= 0; --i) {
+      double dot = 0.0;
+      for (int r = i + 1; r < 6; ++r) dot += OFB_M6(l, r, i) * b[r];
+      b[i] = (b[i] - dot) / OFB_M6(l, i, i);
+    }
+    for (int r = 0; r < 6; ++r) OFB_M6(inv, r, c) = b[r];
+  }
+}
+// nalgebra QR::new + try_inverse (Householder, doubly normalised axis); `m` is destroyed
+__device__ __noinline__ bool lsq_qr6_inverse(double *m, double *inv) {
+  double diag[6];
+  for (int ic = 0; ic < 6; ++ic) {
+    double sq = 0.0;
+    for (int r = ic; r < 6; ++r) sq += OFB_M6(m, r, ic) * OFB_M6(m, r, ic);
+    const double nrm = sqrt(sq);
+    const double x0 = OFB_M6(m, ic, ic);
+    const double modulus = x0 >= 0.0 ? x0 : -x0;
+    const double sgn = x0 >= 0.0 ? 1.0 : -1.0;
+    const double signed_norm = sgn * nrm;
+    const double factor = (sq + modulus * nrm) * 2.0;
+    OFB_M6(m, ic, ic) = x0 + signed_norm;
+    if (factor != 0.0) {
+      const double sf = sqrt(factor);
+      for (int r = ic; r < 6; ++r) OFB_M6(m, r, ic) = OFB_M6(m, r, ic) / sf;
+      double n2 = 0.0;
+      for (int r = ic; r < 6; ++r) n2 += OFB_M6(m, r, ic) * OFB_M6(m, r, ic);
+      const double nn = sqrt(n2);
+      for (int r = ic; r < 6; ++r) OFB_M6(m, r, ic) = OFB_M6(m, r, ic) / nn;
+      const double rn = -signed_norm;
+      diag[ic] = rn;
+      const double sign = signbit(rn) ? -1.0 : 1.0;
+      const double m_two = sign * -2.0;
+      for (int c = ic + 1; c < 6; ++c) {
+        double dot = 0.0;
+        for (int r = ic; r < 6; ++r) dot += OFB_M6(m, r, ic) * OFB_M6(m, r, c);
+        const double fac = (dot - 0.0) * m_two;
+        for (int r = ic; r < 6; ++r) OFB_M6(m, r, c) = fac * OFB_M6(m, r, ic) + sign * OFB_M6(m, r, c);
+      }
+    } else {
+      diag[ic] = signed_norm;
+    }
+  }
+  for (int c = 0; c < 6; ++c) {
+    double b[6] = {0, 0, 0, 0, 0, 0};
+    b[c] = 1.0;
+    for (int i = 0; i < 6; ++i) {
+      const double sign = signbit(diag[i]) ? -1.0 : 1.0;
+      double dot = 0.0;
+      for (int r = i; r < 6; ++r) dot += OFB_M6(m, r, i) * b[r];
+      const double fac = (dot - 0.0) * (sign * -2.0);
+      for (int r = i; r < 6; ++r) b[r] = fac * OFB_M6(m, r, i) + sign * b[r];
+    }
+    for (int i = 5; i >= 0; --i) {
+      const double d = fabs(diag[i]);
+      if (d == 0.0) return false;
+      const double coeff = b[i] / d;
+      b[i] = coeff;
+      for (int r = 0; r < i; ++r) b[r] = -coeff * OFB_M6(m, r, i) + b[r];
+    }
+    for (int r = 0; r < 6; ++r) OFB_M6(inv, r, c) = b[r];
+  }
+  return true;
+}
+// least_square.rs:329-342 ; `work` is a 36-double temporary
+__device__ __forceinline__ bool lsq_invert_normal_matrix(const double *m, double *inv, double *work) {
+  for (int i = 0; i < 36; ++i) work[i] = m[i];
+  if (lsq_cholesky6(work)) { lsq_cholesky6_inverse(work, inv); return true; }
+  for (int i = 0; i < 36; ++i) work[i] = m[i];
+  if (lsq_qr6_inverse(work, inv)) return true;
+  for (int i = 0; i < 36; ++i) inv[i] = 0.0;
+  return false;
+}
+__device__ __forceinline__ void lsq_gemv6(const double *m, const double *v, double *out) {
+  for (int r = 0; r < 6; ++r) out[r] = OFB_M6(m, r, 0) * v[0];
+  for (int c = 1; c < 6; ++c)
+    for (int r = 0; r < 6; ++r) out[r] = OFB_M6(m, r, c) * v[c] + out[r];
+}
+__device__ __forceinline__ double lsq_dot6(const double *a, const double *b) {
+  double res = 0.0;
+  for (int i = 0; i < 6; ++i) res += a[i] * b[i];
+  return res;
+}
+// least_square.rs:188-199
+__device__ __forceinline__ double lsq_angular_diff(double a, double b) {
+  double d = a - b;
+  while (d > kPi) d -= kTwoPi;
+  while (d < -kPi) d += kTwoPi;
+  return d;
+}
+
+}  // namespace ofb

@@ -25,6 +25,7 @@
 #include "dev_geometry.cuh"
 #include "dev_ephemeris.cuh"
 #include "dev_rng.cuh"
+#include "dev_lsq.cuh"
 
 using namespace ofb;
 
@@ -577,6 +578,202 @@ propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double
 #pragma unroll
   for (int q = 0; q < 11; ++q) out[(size_t)q * n + i] = o[q];
   status[i] = stt;
+}
+
+// =================================================================================================
+// differential orbit correction (FitLSQ), one thread per trajectory: dev_lsq.cuh
+// =================================================================================================
+struct LsqBatchDev {
+  unsigned long long n_traj, n_obs;
+  const unsigned long long *traj_offset;
+  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
+  const double *scorer;  // [3][n_obs] observer position, equatorial J2000 (scorer_observer_kernel)
+};
+
+__global__ void __launch_bounds__(64)
+lsq_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ iod, OutfitLsqResult *__restrict__ out,
+           OutfitObsFit *__restrict__ fit, double *__restrict__ tmp) {
+  const unsigned long long tr = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tr >= B.n_traj) return;
+  const unsigned long long o0 = B.traj_offset[tr];
+  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
+  OutfitLsqResult *res = out + tr;
+  OutfitObsFit *F = fit + o0;
+  double *t_rra = tmp + o0, *t_rdec = tmp + B.n_obs + o0, *t_chi = tmp + 2 * B.n_obs + o0;
+  for (unsigned i = 0; i < n_obs; ++i) {  // ObsFitData::new (obs_fit_data.rs:105-116)
+    F[i].residual_ra = 0.0; F[i].residual_dec = 0.0; F[i].chi = 0.0; F[i].selection = 0; F[i]._pad0 = 0;
+  }
+  {  // zero the record (matrices, sigma, counters)
+    double *z = reinterpret_cast<double *>(res);
+    for (unsigned i = 0; i < sizeof(OutfitLsqResult) / 8; ++i) z[i] = 0.0;
+  }
+  const OutfitIodResult I = iod[tr];
+  if (I.status != OUTFIT_ST_OK) { res->status = I.status; res->kind = OUTFIT_LSQ_NONE; return; }
+  double el[7];
+  {
+    Orbit orb;
+    orb.kind = I.element_kind; orb.corrected = I.corrected; orb.epoch = I.epoch;
+    for (int j = 0; j < 6; ++j) orb.e[j] = I.elem[j];
+    Equinoctial q;
+    const int rq = to_equinoctial(orb, q);
+    if (rq != 0) { res->status = rq; res->kind = OUTFIT_LSQ_NONE; return; }
+    el[0] = q.epoch; el[1] = q.a; el[2] = q.h; el[3] = q.k; el[4] = q.p; el[5] = q.q; el[6] = q.lambda;
+  }
+  unsigned num_free = 0;
+  for (int j = 0; j < 6; ++j) num_free += C.free_el[j] ? 1u : 0u;
+  double el_lin[7];  // the elements the last accepted step was linearised at (stands in for last_equations)
+  bool have_lin = false;
+  double nm[36], cov[36], work[36], last_nm[36], last_cov[36];
+  for (int i = 0; i < 36; ++i) { last_nm[i] = 0.0; last_cov[i] = 0.0; }
+  const double kMax = 1.7976931348623157e308;
+  double last_rms = kMax;
+  unsigned long long last_nmeas = 0, total_it = 0;
+  int fail_code = 0;
+  // run_differential_correction (diff_cor.rs:282-442)
+  for (unsigned long long outer = 0; outer <= C.max_outlier_rejection_passes && !fail_code; ++outer) {
+    double prev_rms = kMax;
+    unsigned long long stagnation = 0;
+    bool converged = false;
+    have_lin = false;
+    for (unsigned long long inner = 0; inner < C.max_newton_iterations; ++inner) {
+      ++total_it;
+      // single_iteration (single_iteration.rs:140-317) + solve_weighted_least_squares (least_square.rs:225-327)
+      for (int i = 0; i < 36; ++i) nm[i] = 0.0;
+      double rhs[6] = {0, 0, 0, 0, 0, 0};
+      double qsum = 0.0;
+      unsigned long long active = 0;
+      for (unsigned i = 0; i < n_obs; ++i) {
+        const unsigned long long gI = o0 + i;
+        t_rra[i] = F[i].residual_ra; t_rdec[i] = F[i].residual_dec; t_chi[i] = F[i].chi;
+        if (F[i].selection != 0) continue;
+        double ra, dec, pr[6], pd[6];
+        const V3 obs{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)};
+        if (!lsq_obs_and_partials(el, __ldg(B.mjd_tt + gI), obs, ra, dec, pr, pd)) continue;
+        const double sra = __ldg(B.sigma_ra + gI), sdec = __ldg(B.sigma_dec + gI);
+        const double xr = lsq_angular_diff(__ldg(B.ra + gI) - 0.0, ra);
+        const double xd = (__ldg(B.dec + gI) - 0.0) - dec;
+        const double ca = xr / sra, cd = xd / sdec;
+        t_rra[i] = xr; t_rdec[i] = xd; t_chi[i] = sqrt(ca * ca + cd * cd);
+        const double wr = 1.0 / (sra * sra), wd = 1.0 / (sdec * sdec), wc = 0.0;
+        ++active;
+        for (int j = 0; j < 6; ++j) {
+          for (int k = 0; k < 6; ++k)
+            OFB_M6(nm, j, k) += pr[j] * wr * pr[k] + pd[j] * wd * pd[k] + wc * (pd[j] * pr[k] + pr[j] * pd[k]);
+          rhs[j] += (pr[j] * wr + pd[j] * wc) * xr + (pr[j] * wc + pd[j] * wd) * xd;
+        }
+        qsum += wr * xr * xr + wd * xd * xd + 2.0 * wc * xr * xd;
+      }
+      const unsigned long long nmeas = 2 * active;
+      for (int j = 0; j < 6; ++j)
+        if (!C.free_el[j]) {
+          for (int k = 0; k < 6; ++k) { OFB_M6(nm, j, k) = 0.0; OFB_M6(nm, k, j) = 0.0; }
+          OFB_M6(nm, j, j) = 1.0;
+          rhs[j] = 0.0;
+        }
+      const bool inv_ok = lsq_invert_normal_matrix(nm, cov, work);
+      double dx[6] = {0, 0, 0, 0, 0, 0};
+      if (inv_ok) lsq_gemv6(cov, rhs, dx);
+      for (int j = 0; j < 6; ++j)
+        if (!C.free_el[j]) dx[j] = 0.0;
+      const double new_rms = nmeas > 0 ? sqrt(qsum / (double)nmeas) : 0.0;
+      double cdx[6];
+      lsq_gemv6(nm, dx, cdx);
+      const double cnorm = sqrt(lsq_dot6(dx, cdx));
+      double corrected[6];
+      for (int j = 0; j < 6; ++j) corrected[j] = C.free_el[j] ? el[1 + j] + dx[j] : el[1 + j];
+      if (!inv_ok) { fail_code = OUTFIT_ST_LSQ_INVERSION; break; }
+      if (lsq_is_bizarre(corrected, C)) { fail_code = OUTFIT_ST_LSQ_BIZARRE; break; }
+      if (prev_rms < kMax && new_rms / prev_rms >= C.rms_divergence_ratio) { fail_code = OUTFIT_ST_LSQ_DIVERGED; break; }
+      const bool stagnated = prev_rms < kMax && new_rms / prev_rms >= C.rms_stagnation_ratio;
+      if (stagnated) {
+        if (++stagnation >= C.max_stagnation_iterations) break;
+      } else {
+        stagnation = 0;
+      }
+      // advance the state
+      for (int j = 0; j < 7; ++j) el_lin[j] = el[j];
+      have_lin = true;
+      for (int i = 0; i < 36; ++i) { last_nm[i] = nm[i]; last_cov[i] = cov[i]; }
+      last_rms = new_rms;
+      last_nmeas = nmeas;
+      for (int j = 0; j < 6; ++j) el[1 + j] = corrected[j];
+      for (unsigned i = 0; i < n_obs; ++i) { F[i].residual_ra = t_rra[i]; F[i].residual_dec = t_rdec[i]; F[i].chi = t_chi[i]; }
+      prev_rms = new_rms;
+      if (cnorm < C.convergence_threshold) { converged = true; break; }
+    }
+    if (fail_code) break;
+    if (!C.enable_outlier_rejection) break;
+    if (outer == 0 && last_rms < C.convergence_before_rejection_threshold) break;
+    if (!converged || !have_lin) break;
+    // update_observation_selection (outlier_rejection.rs:118-235); the equations of the last accepted
+    // step are re-evaluated at el_lin (bit-identical to the values that step used)
+    unsigned long long changes = 0;
+    for (unsigned i = 0; i < n_obs; ++i) {
+      const unsigned long long gI = o0 + i;
+      const int sel = F[i].selection;
+      if (sel == 2) continue;
+      double pr[6] = {0, 0, 0, 0, 0, 0}, pd[6] = {0, 0, 0, 0, 0, 0};
+      double wr = 1.0, wd = 1.0;
+      const double sra = __ldg(B.sigma_ra + gI), sdec = __ldg(B.sigma_dec + gI);
+      if (sel == 0) {
+        double ra, dec;
+        const V3 obs{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)};
+        if (lsq_obs_and_partials(el_lin, __ldg(B.mjd_tt + gI), obs, ra, dec, pr, pd)) {
+          wr = 1.0 / (sra * sra); wd = 1.0 / (sdec * sdec);
+        } else {
+          for (int j = 0; j < 6; ++j) { pr[j] = 0.0; pd[j] = 0.0; }
+        }
+      }
+      const double var_ra = sra * sra, var_dec = sdec * sdec;
+      const double cov_cross = -sra * sdec * 0.0 / (wr * wd);
+      double gga[6], ggd[6];
+      lsq_gemv6(last_cov, pr, gga);
+      lsq_gemv6(last_cov, pd, ggd);
+      const double paa = lsq_dot6(pr, gga), pdd = lsq_dot6(pd, ggd), pad = lsq_dot6(pr, ggd);
+      const double v00 = var_ra - paa, v01 = cov_cross - pad, v11 = var_dec - pdd;
+      const double det = v00 * v11 - v01 * v01;
+      const double scale = fmax(fabs(v00), fabs(v11));
+      if (fabs(det) < kEps * scale * scale || scale == 0.0) continue;
+      const double i00 = v11 / det, i01 = -v01 / det, i10 = -v01 / det, i11 = v00 / det;
+      const double rr = F[i].residual_ra, rd = F[i].residual_dec;
+      double y0 = i00 * rr, y1 = i10 * rr;
+      y0 = i01 * rd + y0;
+      y1 = i11 * rd + y1;
+      const double chi2 = rr * y0 + rd * y1;
+      if (sel == 0 && chi2 > C.chi2_reject) { F[i].selection = 1; ++changes; }
+      else if (sel == 1 && chi2 <= C.chi2_recover) { F[i].selection = 0; ++changes; }
+    }
+    if (changes == 0) break;
+  }
+  res->status = OUTFIT_ST_OK;
+  res->total_newton_iterations = total_it;
+  if (fail_code) {  // Err(_) => Ok(initial_orbit) (mod.rs:113)
+    res->kind = OUTFIT_LSQ_IOD_FALLBACK;
+    res->fallback_cause = fail_code;
+    res->epoch = I.epoch;
+    for (int j = 0; j < 6; ++j) res->elem[j] = I.elem[j];
+    res->normalised_rms = I.rms;
+    for (unsigned i = 0; i < n_obs; ++i) { F[i].residual_ra = 0.0; F[i].residual_dec = 0.0; F[i].chi = 0.0; F[i].selection = 0; }
+    return;
+  }
+  // rescale_covariance (least_square.rs:371-394)
+  double mu = 1.0;
+  if (num_free < last_nmeas) {
+    const double factor = sqrt((double)last_nmeas / (double)(last_nmeas - num_free));
+    mu = last_rms > 1.0 ? last_rms * factor : factor;
+  }
+  const double mu2 = mu * mu;
+  res->kind = OUTFIT_LSQ_CORRECTED;
+  res->epoch = el[0];
+  for (int j = 0; j < 6; ++j) res->elem[j] = el[1 + j];
+  for (int i = 0; i < 36; ++i) {
+    const double cv = last_cov[i] * mu2;
+    res->covariance[i] = cv;
+    res->normal_matrix[i] = last_nm[i] / mu2;
+  }
+  for (int j = 0; j < 6; ++j) res->sigma[j] = sqrt(last_cov[7 * j] * mu2);
+  res->normalised_rms = last_rms;
+  res->num_measurements = last_nmeas;
 }
 
 // =================================================================================================
@@ -1170,6 +1367,152 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
   } else {
     cudaStreamSynchronize(cs);
   }
+  return rc;
+}
+
+extern "C" void outfit_b200_lsq_config_default(OutfitLsqConfig *c) {  // diff_cor.rs:175-192
+  if (!c) return;
+  memset(c, 0, sizeof *c);
+  c->max_newton_iterations = 30;
+  c->max_outlier_rejection_passes = 10;
+  c->convergence_threshold = 1e-4;
+  c->convergence_before_rejection_threshold = 2.0;
+  c->rms_stagnation_ratio = 0.98;
+  c->rms_divergence_ratio = 1.5;
+  c->max_stagnation_iterations = 3;
+  c->enable_outlier_rejection = 1;
+  c->chi2_rejection_threshold = 25.0;
+  c->chi2_recovery_threshold = 9.0;
+  c->eccentricity_limit = 1.2;
+  c->min_semi_major_axis = 1e-6;
+  c->max_semi_major_axis = 1e4;
+  c->min_periapsis_distance = 1e-6;
+  c->max_apoapsis_distance = 1e4;
+  for (int j = 0; j < 6; ++j) c->free_elements[j] = 1;
+}
+
+static LsqCfgDev to_lsq_dev(const OutfitLsqConfig &c) {
+  LsqCfgDev d;
+  d.max_newton_iterations = c.max_newton_iterations;
+  d.max_outlier_rejection_passes = c.max_outlier_rejection_passes;
+  d.max_stagnation_iterations = c.max_stagnation_iterations;
+  d.convergence_threshold = c.convergence_threshold;
+  d.convergence_before_rejection_threshold = c.convergence_before_rejection_threshold;
+  d.rms_stagnation_ratio = c.rms_stagnation_ratio;
+  d.rms_divergence_ratio = c.rms_divergence_ratio;
+  d.chi2_reject = c.chi2_rejection_threshold;
+  d.chi2_recover = c.chi2_recovery_threshold;
+  d.ecc_limit = c.eccentricity_limit;
+  d.min_a = c.min_semi_major_axis; d.max_a = c.max_semi_major_axis;
+  d.min_q = c.min_periapsis_distance; d.max_Q = c.max_apoapsis_distance;
+  d.enable_outlier_rejection = c.enable_outlier_rejection;
+  for (int j = 0; j < 6; ++j) d.free_el[j] = c.free_elements[j];
+  return d;
+}
+
+extern "C" int outfit_b200_fit_lsq_device(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitObsBatch *b,
+                                          const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit,
+                                          void *cuda_stream) {
+  if (!ctx || !cfg || !b) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (b->n_traj && (!iod || !out || !fit)) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq: iod, out and fit are required");
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const size_t n = b->n_obs;
+  if (b->n_traj == 0) return OUTFIT_OK;
+  const bool have_geo = b->obs_geo_ecl != nullptr;
+  const bool have_bf = b->observer_body_fixed && b->mjd_ut1;
+  if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  // scratch: scorer[3][n] + tentative residuals[3][n] (+ geo[3][n] + helio[3][n] from pvobs) + status[n]
+  const size_t planes = have_geo ? 6 : 12;
+  int rc = ensure_scratch(ctx, planes * n * sizeof(double) + n * sizeof(int) + 256);
+  if (rc) return rc;
+  double *d_scorer = reinterpret_cast<double *>(ctx->scratch);
+  double *d_tmp = d_scorer + 3 * n;
+  int *d_status = reinterpret_cast<int *>(d_scorer + planes * n);
+  const double *d_geo = b->obs_geo_ecl;
+  const int tpb = 128;
+  const unsigned gblocks = (unsigned)((n + tpb - 1) / tpb);
+  if (!have_geo) {
+    double *geo = d_scorer + 6 * n, *helio = d_scorer + 9 * n;
+    if (n) observer_cache_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, b->mjd_ut1, b->observer_body_fixed, geo, helio, d_status);
+    d_geo = geo;
+  }
+  if (n) scorer_observer_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, d_geo, d_scorer, d_status);
+  LsqBatchDev B;
+  B.n_traj = b->n_traj; B.n_obs = n; B.traj_offset = (const unsigned long long *)b->traj_offset;
+  B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
+  B.scorer = d_scorer;
+  const unsigned lblocks = (unsigned)((b->n_traj + 63) / 64);
+  lsq_kernel<<<lblocks, 64, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
+                                   const OutfitObsBatch *hb, const OutfitIodResult *iod, OutfitLsqResult *out,
+                                   OutfitObsFit *fit) {
+  if (!ctx || !cfg || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (!iod && !iod_params) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq: iod results or iod_params are required");
+  const size_t T = hb->n_traj, n = hb->n_obs;
+  if (T == 0) return OUTFIT_OK;
+  if (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec)
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  std::vector<OutfitIodResult> own_iod;
+  if (!iod) {  // initial_orbits = None: run the IOD first (mod.rs:80)
+    own_iod.resize(T);
+    const int rc = outfit_b200_fit_full_iod(ctx, iod_params, hb, own_iod.data());
+    if (rc) return rc;
+    iod = own_iod.data();
+  }
+  CK(cudaSetDevice(ctx->device));
+  const bool have_geo = hb->obs_geo_ecl != nullptr;
+  const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
+  if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+  cudaStream_t stream = ctx->compute_stream;
+  const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_geo ? 3 : 4) * n * 8 + T * sizeof(OutfitIodResult) +
+                       T * sizeof(OutfitLsqResult) + n * sizeof(OutfitObsFit) + 16 * 256;
+  unsigned char *arena = nullptr;
+  if (cudaMalloc(&arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(fit_lsq arena)");
+  size_t off = 0;
+  auto put = [&](const void *src, size_t nbytes) -> void * {
+    void *dst = arena + off;
+    off += (nbytes + 255) & ~(size_t)255;
+    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream);
+    return dst;
+  };
+  OutfitObsBatch db = *hb;
+  db.traj_offset = (const uint64_t *)put(hb->traj_offset, (T + 1) * 8);
+  db.mjd_tt = (const double *)put(hb->mjd_tt, n * 8);
+  db.ra = (const double *)put(hb->ra, n * 8);
+  db.dec = (const double *)put(hb->dec, n * 8);
+  db.sigma_ra = (const double *)put(hb->sigma_ra, n * 8);
+  db.sigma_dec = (const double *)put(hb->sigma_dec, n * 8);
+  db.obs_helio_equ = nullptr; db.noise_z = nullptr; db.traj_seed = nullptr;
+  if (have_geo) {
+    db.obs_geo_ecl = (const double *)put(hb->obs_geo_ecl, 3 * n * 8);
+    db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
+  } else {
+    db.obs_geo_ecl = nullptr;
+    db.observer_body_fixed = (const double *)put(hb->observer_body_fixed, 3 * n * 8);
+    db.mjd_ut1 = (const double *)put(hb->mjd_ut1, n * 8);
+  }
+  const OutfitIodResult *d_iod = (const OutfitIodResult *)put(iod, T * sizeof(OutfitIodResult));
+  OutfitLsqResult *d_out = (OutfitLsqResult *)put(nullptr, T * sizeof(OutfitLsqResult));
+  OutfitObsFit *d_fit = (OutfitObsFit *)put(nullptr, n * sizeof(OutfitObsFit));
+  int rc = outfit_b200_fit_lsq_device(ctx, cfg, &db, d_iod, d_out, d_fit, stream);
+  if (rc == OUTFIT_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitLsqResult), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && fit) e = cudaMemcpyAsync(fit, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "fit_lsq: copy back / kernel", e);
+  } else {
+    cudaStreamSynchronize(stream);
+  }
+  cudaFree(arena);
   return rc;
 }
 
