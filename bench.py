@@ -382,6 +382,48 @@ def main():
             eph["cpu_sample"] = f"{ns} orbits x {n_ep} epochs, oracle on all {cores} host threads (observer state re-evaluated per entry like the reference)"
         del d_eo, d_es
 
+
+    # FitLSQ leg: differential correction of the batch's IOD orbits, device-resident
+    lsq = None
+    if not args.no_kepler:
+        from outfit_b200 import DifferentialCorrectionConfig, LSQ_RESULT_DTYPE, OBS_FIT_DTYPE
+        lcfg = DifferentialCorrectionConfig.default()
+        n_all = int(batch["mjd_tt"].shape[0])
+        d_lo = torch.zeros(T * LSQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        d_lf = torch.zeros(n_all * OBS_FIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        ctx.fit_full_iod_device(devb, params, d_out, stream=stream)  # initial orbits = this batch's IOD results
+        for _ in range(3):
+            ctx.fit_lsq_device(devb, lcfg, d_out, d_lo, d_lf, stream=stream)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(5):
+            ctx.fit_lsq_device(devb, lcfg, d_out, d_lo, d_lf, stream=stream)
+        l1.record()
+        torch.cuda.synchronize()
+        lms = l0.elapsed_time(l1) / 5
+        launches += 8 * 2 + per_step_launches + 2  # 8 device calls + the IOD call + the host-entry call
+        lres = d_lo.cpu().numpy().view(LSQ_RESULT_DTYPE).reshape(-1)
+        t0 = time.perf_counter()
+        lhost, _ = ctx.fit_lsq(host_batch, params, lcfg, initial_orbits=d_out.cpu().numpy().view(RESULT_DTYPE).reshape(-1))
+        lhost_s = time.perf_counter() - t0
+        n_it = int(lres["total_newton_iterations"].sum())
+        lsq = {"trajectories_per_s": T / (lms * 1e-3), "ms": lms, "host_entry_trajectories_per_s": T / lhost_s,
+               "host_entry_ms": lhost_s * 1e3, "host_equals_device": bool(lhost.tobytes() == lres.tobytes()),
+               "corrected_fraction": float((lres["kind"] == 1).mean()), "iod_fallback_fraction": float((lres["kind"] == 2).mean()),
+               "newton_iterations": n_it, "observation_equations_per_s": n_it * (n_all / T) / (lms * 1e-3),
+               "workload": "differential correction (two-body, default DifferentialCorrectionConfig) of the same batch from its IOD orbits; one thread per trajectory"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import binding as O
+            et_ = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+            ob_ = O.from_soa_batch(batch)
+            io_ = np.ascontiguousarray(d_out.cpu().numpy().view(O.IOD_RESULT_DTYPE).reshape(-1))
+            t0 = time.perf_counter()
+            O.fit_lsq(ob_, et_, O.default_lsq_config(), io_, n_threads=0)
+            lsq["cpu_trajectories_per_s"] = T / (time.perf_counter() - t0)
+            lsq["cpu_sample"] = f"the whole batch ({T} trajectories), oracle on all {cores} host threads"
+        del d_lo, d_lf
+
     # max over ranks
     tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms, e2e_seeded_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -444,6 +486,7 @@ def main():
             "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (ms * 1e-3),
                        "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
             "ephemeris": eph,
+            "lsq": lsq,
             "counters": counters,
             "selected_ok_fraction": float((res_host["status"] == 0).mean()),
         }
