@@ -4,6 +4,7 @@
 // Mirrors (names, argument meaning, error behaviour; /root/reference/src):
 //   IODParams / IODParamsBuilder::build     initial_orbit_determination/mod.rs:225-344, 360-624
 //   FitIOD::fit_full_iod on an ObsDataset   initial_orbit_determination/obs_dataset_api.rs:145-207
+//   FitLSQ::fit_lsq on an ObsDataset        differential_orbit_correction/obs_dataset_api.rs:113-190
 //   FitOrbitResult / GaussResult            constants.rs:134-175, gauss_result.rs:99-102
 //   kepler::propagate_universal             kepler/propagation.rs:114-174
 //   OrbitalElements::compute::<Combined>    ephemeris/mod.rs:189-292
@@ -132,6 +133,22 @@ struct FitOrbitResult {
   uint32_t realization;
 };
 
+// FitOrbitResult::DifferentialCorrection((OrbitalElements::Equinoctial{elements, uncertainty, covariance}, rms))
+// (differential_orbit_correction/mod.rs:60-115), or -- when the loop failed -- the IOD orbit it started from
+struct LsqOrbitResult {
+  bool ok;                 // an orbit is present (corrected or IOD fallback)
+  bool corrected;          // true: DifferentialCorrection; false with ok: the IOD orbit was returned (mod.rs:113)
+  int error;               // !ok: the IOD / conversion error (OUTFIT_ST_*)
+  int fallback_cause;      // ok && !corrected: OUTFIT_ST_LSQ_INVERSION | LSQ_BIZARRE | LSQ_DIVERGED
+  double reference_epoch;
+  double elem[6];          // corrected: equinoctial (a, h, k, p, q, lambda)
+  double sigma[6];         // EquinoctialUncertainty
+  double covariance[36];   // column-major 6x6
+  double normal_matrix[36];
+  double normalised_rms;
+  uint64_t total_newton_iterations, num_measurements;
+};
+
 class Context {
  public:
   explicit Context(int device = -1) {
@@ -168,6 +185,38 @@ class Context {
       f.realization = r.realization;
     }
     return out;
+  }
+
+  // FitLSQ::fit_lsq (differential_orbit_correction/obs_dataset_api.rs:113-190): `initial_orbits` = the raw IOD
+  // records of the same batch, or nullptr to run the IOD first with `params`.  fit (optional): per-observation
+  // residuals / chi / selection flags after the fit.
+  std::vector<LsqOrbitResult> fit_lsq(const OutfitObsBatch &batch, const OutfitIodParams &params,
+                                      const OutfitLsqConfig &cfg, const OutfitIodResult *initial_orbits = nullptr,
+                                      std::vector<OutfitObsFit> *fit = nullptr) {
+    std::vector<OutfitLsqResult> raw(batch.n_traj);
+    if (fit) fit->resize(batch.n_obs);
+    check(outfit_b200_fit_lsq(h_, &params, &cfg, &batch, initial_orbits, raw.data(), fit ? fit->data() : nullptr));
+    std::vector<LsqOrbitResult> out(raw.size());
+    for (size_t t = 0; t < raw.size(); ++t) {
+      const OutfitLsqResult &r = raw[t];
+      LsqOrbitResult &f = out[t];
+      f.ok = r.kind != OUTFIT_LSQ_NONE;
+      f.corrected = r.kind == OUTFIT_LSQ_CORRECTED;
+      f.error = r.status; f.fallback_cause = r.fallback_cause;
+      f.reference_epoch = r.epoch;
+      std::memcpy(f.elem, r.elem, sizeof r.elem);
+      std::memcpy(f.sigma, r.sigma, sizeof r.sigma);
+      std::memcpy(f.covariance, r.covariance, sizeof r.covariance);
+      std::memcpy(f.normal_matrix, r.normal_matrix, sizeof r.normal_matrix);
+      f.normalised_rms = r.normalised_rms;
+      f.total_newton_iterations = r.total_newton_iterations; f.num_measurements = r.num_measurements;
+    }
+    return out;
+  }
+  static OutfitLsqConfig default_lsq_config() {  // DifferentialCorrectionConfig::default()
+    OutfitLsqConfig c;
+    outfit_b200_lsq_config_default(&c);
+    return c;
   }
 
   // kepler::propagate_universal over n states: rv [6][n], out [11][n] (r1, v1, f, g, fdot, gdot, psi)

@@ -11,8 +11,11 @@ int main() {
   b.add_trajectory(tr);
   OutfitObsBatch ob = b.finish();
   bool sorted = ob.mjd_tt[0] < ob.mjd_tt[1] && ob.mjd_tt[1] < ob.mjd_tt[2] && ob.n_traj == 1 && ob.n_obs == 3 && ob.max_obs_per_traj == 3;
+  OutfitLsqConfig lc = Context::default_lsq_config();
+  bool lsq_default = lc.max_newton_iterations == 30 && lc.max_outlier_rejection_passes == 10 && lc.free_elements[5] == 1 &&
+                     lc.chi2_rejection_threshold == 25.0 && sizeof(OutfitLsqResult) == 8 * 90 && sizeof(OutfitObsFit) == 32;
   bool nodev = false;
   try { Context c(0); } catch (const Error &e) { nodev = e.code == OUTFIT_E_NO_DEVICE; }
   std::printf("params=%u threw=%d sorted=%d nodev_or_ok=%d\n", p.max_triplets, (int)threw, (int)sorted, (int)nodev);
-  return (threw && sorted) ? 0 : 1;
+  return (threw && sorted && lsq_default) ? 0 : 1;
 }

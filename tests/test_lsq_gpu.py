@@ -96,7 +96,8 @@ def test_lsq_tight_limits_and_iteration_caps(env):
     # max_newton_iterations = 1: one step, no convergence test passed unless the step is already tiny
     _, ob, _, got, gfit, want, wfit, fl, un = run_both(env, 600, 12, seed=305, max_newton_iterations=1,
                                                        eccentricity_limit=0.3, rms_divergence_ratio=1.05)
-    st = assert_lsq_parity(got, want, gfit, wfit, ob, fl, un, sigma_tol=1e-6)
+    # (max_outlier_fraction: the ~1.5 % of starts with absurd residuals -- IOD rms ~1e5 -- take one chaotic step)
+    st = assert_lsq_parity(got, want, gfit, wfit, ob, fl, un, sigma_tol=1e-6, max_outlier_fraction=0.03)
     assert (want["fallback_cause"] == 19).any()  # BizarreOrbit through the eccentricity limit
     assert got["total_newton_iterations"].max() <= 1, st
 
@@ -110,13 +111,28 @@ def test_lsq_without_initial_orbits_runs_the_iod_first(env):
     a, afit = env["ctx"].fit_lsq(batch, p, cfg, initial_orbits=iod)
     b, bfit = env["ctx"].fit_lsq(batch, p, cfg)
     assert a.tobytes() == b.tobytes() and afit.tobytes() == bfit.tobytes()
-    c, cfit = env["ctx"].fit_lsq(batch, p, cfg, use_body_fixed=True)  # observer geometry from pvobs on the device
-    # (the batch's cached observer positions come from the synthetic generator's numpy arithmetic, pvobs from
-    # the device: ~1e-12 AU apart, so the IOD picks and the fallbacks may differ on a few per cent)
-    same = (a["kind"] == c["kind"]) & (a["total_newton_iterations"] == c["total_newton_iterations"])
-    assert same.mean() > 0.85 and (c["kind"] == 1).sum() > 500
-    ok = same & (a["kind"] == 1)
-    assert np.median(np.abs(a["elem"][ok] - c["elem"][ok]).max(axis=1)) < 1e-7
+
+
+def test_lsq_with_on_device_observer_geometry(env):
+    """Body-fixed observer coordinates + UT1 (pvobs on the device) instead of a precomputed cache: parity with
+    the oracle fed by the oracle's own pvobs / Earth positions, from the same initial orbits."""
+    from outfit_b200 import DifferentialCorrectionConfig, IODParams
+    from parity_util import oracle_observer_cache
+    O = env["O"]
+    batch = env["synth"].make_trajectories(500, 12, seed=309, table=env["table"], max_triplets=10, n_noise=1)
+    p = IODParams.builder(n_noise_realizations=0, max_triplets=10)
+    cfg = DifferentialCorrectionConfig.default()
+    iod = env["ctx"].fit_full_iod(batch, p, use_body_fixed=True)
+    got, gfit = env["ctx"].fit_lsq(batch, p, cfg, initial_orbits=iod, use_body_fixed=True)
+    hel, geo = oracle_observer_cache(O, env["et"], batch)
+    ob = O.from_soa_batch(batch)
+    ob["helio_equ"], ob["geo_ecl"] = hel, geo
+    ocfg = O.default_lsq_config()
+    oiod = np.ascontiguousarray(iod.view(O.IOD_RESULT_DTYPE))
+    want, wfit = O.fit_lsq(ob, env["et"], ocfg, oiod, n_threads=0)
+    fl, un = oracle_lsq_floor(O, ob, env["et"], ocfg, oiod, want, wfit)
+    st = assert_lsq_parity(got, want, gfit, wfit, ob, fl, un)
+    assert st["n_corrected"] > 150, st
 
 
 def test_lsq_device_entry_matches_host_entry(env):
