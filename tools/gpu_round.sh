@@ -13,3 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 OUTFIT_B200_STREAMS=1 PERF_T=30000 PERF_PARITY=0 ncu --set full --clock-control none --import-source on -k regex:'roots_kernel|correct_kernel|score_kernel' \
     --launch-skip 3 -c 3 -o gpurun_out/${TAG}_phases -f python tools/gpu_perf.py > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+ncu --set full --clock-control none --import-source on -k regex:'lsq_kernel' --launch-skip 1 -c 1 \
+    -o gpurun_out/${TAG}_lsq -f python tools/gpu_perf_lsq.py 30000 > gpurun_out/${TAG}_ncu_lsq.log 2>&1; echo "ncu lsq rc=$?"
+fi
