@@ -104,9 +104,11 @@ def body_fixed_position(obscode):
     return np.array([ERAU * rc * math.cos(lon), ERAU * rc * math.sin(lon), ERAU * rs])
 
 
-def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0):
+def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0, ut1_table=None):
     """{id: [record, ...]} -> (ids, batch): the body-fixed flavour of OutfitObsBatch.  Each trajectory is
-    sorted by TT epoch (obs_dataset_api.rs:222-223); UT1 = UTC + dut1_s."""
+    sorted by TT epoch (obs_dataset_api.rs:222-223); UT1 = UTC + dut1_s, or -- with a `ut1.Ut1Table`
+    read from JPL's latest_eop2.long -- what `epoch.to_ut1(provider).to_mjd_tai_days()` gives
+    (observer_extension.rs:191-192)."""
     ids = list(trajectories)
     rows = []
     offs = [0]
@@ -126,4 +128,6 @@ def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0):
         else np.zeros((3, 0)),
         "noise_z": None,
     }
+    if ut1_table is not None and n:
+        batch["mjd_ut1"] = ut1_table.mjd_ut1(batch["mjd_tt"])
     return ids, batch
