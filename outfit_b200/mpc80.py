@@ -128,6 +128,9 @@ def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0, ut1_table=None):
         else np.zeros((3, 0)),
         "noise_z": None,
     }
+    for i, r in enumerate(rows):  # per-record uncertainties (ADES rmsRA / rmsDec) override the constant
+        if "sigma_ra" in r and "sigma_dec" in r:
+            batch["sigma_ra"][i], batch["sigma_dec"][i] = r["sigma_ra"], r["sigma_dec"]
     if ut1_table is not None and n:
         batch["mjd_ut1"] = ut1_table.mjd_ut1(batch["mjd_tt"])
     return ids, batch
