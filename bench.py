@@ -37,6 +37,7 @@ WORKLOADS = {
     # name: (trajectories per GPU, n_obs, max_triplets, n_noise, noise_scale)
     "c3_100k_x12": (100_000, 12, 30, 10, 1.1),
     "c4_ragged_8_30": (100_000, (8, 30), 30, 10, 1.1),
+    "c4_125k_ragged_8_30": (125_000, (8, 30), 30, 10, 1.1),  # BASELINE configs[3]: 1 M trajectories over 8 GPUs
     "small": (4_000, 12, 30, 10, 1.1),
 }
 # static flop weights per counted event; libm calls are reported separately
