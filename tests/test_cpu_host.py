@@ -63,6 +63,17 @@ def test_struct_layouts_match_the_oracle_and_numpy_views(lib, oracle):
     for name, _ in api.IodResult._fields_:
         assert getattr(api.IodResult, name).offset == api.RESULT_DTYPE.fields[name][1]
     assert C.sizeof(api.ObsBatch) == 15 * 8  # ABI v2: + traj_seed
+    # ABI v3: FitLSQ records -- same field offsets as the oracle's (which has no explicit padding member)
+    assert api.LSQ_RESULT_DTYPE.itemsize == oracle.LSQ_RESULT_DTYPE.itemsize == 720
+    for name in oracle.LSQ_RESULT_DTYPE.names:
+        assert api.LSQ_RESULT_DTYPE.fields[name][1] == oracle.LSQ_RESULT_DTYPE.fields[name][1], name
+    assert C.sizeof(api.DifferentialCorrectionConfig) == C.sizeof(oracle.LsqConfig) == 144
+    for name, _ in oracle.LsqConfig._fields_:
+        assert getattr(api.DifferentialCorrectionConfig, name).offset == getattr(oracle.LsqConfig, name).offset, name
+    c = api.DifferentialCorrectionConfig.default(max_newton_iterations=7, free_elements=(1, 0, 1, 1, 1, 1))
+    o = oracle.default_lsq_config(max_newton_iterations=7, free_elements=(1, 0, 1, 1, 1, 1))
+    assert bytes(c)[:56] == bytes(o)[:56] and list(c.free_elements) == list(o.free_elements)
+    assert (c.chi2_rejection_threshold, c.eccentricity_limit, c.max_apoapsis_distance) == (25.0, 1.2, 1e4)
 
 
 def test_iod_params_default_and_validation(lib, oracle):
@@ -173,10 +184,16 @@ ranges = shard.shard_ranges(batch["traj_offset"], world, 6, 2)
 b, e = ranges[rank]
 local = O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, b, e)), et, op, n_threads=1)
 allr = shard.gather_results(local, ranges, rank, world, dist=dist)
+# the differential correction shards the same way (its records are per trajectory as well)
+cfg = O.default_lsq_config()
+lloc, lfit = O.fit_lsq(O.from_soa_batch(shard.slice_batch(batch, b, e)), et, cfg, local, n_threads=1)
+lall = shard.gather_results(lloc, ranges, rank, world, dist=dist)
 if rank == 0:
     whole = O.fit_full_iod(O.from_soa_batch(batch), et, op, n_threads=1)
     assert allr.tobytes() == whole.tobytes(), "sharded + gathered != single process"
-    print("GATHER_OK", len(allr))
+    lwhole, _ = O.fit_lsq(O.from_soa_batch(batch), et, cfg, whole, n_threads=1)
+    assert lall.tobytes() == lwhole.tobytes(), "sharded + gathered LSQ != single process"
+    print("GATHER_OK", len(allr), "LSQ_OK", int((lall["kind"] == 1).sum()))
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -192,7 +209,7 @@ def test_two_rank_sharding_and_gather_gloo(tmp_path, oracle):
                           "--master-addr", "127.0.0.1", "--master-port", "29653", str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "GATHER_OK 41" in out.stdout
+    assert "GATHER_OK 41 LSQ_OK" in out.stdout
 
 
 def test_bench_reference_arm_prints_contract_line():
