@@ -42,7 +42,8 @@ hres, hfit = ctx.fit_lsq(batch, p, cfg, initial_orbits=iod)
 host_s = time.perf_counter() - t0
 assert hres.tobytes() == res.tobytes()
 ok = res["kind"] == 1
-print(json.dumps({"T": T, "device_ms": ms, "device_traj_per_s": T / (min(ms) * 1e-3), "host_entry_s": host_s,
+import hashlib
+print(json.dumps({"T": T, "sha1": hashlib.sha1(res.tobytes() + d_fit.cpu().numpy().tobytes()).hexdigest(), "device_ms": ms, "device_traj_per_s": T / (min(ms) * 1e-3), "host_entry_s": host_s,
                   "host_traj_per_s": T / host_s, "kinds": np.bincount(res["kind"], minlength=3).tolist(),
                   "newton_iterations_total": int(res["total_newton_iterations"].sum()),
                   "rms_median_corrected": float(np.median(res["normalised_rms"][ok]))}))
