@@ -404,11 +404,14 @@ def main():
         l1.record()
         torch.cuda.synchronize()
         lms = l0.elapsed_time(l1) / 5
-        launches += 8 * 2 + per_step_launches + 2  # 8 device calls + the IOD call + the host-entry call
+        launches += 8 * 2 + per_step_launches + 3 * 2  # 8 device calls + the IOD call + 3 host-entry calls
         lres = d_lo.cpu().numpy().view(LSQ_RESULT_DTYPE).reshape(-1)
-        t0 = time.perf_counter()
-        lhost, _ = ctx.fit_lsq(host_batch, params, lcfg, initial_orbits=d_out.cpu().numpy().view(RESULT_DTYPE).reshape(-1))
-        lhost_s = time.perf_counter() - t0
+        io_host = d_out.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+        lhost_s = float("inf")
+        for _ in range(3):  # first call: arena growth and first-touch of the result pages
+            t0 = time.perf_counter()
+            lhost, _ = ctx.fit_lsq(host_batch, params, lcfg, initial_orbits=io_host)
+            lhost_s = min(lhost_s, time.perf_counter() - t0)
         n_it = int(lres["total_newton_iterations"].sum())
         lsq = {"trajectories_per_s": T / (lms * 1e-3), "ms": lms, "host_entry_trajectories_per_s": T / lhost_s,
                "host_entry_ms": lhost_s * 1e3, "host_equals_device": bool(lhost.tobytes() == lres.tobytes()),

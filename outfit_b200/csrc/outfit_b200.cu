@@ -1513,8 +1513,13 @@ extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_pa
   cudaStream_t stream = ctx->compute_stream;
   const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_geo ? 3 : 4) * n * 8 + T * sizeof(OutfitIodResult) +
                        T * sizeof(OutfitLsqResult) + n * sizeof(OutfitObsFit) + 16 * 256;
-  unsigned char *arena = nullptr;
-  if (cudaMalloc(&arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(fit_lsq arena)");
+  // the context's cached input arena (shared with the IOD host entry, whose use of it has ended by now)
+  if (ctx->arena_bytes < bytes) {
+    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(fit_lsq arena)");
+    ctx->arena_bytes = bytes;
+  }
+  unsigned char *arena = ctx->arena;
   size_t off = 0;
   auto put = [&](const void *src, size_t nbytes) -> void * {
     void *dst = arena + off;
@@ -1550,7 +1555,6 @@ extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_pa
   } else {
     cudaStreamSynchronize(stream);
   }
-  cudaFree(arena);
   return rc;
 }
 

@@ -10,7 +10,7 @@ cut -c1-600 gpurun_out/${TAG}_bench.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
-OUTFIT_B200_STREAMS=1 PERF_T=30000 PERF_PARITY=0 ncu --set full --clock-control none --import-source on -k regex:'roots_kernel|correct_kernel|score_kernel' \
+[ "${SKIP_NCU_IOD:-0}" = "1" ] || OUTFIT_B200_STREAMS=1 PERF_T=30000 PERF_PARITY=0 ncu --set full --clock-control none --import-source on -k regex:'roots_kernel|correct_kernel|score_kernel' \
     --launch-skip 3 -c 3 -o gpurun_out/${TAG}_phases -f python tools/gpu_perf.py > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
