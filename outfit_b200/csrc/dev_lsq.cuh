@@ -259,6 +259,10 @@ __device__ __forceinline__ double lsq_dot6(const double *a, const double *b) {
 // least_square.rs:188-199
 __device__ __forceinline__ double lsq_angular_diff(double a, double b) {
   double d = a - b;
+  // the reference's subtract-until-in-range loop never ends for an infinite difference and takes |d| / 2 pi
+  // trips for a huge one (garbage input: predicted and observed RA both lie in [0, 2 pi) otherwise); a kernel
+  // must not hang on it
+  if (!(fabs(d) < 1e6)) return remainder(d, kTwoPi);
   while (d > kPi) d -= kTwoPi;
   while (d < -kPi) d += kTwoPi;
   return d;

@@ -189,3 +189,46 @@ def test_lsq_full_size_properties(env):
     rb["traj_offset"] = np.concatenate([[0], np.cumsum((off[1:] - off[:-1])[rev])]).astype(np.uint64)
     r2, _ = env["ctx"].fit_lsq(rb, p, cfg, initial_orbits=np.ascontiguousarray(iod[rev]))
     assert r2[::-1].tobytes() == res[sub].tobytes()
+
+
+def test_lsq_garbage_observation_does_not_hang_or_leak(env):
+    """An absurd RA (1e300 rad, inf, NaN) in one trajectory: the reference's subtract-2-pi loop would spin
+    (forever for inf); the kernel must return, and every other trajectory must be untouched."""
+    from outfit_b200 import DifferentialCorrectionConfig, IODParams
+    batch = env["synth"].make_trajectories(400, 12, seed=310, table=env["table"], max_triplets=10, n_noise=1)
+    p = IODParams.builder(n_noise_realizations=0, max_triplets=10)
+    cfg = DifferentialCorrectionConfig.default()
+    iod = env["ctx"].fit_full_iod(batch, p)
+    clean, cfit = env["ctx"].fit_lsq(batch, p, cfg, initial_orbits=iod)
+    off = batch["traj_offset"].astype(np.int64)
+    victims = [t for t in range(400) if iod["status"][t] == 0][:3]
+    assert len(victims) == 3
+    for t, bad in zip(victims, (1e300, np.inf, np.nan)):
+        batch["ra"][off[t] + 4] = bad
+    got, gfit = env["ctx"].fit_lsq(batch, p, cfg, initial_orbits=iod)
+    keep = np.ones(400, dtype=bool)
+    keep[victims] = False
+    assert got[keep].tobytes() == clean[keep].tobytes()
+    obs_keep = np.repeat(keep, off[1:] - off[:-1])
+    assert gfit[obs_keep].tobytes() == cfit[obs_keep].tobytes()
+    assert (got["status"][victims] == 0).all() and np.isin(got["kind"][victims], (1, 2)).all()
+
+
+def test_lsq_golden_fixture(env):
+    """Committed oracle output (tests/golden/lsq_golden.npz: the IOD golden's batch with injected outliers,
+    started from the IOD golden's records) -- the rejection step is on this path."""
+    import importlib.util
+    import os
+    from outfit_b200 import DifferentialCorrectionConfig, RESULT_DTYPE
+    O = env["O"]
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_lsq_golden", os.path.join(gold, "make_lsq_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gold, "lsq_golden.npz"))
+    _, batch, iod = mod.golden_inputs(np.load(os.path.join(gold, "iod_golden.npz")))
+    want = np.frombuffer(g["results"].tobytes(), dtype=O.LSQ_RESULT_DTYPE)
+    wfit = np.frombuffer(g["fit"].tobytes(), dtype=O.OBS_FIT_DTYPE)
+    got, gfit = env["ctx"].fit_lsq(batch, None, DifferentialCorrectionConfig.default(), initial_orbits=iod.view(RESULT_DTYPE))
+    st = assert_lsq_parity(got, want, gfit, wfit, O.from_soa_batch(batch), list(g["floors"]), g["unstable"])
+    assert st["n_corrected"] >= 20 and (gfit["selection"] == 1).sum() >= 10, st

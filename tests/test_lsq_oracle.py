@@ -267,3 +267,20 @@ def test_full_loop_reaches_the_noise_floor(oracle):
     assert fb.any() and np.array_equal(res["elem"][fb], iod["elem"][fb]) and np.isin(res["fallback_cause"][fb], (18, 19, 20)).all()
     bad = res["kind"] == 0
     assert np.array_equal(res["status"][bad], iod["status"][bad]) and (iod["status"][~bad] == 0).all()
+
+
+def test_oracle_reproduces_the_lsq_golden_fixture(oracle):
+    """tests/golden/lsq_golden.npz (make_lsq_golden.py): guards the oracle itself against drift."""
+    import importlib.util
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_lsq_golden", os.path.join(gold, "make_lsq_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gold, "lsq_golden.npz"))
+    table, batch, iod = mod.golden_inputs(np.load(os.path.join(gold, "iod_golden.npz")))
+    assert np.array_equal(np.array([batch["ra"].sum(), batch["dec"].sum(), batch["mjd_tt"].sum()]), g["input_digest"])
+    et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    res, fit = O.fit_lsq(O.from_soa_batch(batch), et, O.default_lsq_config(), iod, n_threads=2)
+    assert res.tobytes() == g["results"].tobytes() and fit.tobytes() == g["fit"].tobytes()
+    assert (fit["selection"] == 1).sum() >= 10 and (res["kind"] == 1).sum() >= 20
