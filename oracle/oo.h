@@ -380,6 +380,9 @@ int oo_run_differential_correction(const oo_traj_view *tv, const oo_ephem_table 
                                    oo_obs_fit_data *fit, oo_lsq_result *out);
 void oo_differential_correction(const oo_traj_view *tv, const oo_ephem_table *tab, const oo_iod_result *iod,
                                 const oo_lsq_config *cfg, oo_lsq_result *out, oo_obs_fit_data *fit);
+void oo_equinoctial_to_keplerian(const double eq[6], double kep[6]);   /* keplerian_element.rs:185-233 */
+void oo_jacobian_to_keplerian(const double eq[6], double jac[36]);     /* equinoctial_element.rs:1049-1140 */
+void oo_propagate_covariance(const double jac[36], const double cov[36], double out[36]); /* uncertainty.rs:412 */
 /* FitLSQ::fit_lsq (obs_dataset_api.rs:113-190) with initial_orbits = Some(IOD results), over a flat
    batch, one task per trajectory.  fit: [sum n] per-observation fit data (final state). */
 void oo_fit_lsq(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,

@@ -556,3 +556,54 @@ void oo_differential_correction(const oo_traj_view *tv, const oo_ephem_table *ta
     fit[i].sigma_dec = tv->sigma_dec[i];
   }
 }
+
+/* keplerian_element.rs:185-233 (KeplerianElements::from_equinoctial_internal): (a,h,k,p,q,lambda) ->
+   (a,e,i,Omega,omega,M) */
+void oo_equinoctial_to_keplerian(const double eq[6], double kep[6]) {
+  const double eps = 1.0e-12;
+  double h = eq[1], k = eq[2], p = eq[3], q = eq[4];
+  double ecc = sqrt(h * h + k * k);
+  double dig = ecc < eps ? 0.0 : atan2(h, k);
+  double tgi2 = sqrt(p * p + q * q);
+  double node = tgi2 < eps ? 0.0 : atan2(p, q);
+  kep[0] = eq[0];
+  kep[1] = ecc;
+  kep[2] = 2.0 * atan(tgi2);
+  kep[3] = node;
+  kep[4] = oo_rem_euclid(dig - node, OO_DPI);
+  kep[5] = oo_rem_euclid(eq[5] - dig, OO_DPI);
+}
+
+/* equinoctial_element.rs:1049-1140 (jacobian_to_keplerian): d(a,e,i,Omega,omega,M)/d(a,h,k,p,q,lambda),
+   column-major 6x6 */
+void oo_jacobian_to_keplerian(const double eq[6], double jac[36]) {
+  const double eps = 1.0e-12;
+  double h = eq[1], k = eq[2], p = eq[3], q = eq[4];
+  double e = sqrt(h * h + k * k), e_sq = e * e;
+  double dvh = 0.0, dvk = 0.0;
+  if (!(e < eps)) { dvh = k / e_sq; dvk = -h / e_sq; }
+  double t = sqrt(p * p + q * q), t_sq = t * t;
+  double dip = 0.0, diq = 0.0, dnp = 0.0, dnq = 0.0;
+  if (!(t < eps)) {
+    double denom = t * (1.0 + t_sq);
+    dip = 2.0 * p / denom; diq = 2.0 * q / denom;
+    dnp = q / t_sq; dnq = -p / t_sq;
+  }
+  double em = fmax(e, eps);
+  memset(jac, 0, 36 * sizeof(double));
+  M6(jac, 0, 0) = 1.0;
+  M6(jac, 1, 1) = h / em; M6(jac, 4, 1) = dvh; M6(jac, 5, 1) = -dvh;
+  M6(jac, 1, 2) = k / em; M6(jac, 4, 2) = dvk; M6(jac, 5, 2) = -dvk;
+  M6(jac, 2, 3) = dip; M6(jac, 3, 3) = dnp; M6(jac, 4, 3) = -dnp;
+  M6(jac, 2, 4) = diq; M6(jac, 3, 4) = dnq; M6(jac, 4, 4) = -dnq;
+  M6(jac, 5, 5) = 1.0;
+}
+
+/* uncertainty.rs:412-416 (OrbitalCovariance::propagate): J * C * J^T, nalgebra's column-by-column gemv */
+void oo_propagate_covariance(const double jac[36], const double cov[36], double out[36]) {
+  double jc[36], jt[36];
+  for (int c = 0; c < 6; c++) gemv6(jac, &cov[6 * c], &jc[6 * c]);
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) M6(jt, r, c) = M6(jac, c, r);
+  for (int c = 0; c < 6; c++) gemv6(jc, &jt[6 * c], &out[6 * c]);
+}
