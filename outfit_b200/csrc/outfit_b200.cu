@@ -515,30 +515,70 @@ __global__ void __launch_bounds__(128)
 propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double *__restrict__ t0,
                            const double *__restrict__ t1, const double *__restrict__ psi_guess,
                            OutfitSolverType st, double *__restrict__ out, int *__restrict__ status) {
+  // The initial guess is the one type-dependent step (elliptic: acos + a sincos Newton; hyperbolic: log,
+  // sinh and an expm1 Newton; parabolic: a cubic) and random batches mix the types inside every warp, which
+  // then pays for all of them.  The five scalars the guess needs are therefore exchanged through shared
+  // memory in TYPE ORDER within the block: thread j evaluates the guess of the j-th state of that order, so
+  // three of the four warps of a block run a single type, and every thread reads its own guess back.  The
+  // arithmetic per state is untouched (same bits).
+  __shared__ double g_in[5][128];
+  __shared__ double g_psi[128];
+  __shared__ unsigned g_cnt[4][4];
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const V3 r = V3{rv[i], rv[n + i], rv[2 * n + i]};
-  const V3 v = V3{rv[3 * n + i], rv[4 * n + i], rv[5 * n + i]};
+  const bool live = i < n;
+  const size_t ic = live ? i : 0;
+  const V3 r = V3{rv[ic], rv[n + ic], rv[2 * n + ic]};
+  const V3 v = V3{rv[3 * n + ic], rv[4 * n + ic], rv[5 * n + ic]};
   double o[11];
 #pragma unroll
   for (int q = 0; q < 11; ++q) o[q] = NAN;
   int stt = OUTFIT_ST_OK;
   const double r0 = bf_sqrt(dot(r, r));
-  if (r0 < kEps) {
+  const bool degenerate = r0 < kEps;
+  const double v2 = dot(v, v);
+  const double sig0 = bf_div(dot(r, v), kGaussK);
+  const double alpha = bf_div(v2 - bf_div(2.0 * kMu, r0), kMu);
+  const V3 h = cross(r, v);
+  double e0 = bf_sqrt(1.0 + bf_div(alpha * dot(h, h), kMu));
+  e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
+  const double dt = t1[ic] - t0[ic];
+  double psi_own = 0.0;
+  if (psi_guess) {
+    psi_own = psi_guess[ic];
+  } else {
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const unsigned key = (!live || degenerate) ? 3u : (alpha < 0.0 ? 0u : (alpha > 0.0 ? 1u : 2u));
+    unsigned rank_in_warp = 0;
+#pragma unroll
+    for (unsigned k = 0; k < 4; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, key == k);
+      if (lane == 0) g_cnt[wib][k] = (unsigned)__popc(b);
+      if (key == k) rank_in_warp = (unsigned)__popc(b & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    unsigned pos = rank_in_warp, n_work = 0;
+    for (unsigned k = 0; k < 4; ++k)
+      for (unsigned w = 0; w < 4; ++w) {
+        const unsigned c = g_cnt[w][k];
+        if (k < key || (k == key && w < wib)) pos += c;
+        if (k < 3) n_work += c;
+      }
+    g_in[0][pos] = dt; g_in[1][pos] = r0; g_in[2][pos] = sig0; g_in[3][pos] = alpha; g_in[4][pos] = e0;
+    __syncthreads();
+    if (threadIdx.x < n_work)
+      g_psi[threadIdx.x] = prelim_kepuni_v(g_in[0][threadIdx.x], g_in[1][threadIdx.x], g_in[2][threadIdx.x],
+                                           g_in[3][threadIdx.x], g_in[4][threadIdx.x], st.convergency,
+                                           (unsigned)st.max_iter_prelim_kepuni, st.parabolic_method);
+    __syncthreads();
+    psi_own = g_psi[pos < 128 ? pos : 127];
+  }
+  if (!live) return;
+  if (degenerate) {
     stt = OUTFIT_ST_DEGENERATE_STATE;
   } else {
-    const double v2 = dot(v, v);
-    const double sig0 = bf_div(dot(r, v), kGaussK);
-    const double alpha = bf_div(v2 - bf_div(2.0 * kMu, r0), kMu);
-    const V3 h = cross(r, v);
-    double e0 = bf_sqrt(1.0 + bf_div(alpha * dot(h, h), kMu));
-    e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
-    const double dt = t1[i] - t0[i];
-    // initial guess (prelim_kepler/*.rs) out of line, Newton (newton_solver.rs:240-352) inlined with the
+    // initial guess (prelim_kepler/*.rs) out of line (above), Newton (newton_solver.rs:240-352) inlined with the
     // register-resident Stumpff series of dev_correct.cuh: same operations, same bits as dev_kepler.cuh
-    double psi = psi_guess ? psi_guess[i]
-                           : prelim_kepuni_v(dt, r0, sig0, alpha, e0, st.convergency, (unsigned)st.max_iter_prelim_kepuni,
-                                             st.parabolic_method);
+    double psi = psi_own;
     const double psi0 = psi;
     double s01[2] = {0.0, 0.0}, s2 = 0.0, s3 = 0.0;
     WorkC wc;
