@@ -161,6 +161,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
   int orbit_status = 0;
   double a = 0, h = 0, k = 0, lambda = 0, t_ref = 0, n_mot = 0, lon_peri = 0, ch = 0, ck = 0, bhk = 0;
   V3 fv = V3{0, 0, 0}, gv = V3{0, 0, 0};
+  double sx0 = 0, cx0 = 0;  // sincos of the Newton start pi + lon_peri: the same for every epoch of the orbit
   if (i < n_orbits) {
     Equinoctial eq;
     const int kd = kind[i];
@@ -192,6 +193,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
         const double common = 2.0 * eq.p * eq.q * inv_u;
         fv = V3{(1.0 - eq.p * eq.p + eq.q * eq.q) * inv_u, common, -2.0 * eq.p * inv_u};
         gv = V3{common, (1.0 + eq.p * eq.p - eq.q * eq.q) * inv_u, 2.0 * eq.q * inv_u};
+        sincos_angle(kPi + lon_peri, &sx0, &cx0);
       }
     }
   }
@@ -216,11 +218,12 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
           if (lam1 < lon_peri) lam1 += kTwoPi;
           // generalised Kepler equation, roots 0.0.8 Newton (equinoctial_element.rs:326-348)
           const double eps = kEps * 1e2;
-          double x = kPi + lon_peri, sF, cF;
+          double x = kPi + lon_peri, sF = sx0, cF = cx0;
           int iter = 0;
-          bool last = false, ok = true;
+          bool last = false, ok = true, have = true;  // the first evaluation point is per orbit (hoisted above)
           for (;;) {
-            sincos_angle(x, &sF, &cF);
+            if (!have) sincos_angle(x, &sF, &cF);
+            have = false;
             if (last) break;
             const double f = x - k * sF + h * cF - lam1;
             const double d = 1.0 - k * cF - h * sF;

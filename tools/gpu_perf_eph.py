@@ -20,3 +20,9 @@ for _ in range(3): ctx.ephemeris_twobody_device(n, d[0], d[1], d[2], E, d[3], d[
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 print(f"ephemeris {n} x {E}: {ms:.3f} ms  {n*E/ms*1e3/1e9:.2f} G entries/s  {76.0*n*E/ms*1e3/1e9:.0f} GB/s  ok={float((d_s==0).float().mean()):.4f}")
+import hashlib
+hsh = hashlib.sha1()
+for q in range(9):
+    hsh.update(d_o[q * E * n:(q + 1) * E * n].cpu().numpy().tobytes())
+hsh.update(d_s.cpu().numpy().tobytes())
+print("sha1", hsh.hexdigest())
