@@ -140,3 +140,23 @@ def test_config1_differential_correction_gpu_matches_oracle(oracle):
     fl, un = oracle_lsq_floor(O, ob, et, O.default_lsq_config(), iod, want, wfit)
     st = assert_lsq_parity(got, want, gfit, wfit, ob, fl, un, max_flip_fraction=0.0)
     assert st["n_corrected"] == 1 and np.array_equal(gfit["selection"], wfit["selection"])
+
+
+def test_quick_start_example_host_side(tmp_path):
+    """examples/run_full_iod.py --dry-run: reader -> batch for the fixture, an MPC file and an ADES file."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = [sys.executable, os.path.join(root, "examples", "run_full_iod.py"), "--dry-run"]
+    out = subprocess.run(exe, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "1 trajectory(ies), 37 observations" in out.stdout, out.stderr[-800:]
+    line = "     K09R05F* C2009 09 15.22735 22 52 23.37 -14 47 05.4          20.7 Vr~097wG96"
+    obs = tmp_path / "x.obs"
+    obs.write_text("\n".join(line[:23] + f"{15.2 + d:8.5f}" + line[31:] for d in range(3)) + "\n")
+    out = subprocess.run(exe + [str(obs)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "1 trajectory(ies), 3 observations" in out.stdout, out.stderr[-800:]
+    xml = tmp_path / "x.xml"
+    xml.write_text("<ades version='2017'><optical><trkSub>a1</trkSub><stn>G96</stn><obsTime>2016-08-30T00:00:00Z</obsTime>"
+                   "<ra>180.5</ra><dec>12.25</dec><rmsRA>0.2</rmsRA><rmsDec>0.2</rmsDec></optical></ades>")
+    out = subprocess.run(exe + [str(xml)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "1 trajectory(ies), 1 observations" in out.stdout, out.stderr[-800:]
