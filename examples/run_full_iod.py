@@ -2,7 +2,7 @@
 """The reference's quick start (README / examples/run_full_iod.rs: one MPC 80-column file -> Gauss IOD)
 on the B200 path, followed by the differential correction of the orbit found.
 
-    python examples/run_full_iod.py [FILE.obs | FILE.xml] [--eop2 latest_eop2.long] [--de DE_FILE] [--no-lsq]
+    python examples/run_full_iod.py [FILE.obs | FILE.xml | FILE.parquet] [--eop2 latest_eop2.long] [--de DE_FILE] [--no-lsq]
 
 Without a file the committed fixture of the reference's own quick-start input is used
 (tests/golden/config1_2015AB.json: the 37 observations of 2015 AB).  Without --de a synthetic DE440-shaped
@@ -27,6 +27,9 @@ def load_trajectories(path):
     if path is None:
         d = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_2015AB.json")))
         return {d["designation"]: d["records"]}
+    if path.endswith(".parquet"):
+        from outfit_b200 import tabular
+        return tabular.parse(path)  # default schema: traj_id, jd (UTC), ra / dec (deg), obscode
     text = open(path).read()
     if path.endswith(".xml"):
         return ades.parse(text)
