@@ -279,12 +279,16 @@ class OutfitB200:
         b.max_obs_per_traj = int(batch.get("max_obs_per_traj", 0))
         return b
 
-    def fit_full_iod(self, batch, params, use_body_fixed=False):
-        """HOST buffers in, numpy structured array (RESULT_DTYPE) out; H2D/D2H inside the call."""
+    def fit_full_iod(self, batch, params, use_body_fixed=False, out=None):
+        """HOST buffers in, numpy structured array (RESULT_DTYPE) out; H2D/D2H inside the call.
+        `out`: optional caller-owned RESULT_DTYPE array of n_traj records to write into (the C-ABI's buffers
+        are caller-owned; a page-locked one makes the final D2H copy asynchronous and ~5x faster)."""
         b = self._batch_struct(batch, use_body_fixed)
         if params.n_noise_realizations == 0:
             b.noise_z = None
-        out = np.zeros(int(b.n_traj), dtype=RESULT_DTYPE)
+        if out is None:
+            out = np.zeros(int(b.n_traj), dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape == (int(b.n_traj),) and out.flags["C_CONTIGUOUS"]
         self._check(self._L.outfit_b200_fit_full_iod(self._h, C.byref(params), C.byref(b), out.ctypes.data))
         return out
 

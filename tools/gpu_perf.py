@@ -37,8 +37,12 @@ if os.environ.get("PERF_E2E", "0") == "1":
     pinned = {k: torch.from_numpy(batch[k].view(np.int64) if batch[k].dtype == np.uint64 else batch[k]).pin_memory() for k in keys}
     hb = {k: (pinned[k].numpy().view(np.uint64) if k == "traj_offset" else pinned[k].numpy()) for k in keys}
     r0 = ctx.fit_full_iod(hb, params)
+    pinned_out = None
+    if os.environ.get("PERF_PINNED_OUT", "0") == "1":
+        from outfit_b200 import RESULT_DTYPE
+        pinned_out = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
     t0 = time.perf_counter()
-    for _ in range(3): r1 = ctx.fit_full_iod(hb, params)
+    for _ in range(3): r1 = ctx.fit_full_iod(hb, params, out=pinned_out)
     dt = (time.perf_counter() - t0) / 3
     same = all(np.array_equal(r1[f], res[f]) for f in ("status", "triplet_idx", "realization", "attempts")) and np.array_equal(r1["elem"][res["status"] == 0], res["elem"][res["status"] == 0])
     try:
