@@ -1,0 +1,43 @@
+// Prints the C++ host-side I/O results for tests/test_cpp_io.py to compare with the Python modules.
+#include "../../outfit_b200/host/outfit_b200_io.hpp"
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+int main(int argc, char **argv) {
+  using namespace outfit;
+  using namespace outfit::io;
+  if (argc < 3) return 2;
+  std::ifstream f(argv[1]);
+  const std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  auto traj = parse_mpc80(text, true);
+  std::printf("ntraj %zu id %s n %zu\n", traj.size(), traj[0].first.c_str(), traj[0].second.size());
+  std::ifstream g(argv[2]);
+  const std::string eop((std::istreambuf_iterator<char>(g)), std::istreambuf_iterator<char>());
+  Ut1Table ut1 = Ut1Table::from_eop2_text(eop);
+  std::map<std::string, Site> sites = {{"500", {0.0, 0.0, 0.0}}, {"G96", {249.21128, 0.845111, 0.533614}},
+                                       {"F51", {203.74409, 0.936241, 0.351543}}};
+  auto obs = to_observations(traj[0].second, sites, 0.5, 0.0, &ut1);
+  for (const Observation &o : obs)
+    std::printf("obs %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", o.mjd_tt, o.ra, o.dec, o.sigma_ra, o.body_fixed[0],
+                o.body_fixed[1], o.body_fixed[2], o.mjd_ut1);
+  ObsBatchBuilder b;
+  b.add_trajectory(obs);
+  OutfitObsBatch ob = b.finish();
+  std::printf("batch %llu %llu sorted %d\n", (unsigned long long)ob.n_traj, (unsigned long long)ob.n_obs,
+              (int)(ob.mjd_tt[0] <= ob.mjd_tt[ob.n_obs - 1]));
+  LsqOrbitResult r{};
+  const double eq[6] = {1.8017360713, 0.2693736809404963, 0.08856415260522467, 0.0008089970142830734, 0.10168201110394352, 1.693697008};
+  for (int j = 0; j < 6; ++j) r.elem[j] = eq[j];
+  for (int i = 0; i < 36; ++i) r.covariance[i] = (i % 7 == 0) ? 1e-8 * (1 + i / 7) : 1e-10 * ((i * 7) % 5);
+  for (int c = 0; c < 6; ++c)
+    for (int rr = 0; rr < c; ++rr) r.covariance[6 * c + rr] = r.covariance[6 * rr + c];
+  KeplerianFit k = lsq_to_keplerian(r);
+  std::printf("kep");
+  for (int j = 0; j < 6; ++j) std::printf(" %.17g", k.elem[j]);
+  std::printf("\ncov");
+  for (int i = 0; i < 36; ++i) std::printf(" %.17g", k.covariance[i]);
+  std::printf("\nsig");
+  for (int j = 0; j < 6; ++j) std::printf(" %.17g", k.sigma[j]);
+  std::printf("\n");
+  return 0;
+}

@@ -1,0 +1,61 @@
+"""The C++17 host-side I/O header (outfit_b200/host/outfit_b200_io.hpp: MPC 80-column reader, UT1 table,
+Keplerian form of the LSQ records) against the Python modules that do the same.  CPU only."""
+import os
+import subprocess
+
+import numpy as np
+
+from outfit_b200 import elements, mpc80
+from outfit_b200.ut1 import Ut1Table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LINE = "     K09R05F* C2009 09 15.22735 22 52 23.37 -14 47 05.4          20.7 Vr~097wG96"
+EOP2 = " $EOP2\n EOP2=\n 55000.00000, 30.0, 280.0, 34100.2500, 0.01,\n 55089.00000, 31.0, 281.0, 34160.7500, 0.01,\n 55091.00000, 31.0, 281.0, 34162.1250, 0.01,\n $END\n"
+
+
+def test_cpp_host_io_matches_python(tmp_path):
+    lines = [LINE[:23] + f"{15.22735 + d:8.5f} " + LINE[32:] for d in (2.0, 0.0, 1.0)]
+    lines[1] = lines[1][:77] + "F51"
+    lines.append(LINE[:14] + "S" + LINE[15:])        # satellite record: skipped
+    lines.append("short line")
+    obs = tmp_path / "x.obs"
+    obs.write_text("\n".join(lines) + "\n")
+    eop = tmp_path / "eop2.long"
+    eop.write_text(EOP2)
+    exe = str(tmp_path / "io_smoke")
+    libdir = os.path.join(ROOT, "outfit_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "cpp", "host_io_smoke.cpp"),
+                           "-o", exe, "-L" + libdir, "-loutfit_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, str(obs), str(eop)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = [ln.split() for ln in out.stdout.splitlines()]
+    assert rows[0] == ["ntraj", "1", "id", "K09R05F", "n", "3"]
+    got = np.array([[float(x) for x in r[1:]] for r in rows if r[0] == "obs"])
+    # the Python chain on the same files
+    tr = mpc80.parse(obs.read_text(), single_trajectory=True)
+    assert list(tr) == ["K09R05F"] and len(tr["K09R05F"]) == 3
+    table = Ut1Table.from_eop2_text(EOP2)
+    recs = tr["K09R05F"]                              # file order (the C++ rows are printed before sorting)
+    for g, r in zip(got, recs):
+        tt = mpc80.utc_to_tt(r["mjd_utc"])
+        assert g[0] == tt and g[1] == r["ra"] and g[2] == r["dec"] and g[3] == 0.5 * mpc80.ARCSEC
+        assert np.allclose(g[4:7], mpc80.body_fixed_position(r["obscode"]), rtol=1e-14, atol=0)  # deg -> rad rounding
+        assert g[7] == table.mjd_ut1(tt)[0]
+    assert [r for r in rows if r[0] == "batch"][0][1:] == ["1", "3", "sorted", "1"]
+    # Keplerian form of an equinoctial record with a covariance
+    eq = np.array([[1.8017360713, 0.2693736809404963, 0.08856415260522467, 0.0008089970142830734, 0.10168201110394352, 1.693697008]])
+    cov = np.zeros(36)
+    for i in range(36):
+        cov[i] = 1e-8 * (1 + i // 7) if i % 7 == 0 else 1e-10 * ((i * 7) % 5)
+    cm = cov.reshape(6, 6)                            # [col][row]
+    for c in range(6):
+        for r in range(c):
+            cm[c, r] = cm[r, c]
+    kep = np.array([float(x) for x in [r for r in rows if r[0] == "kep"][0][1:]])
+    assert list(kep) == [1.8017360713, 0.2835591457, 0.20267383289999996, 0.007955979, 1.2451951388, 0.4405458902000001]
+    assert np.abs(elements.equinoctial_to_keplerian(eq)[0] - kep).max() <= 4e-16
+    want = elements.propagate_covariance(cm.T[None], elements.jacobian_to_keplerian(eq))[0]
+    gcov = np.array([float(x) for x in [r for r in rows if r[0] == "cov"][0][1:]]).reshape(6, 6).T
+    assert np.allclose(gcov, want, rtol=1e-12, atol=1e-24)
+    gsig = np.array([float(x) for x in [r for r in rows if r[0] == "sig"][0][1:]])
+    assert np.allclose(gsig, np.sqrt(np.diag(want)), rtol=1e-12)
