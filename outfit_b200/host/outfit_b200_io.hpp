@@ -6,12 +6,15 @@
 //
 //   MPC 80-column optical astrometry  -> outfit::Observation rows        (reference input: tests/data/*.obs)
 //   JPL latest_eop2.long              -> UT1 epochs for pvobs             observer_extension.rs:191-192
+//   JPL DE binary file                -> Chebyshev table                  horizon_data.rs:239-292,598-684
 //   equinoctial LSQ record            -> Keplerian elements + covariance  keplerian_element.rs:185-233,
 //                                        equinoctial_element.rs:1049-1140, uncertainty.rs:412-416
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <sstream>
 #include <string>
@@ -195,6 +198,64 @@ inline std::vector<Observation> to_observations(const std::vector<Mpc80Record> &
     out.push_back(o);
   }
   return out;
+}
+
+// ---- JPL DE binary ephemeris file (little-endian linux_p1550p2650.440 family) -----------------------
+// Layout as the reference parses it (HorizonData::read_horizon_file,
+// jpl_ephem/horizon/horizon_data.rs:239-251, 270-292, 336-368, 598-684): SS[3] f64 at byte 2652 (start JD,
+// end JD, days per record), NCON i32 at 2676, EMRAT f64 at 2688, IPT[12][3] u32 + NUMDE u32 + LPT[3] u32 at
+// 2696, IPT[13], IPT[14] after the constant names when NCON > 400; record size = (4 + sum 2 n_coeff n_sub dim)
+// * 4 bytes; data records from byte 2 * recsize, IPT offsets 1-based.  Rows used: 2 (EMB), 9 (Moon), 10 (Sun).
+struct DeTable {
+  std::vector<double> cheb;      // [n_blocks][block_stride]
+  size_t n_blocks = 0, block_stride = 0;
+  double jd_start = 0, jd_end = 0, block_days = 0, emrat = 0;
+  uint32_t ipt[3][3] = {};       // EMB, Moon, Sun: {0-based offset in a block, n_coeff, n_sub}
+  uint32_t numde = 0;
+};
+inline DeTable read_de_binary(const std::string &path) {
+  std::FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) throw Error(OUTFIT_E_INVALID_ARGUMENT, "cannot open " + path);
+  std::vector<unsigned char> buf;
+  unsigned char chunk[1 << 16];
+  size_t got;
+  while ((got = std::fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+  std::fclose(f);
+  if (buf.size() < 4096) throw Error(OUTFIT_E_INVALID_ARGUMENT, "DE file shorter than its header");
+  auto f64 = [&](size_t off) { double v; std::memcpy(&v, &buf[off], 8); return v; };
+  auto u32 = [&](size_t off) { uint32_t v; std::memcpy(&v, &buf[off], 4); return v; };
+  DeTable t;
+  t.jd_start = f64(2652); t.jd_end = f64(2660); t.block_days = f64(2668);
+  int32_t ncon; std::memcpy(&ncon, &buf[2676], 4);
+  t.emrat = f64(2688);
+  uint32_t ipt[15][3] = {};
+  for (int i = 0; i < 36; ++i) ipt[i / 3][i % 3] = u32(2696 + 4 * (size_t)i);
+  t.numde = u32(2696 + 144);
+  for (int c = 0; c < 3; ++c) ipt[12][c] = u32(2696 + 148 + 4 * (size_t)c);
+  if (t.numde >= 440 && ncon > 400) {
+    const size_t off = 2856 + (size_t)(ncon - 400) * 6;
+    if (off + 24 > buf.size()) throw Error(OUTFIT_E_INVALID_ARGUMENT, "DE header truncated");
+    for (int i = 0; i < 6; ++i) ipt[13 + i / 3][i % 3] = u32(off + 4 * (size_t)i);
+  }
+  static const int dim[15] = {3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 3, 3, 1};
+  size_t words = 4;
+  for (int i = 0; i < 15; ++i) words += 2 * (size_t)ipt[i][1] * ipt[i][2] * dim[i];
+  const size_t recsize = words * 4;
+  t.block_stride = recsize / 8;
+  if (buf.size() < 2 * recsize + recsize) throw Error(OUTFIT_E_INVALID_ARGUMENT, "no data records");
+  t.n_blocks = (buf.size() - 2 * recsize) / recsize;
+  t.cheb.resize(t.n_blocks * t.block_stride);
+  std::memcpy(t.cheb.data(), &buf[2 * recsize], t.cheb.size() * 8);
+  if (std::fabs(t.cheb[0] - t.jd_start) > 1e-6 || std::fabs((t.cheb[1] - t.cheb[0]) - t.block_days) > 1e-6)
+    throw Error(OUTFIT_E_INVALID_ARGUMENT, "first data record does not start at SS[0] / span SS[2] days");
+  const int rows[3] = {2, 9, 10};
+  for (int b = 0; b < 3; ++b) {
+    t.ipt[b][0] = ipt[rows[b]][0] - 1; t.ipt[b][1] = ipt[rows[b]][1]; t.ipt[b][2] = ipt[rows[b]][2];
+  }
+  return t;
+}
+inline void load_ephemeris(Context &ctx, const DeTable &t) {
+  ctx.load_ephemeris(t.cheb.data(), t.n_blocks, t.block_stride, t.jd_start, t.block_days, t.ipt, t.emrat);
 }
 
 // ---- Keplerian form of an equinoctial LSQ record ----------------------------------------------

@@ -39,5 +39,13 @@ int main(int argc, char **argv) {
   std::printf("\nsig");
   for (int j = 0; j < 6; ++j) std::printf(" %.17g", k.sigma[j]);
   std::printf("\n");
+  if (argc > 3) {
+    DeTable t = read_de_binary(argv[3]);
+    double sum = 0.0;
+    for (double v : t.cheb) sum += v;
+    std::printf("de %zu %zu %.17g %.17g %.17g %.17g %u", t.n_blocks, t.block_stride, t.jd_start, t.jd_end, t.block_days, t.emrat, t.numde);
+    for (int b = 0; b < 3; ++b) std::printf(" %u %u %u", t.ipt[b][0], t.ipt[b][1], t.ipt[b][2]);
+    std::printf(" %.17g\n", sum);
+  }
   return 0;
 }

@@ -26,7 +26,10 @@ def test_cpp_host_io_matches_python(tmp_path):
     libdir = os.path.join(ROOT, "outfit_b200")
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "cpp", "host_io_smoke.cpp"),
                            "-o", exe, "-L" + libdir, "-loutfit_b200", "-Wl,-rpath," + libdir])
-    out = subprocess.run([exe, str(obs), str(eop)], capture_output=True, text=True)
+    from outfit_b200 import de_reader, synth
+    de = str(tmp_path / "synth.440")
+    de_reader.write_de_binary(de, synth.make_ephemeris_table(n_blocks=12))
+    out = subprocess.run([exe, str(obs), str(eop), de], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     rows = [ln.split() for ln in out.stdout.splitlines()]
     assert rows[0] == ["ntraj", "1", "id", "K09R05F", "n", "3"]
@@ -59,3 +62,10 @@ def test_cpp_host_io_matches_python(tmp_path):
     assert np.allclose(gcov, want, rtol=1e-12, atol=1e-24)
     gsig = np.array([float(x) for x in [r for r in rows if r[0] == "sig"][0][1:]])
     assert np.allclose(gsig, np.sqrt(np.diag(want)), rtol=1e-12)
+    # DE binary file: the C++ parser against the Python one on the same (synthetic) file
+    want_de = de_reader.read_de_binary(de)
+    g = [r for r in rows if r[0] == "de"][0][1:]
+    assert int(g[0]) == want_de["cheb"].shape[0] and int(g[1]) == want_de["cheb"].shape[1]
+    assert [float(x) for x in g[2:6]] == [want_de["jd_start"], want_de["jd_end"], want_de["block_days"], want_de["emrat"]]
+    assert int(g[6]) == want_de["numde"] and [int(x) for x in g[7:16]] == [int(v) for v in want_de["ipt"].reshape(-1)]
+    assert abs(float(g[16]) - float(np.sum(want_de["cheb"]))) <= 1e-9 * abs(float(np.sum(want_de["cheb"])))
