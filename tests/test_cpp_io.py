@@ -69,3 +69,52 @@ def test_cpp_host_io_matches_python(tmp_path):
     assert [float(x) for x in g[2:6]] == [want_de["jd_start"], want_de["jd_end"], want_de["block_days"], want_de["emrat"]]
     assert int(g[6]) == want_de["numde"] and [int(x) for x in g[7:16]] == [int(v) for v in want_de["ipt"].reshape(-1)]
     assert abs(float(g[16]) - float(np.sum(want_de["cheb"]))) <= 1e-9 * abs(float(np.sum(want_de["cheb"])))
+
+
+def test_cpp_quick_start_example_builds_and_parses(tmp_path):
+    """examples/run_full_iod.cpp: compiles against the two headers; --dry-run goes from the reference's
+    quick-start observations (fixture records re-encoded as 80-column lines) + a DE-layout file to the batch."""
+    import json
+    from outfit_b200 import de_reader, synth
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_2015AB.json")))
+    lines = []
+    for r in d["records"]:
+        mjd = r["mjd_utc"]
+        jd = mjd + 2400000.5 + 0.5
+        z = int(jd)
+        a = int((z - 1867216.25) / 36524.25)
+        aa = z + 1 + a - a // 4
+        b = aa + 1524
+        c = int((b - 122.1) / 365.25)
+        dd = int(365.25 * c)
+        e = int((b - dd) / 30.6001)
+        day = b - dd - int(30.6001 * e) + (jd - z)
+        month = e - 1 if e < 14 else e - 13
+        year = c - 4716 if month > 2 else c - 4715
+        ra_h = np.degrees(r["ra"]) / 15.0
+        hh = int(ra_h); mm = int((ra_h - hh) * 60); ss = (ra_h - hh - mm / 60.0) * 3600
+        dec = np.degrees(abs(r["dec"]))
+        dg = int(dec); dm = int((dec - dg) * 60); ds = (dec - dg - dm / 60.0) * 3600
+        sign = "-" if r["dec"] < 0 else "+"
+        ln = f"     {d['designation']:<7s}  C{year:4d} {month:02d} {day:08.5f} {hh:02d} {mm:02d} {ss:06.3f}{sign}{dg:02d} {dm:02d} {ds:05.2f}"
+        ln = ln.ljust(77) + r["obscode"]
+        assert len(ln) == 80, (len(ln), ln)
+        lines.append(ln)
+    obs = tmp_path / "2015AB.obs"
+    obs.write_text("\n".join(lines) + "\n")
+    back = mpc80.parse(obs.read_text(), single_trajectory=True)
+    assert sum(len(v) for v in back.values()) == len(d["records"])
+    de = str(tmp_path / "synth.440")
+    de_reader.write_de_binary(de, synth.make_ephemeris_table(mjd_start=54900.0, n_blocks=80))
+    exe = str(tmp_path / "run_full_iod")
+    libdir = os.path.join(ROOT, "outfit_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "run_full_iod.cpp"),
+                           "-o", exe, "-L" + libdir, "-loutfit_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, str(obs), de, "--dry-run"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert f"{len(d['records'])} observations" in out.stdout and "80 blocks of 32 days" in out.stdout
+    # without --dry-run and without a GPU the context refuses to start: no CPU fallback
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe, str(obs), de], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr
