@@ -115,6 +115,11 @@ def test_cpp_quick_start_example_builds_and_parses(tmp_path):
     assert f"{len(d['records'])} observations" in out.stdout and "80 blocks of 32 days" in out.stdout
     # without --dry-run and without a GPU the context refuses to start: no CPU fallback
     import torch
+    out = subprocess.run([exe, str(obs), de], capture_output=True, text=True)
     if not torch.cuda.is_available():
-        out = subprocess.run([exe, str(obs), de], capture_output=True, text=True)
         assert out.returncode == 1 and "no CPU fallback" in out.stderr
+    else:  # on a GPU box: the whole chain, same orbit as the Python example / the reference's golden to ~1e-3
+        assert out.returncode == 0, out.stderr
+        assert "CorrectedOrbit Keplerian" in out.stdout and "differential correction:" in out.stdout, out.stdout
+        a = float(out.stdout.split("CorrectedOrbit")[1].splitlines()[1].split()[0])
+        assert abs(a - 1.801740835743616) < 2e-3
