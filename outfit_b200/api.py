@@ -155,6 +155,12 @@ ABI_SYMBOLS = [
     "outfit_b200_set_work_counters", "outfit_b200_set_pass_streams",
     "outfit_b200_measure_fp64_peak", "outfit_b200_selftest_arith", "outfit_b200_ephemeris_twobody", "outfit_b200_ephemeris_twobody_device",
     "outfit_b200_lsq_config_default", "outfit_b200_fit_lsq", "outfit_b200_fit_lsq_device",
+    "outfit_b200_fit_iod", "outfit_b200_ephemeris_request", "outfit_b200_ephemeris_request_device",
+    "outfit_b200_init_multi", "outfit_b200_group_destroy", "outfit_b200_group_size", "outfit_b200_group_ctx",
+    "outfit_b200_group_last_error", "outfit_b200_group_load_ephemeris", "outfit_b200_group_set_pass_streams",
+    "outfit_b200_group_fit_full_iod", "outfit_b200_group_fit_lsq", "outfit_b200_group_propagate_universal",
+    "outfit_b200_group_ephemeris_request", "outfit_b200_group_last_shards", "outfit_b200_shard_ranges",
+    "outfit_b200_host_alloc", "outfit_b200_host_free",
 ]
 
 
@@ -205,8 +211,43 @@ def load_library():
     L.outfit_b200_ephemeris_twobody.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, C.c_double * 3, vp, vp]
     L.outfit_b200_ephemeris_twobody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp,
                                                        C.c_double * 3, vp, vp, vp]
+    L.outfit_b200_fit_iod.argtypes = [vp, C.POINTER(IODParams), C.POINTER(ObsBatch), C.c_uint64, vp]
+    L.outfit_b200_ephemeris_request.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_ephemeris_request_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_init_multi.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.outfit_b200_group_destroy.argtypes = [vp]
+    L.outfit_b200_group_destroy.restype = None
+    L.outfit_b200_group_size.argtypes = [vp]
+    L.outfit_b200_group_ctx.argtypes = [vp, C.c_int]
+    L.outfit_b200_group_ctx.restype = vp
+    L.outfit_b200_group_last_error.argtypes = [vp]
+    L.outfit_b200_group_last_error.restype = cp
+    L.outfit_b200_group_load_ephemeris.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_double, C.c_double, vp, C.c_double]
+    L.outfit_b200_group_set_pass_streams.argtypes = [vp, C.c_int]
+    L.outfit_b200_group_fit_full_iod.argtypes = [vp, C.POINTER(IODParams), C.POINTER(ObsBatch), vp]
+    L.outfit_b200_group_fit_lsq.argtypes = [vp, C.POINTER(IODParams), C.POINTER(DifferentialCorrectionConfig),
+                                            C.POINTER(ObsBatch), vp, vp, vp]
+    L.outfit_b200_group_propagate_universal.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(SolverType), vp, vp]
+    L.outfit_b200_group_ephemeris_request.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_group_last_shards.argtypes = [vp, vp, vp]
+    L.outfit_b200_shard_ranges.argtypes = [C.c_uint64, vp, C.c_uint32, C.c_uint64, C.c_int, vp]
+    L.outfit_b200_host_alloc.argtypes = [C.c_size_t]
+    L.outfit_b200_host_alloc.restype = vp
+    L.outfit_b200_host_free.argtypes = [vp]
+    L.outfit_b200_host_free.restype = None
     _LIB = L
     return L
+
+
+def shard_ranges(traj_offset, n_parts, max_triplets=10, n_noise=20):
+    """The library's work-balanced cut (outfit_b200_shard_ranges; pure host arithmetic): [(t_begin, t_end)] * n_parts."""
+    off = np.ascontiguousarray(traj_offset, dtype=np.uint64)
+    cuts = np.zeros(n_parts + 1, dtype=np.uint64)
+    rc = load_library().outfit_b200_shard_ranges(len(off) - 1, off.ctypes.data, int(max_triplets), int(n_noise), int(n_parts),
+                                                 cuts.ctypes.data)
+    if rc != 0:
+        raise OutfitError(rc, "shard_ranges")
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(n_parts)]
 
 
 def _p(a):
@@ -291,6 +332,15 @@ class OutfitB200:
         assert out.dtype == RESULT_DTYPE and out.shape == (int(b.n_traj),) and out.flags["C_CONTIGUOUS"]
         self._check(self._L.outfit_b200_fit_full_iod(self._h, C.byref(params), C.byref(b), out.ctypes.data))
         return out
+
+    def fit_iod(self, batch, params, traj_index, use_body_fixed=False):
+        """FitIOD::fit_iod (obs_dataset_api.rs:118-143): one trajectory of the batch -> one RESULT_DTYPE record."""
+        b = self._batch_struct(batch, use_body_fixed)
+        if params.n_noise_realizations == 0:
+            b.noise_z = None
+        out = np.zeros(1, dtype=RESULT_DTYPE)
+        self._check(self._L.outfit_b200_fit_iod(self._h, C.byref(params), C.byref(b), int(traj_index), out.ctypes.data))
+        return out[0]
 
     def fit_full_iod_device(self, dev_batch, params, out_ptr, stream=0, use_body_fixed=False):
         """DEVICE-resident buffers (torch tensors or raw pointers); enqueues, does not sync."""
@@ -386,6 +436,18 @@ class OutfitB200:
         self._check(self._L.outfit_b200_ephemeris_twobody_device(self._h, n, _p(kind), _p(epoch), _p(elem), n_epochs,
                                                                  _p(mjd_tt), _p(mjd_ut1), bf, _p(out), _p(status), stream))
 
+    def ephemeris_request(self, kind, epoch, elem, observers, out=None, status=None):
+        """EphemerisRequest with several observers (request.rs:276-340): observers = [(body_fixed (3,), mjd_tt (E_o,),
+        mjd_ut1 (E_o,)), ...] -> out (9, E_total, n), status (E_total, n), epochs in request order."""
+        n = int(kind.shape[0])
+        bf, off, tt, ut = _flatten_request(observers)
+        E = int(off[-1])
+        out = np.empty((9, E, n), dtype=np.float64) if out is None else out
+        status = np.empty((E, n), dtype=np.int32) if status is None else status
+        self._check(self._L.outfit_b200_ephemeris_request(self._h, n, _p(kind), _p(epoch), _p(elem), len(observers), _p(bf),
+                                                          _p(off), _p(tt), _p(ut), out.ctypes.data, status.ctypes.data))
+        return out, status
+
     def selftest_arith(self, n, seed=1, exp_range=60):
         """Mismatch counts (rcp, div, sqrt, sincos) of the library's own arithmetic against CUDA's."""
         out = (C.c_uint64 * 4)()
@@ -396,3 +458,136 @@ class OutfitB200:
         v = C.c_double()
         self._check(self._L.outfit_b200_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+
+def _flatten_request(observers):
+    bf = np.ascontiguousarray([np.asarray(o[0], dtype=np.float64) for o in observers]).reshape(-1)
+    off = np.concatenate([[0], np.cumsum([len(o[1]) for o in observers])]).astype(np.uint64)
+    tt = np.ascontiguousarray(np.concatenate([np.asarray(o[1], dtype=np.float64) for o in observers]))
+    ut = np.ascontiguousarray(np.concatenate([np.asarray(o[2], dtype=np.float64) for o in observers]))
+    return bf, off, tt, ut
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory from outfit_b200_host_alloc (kept alive by the array's base)."""
+    L = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = L.outfit_b200_host_alloc(n)
+    if not ptr:
+        raise OutfitError(-4, "outfit_b200_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                L.outfit_b200_host_free(self.p)
+            except Exception:
+                pass
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    buf._owner = _Owner(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+class OutfitGroup:
+    """Every GPU of the box behind ONE call: the drop-in for `fit_full_iod_parallel` (obs_dataset_api.rs:175-207).
+    `devices`: None = all visible GPUs, an int = the first n, or a list of device ids (an id may repeat:
+    several contexts on one GPU, which is how the sharded path is tested on a single-GPU box)."""
+
+    def __init__(self, devices=None):
+        L = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = L.outfit_b200_init_multi(0, None, C.byref(h))
+        elif isinstance(devices, int):
+            rc = L.outfit_b200_init_multi(devices, None, C.byref(h))
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = L.outfit_b200_init_multi(len(devices), ids, C.byref(h))
+        if rc != 0:
+            raise OutfitError(rc, L.outfit_b200_strerror(rc).decode())
+        self._h, self._L = h, L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.outfit_b200_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._L.outfit_b200_group_size(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.outfit_b200_group_last_error(self._h).decode() or self._L.outfit_b200_strerror(rc).decode()
+            raise OutfitError(rc, msg)
+
+    def load_ephemeris(self, table):
+        cheb = np.ascontiguousarray(table["cheb"], dtype=np.float64)
+        ipt = np.ascontiguousarray(table["ipt"], dtype=np.uint32)
+        self._check(self._L.outfit_b200_group_load_ephemeris(self._h, cheb.ctypes.data, cheb.shape[0], cheb.shape[1],
+                                                             float(table["jd_start"]), float(table["block_days"]),
+                                                             ipt.ctypes.data, float(table["emrat"])))
+
+    def set_pass_streams(self, n):
+        self._check(self._L.outfit_b200_group_set_pass_streams(self._h, int(n)))
+
+    def fit_full_iod(self, batch, params, use_body_fixed=False, out=None):
+        b = OutfitB200._batch_struct(batch, use_body_fixed)
+        if params.n_noise_realizations == 0:
+            b.noise_z = None
+        if out is None:
+            out = np.zeros(int(b.n_traj), dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and out.shape == (int(b.n_traj),) and out.flags["C_CONTIGUOUS"]
+        self._check(self._L.outfit_b200_group_fit_full_iod(self._h, C.byref(params), C.byref(b), out.ctypes.data))
+        return out
+
+    def fit_lsq(self, batch, iod_params, cfg=None, initial_orbits=None, use_body_fixed=False):
+        cfg = cfg or DifferentialCorrectionConfig.default()
+        b = OutfitB200._batch_struct(batch, use_body_fixed)
+        if iod_params is None or iod_params.n_noise_realizations == 0:
+            b.noise_z = None
+        out = np.zeros(int(b.n_traj), dtype=LSQ_RESULT_DTYPE)
+        fit = np.zeros(int(b.n_obs), dtype=OBS_FIT_DTYPE)
+        io = None
+        if initial_orbits is not None:
+            io = np.ascontiguousarray(initial_orbits, dtype=RESULT_DTYPE)
+        self._check(self._L.outfit_b200_group_fit_lsq(self._h, C.byref(iod_params) if iod_params is not None else None,
+                                                      C.byref(cfg), C.byref(b), io.ctypes.data if io is not None else None,
+                                                      out.ctypes.data, fit.ctypes.data))
+        return out, fit
+
+    def propagate_universal(self, rv, t0, t1, solver=None, psi_guess=None, out=None, status=None):
+        solver = solver or SolverType(kind=2)
+        n = rv.shape[1]
+        out = np.empty((11, n), dtype=np.float64) if out is None else out
+        status = np.empty(n, dtype=np.int32) if status is None else status
+        self._check(self._L.outfit_b200_group_propagate_universal(self._h, n, _p(rv), _p(t0), _p(t1), _p(psi_guess),
+                                                                  C.byref(solver), out.ctypes.data, status.ctypes.data))
+        return out, status
+
+    def ephemeris_request(self, kind, epoch, elem, observers, out=None, status=None):
+        n = int(kind.shape[0])
+        bf, off, tt, ut = _flatten_request(observers)
+        E = int(off[-1])
+        out = np.empty((9, E, n), dtype=np.float64) if out is None else out
+        status = np.empty((E, n), dtype=np.int32) if status is None else status
+        self._check(self._L.outfit_b200_group_ephemeris_request(self._h, n, _p(kind), _p(epoch), _p(elem), len(observers),
+                                                                _p(bf), _p(off), _p(tt), _p(ut), out.ctypes.data,
+                                                                status.ctypes.data))
+        return out, status
+
+    def last_shards(self):
+        """(cuts [n+1], wall ms per shard [n]) of the last group call."""
+        n = len(self)
+        cuts = np.zeros(n + 1, dtype=np.uint64)
+        ms = np.zeros(n, dtype=np.float32)
+        self._check(self._L.outfit_b200_group_last_shards(self._h, cuts.ctypes.data, ms.ctypes.data))
+        return cuts, ms

@@ -27,7 +27,10 @@
 
 namespace ofb {
 
-constexpr int kCorrectThreads = 128;
+#ifndef OUTFIT_CORRECT_THREADS
+#define OUTFIT_CORRECT_THREADS 128
+#endif
+constexpr int kCorrectThreads = OUTFIT_CORRECT_THREADS;
 // shared-memory slots per thread (doubles)
 enum {
   SL_R0 = 0, SL_R1 = 3, SL_R2 = 6, SL_S0 = 9, SL_S1 = 12, SL_S2 = 15, SL_I0 = 18, SL_I1 = 21, SL_I2 = 24,

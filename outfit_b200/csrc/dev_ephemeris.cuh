@@ -80,8 +80,8 @@ __device__ __forceinline__ bool earth_posvel(const EphemDev &E, double et, V3 &p
 // table: [9][e_stride] = obs_pos_equ xyz, obs_vel_equ xyz (= Earth velocity), earth_pos_equ xyz
 __global__ void __launch_bounds__(128)
 ephemeris_observer_kernel(EphemDev E, size_t n_epochs, size_t e_stride, const double *__restrict__ mjd_tt,
-                          const double *__restrict__ mjd_ut1, double bfx, double bfy, double bfz,
-                          double *__restrict__ table, int *__restrict__ status) {
+                          const double *__restrict__ mjd_ut1, const double *__restrict__ bf_epoch, double bfx, double bfy,
+                          double bfz, double *__restrict__ table, int *__restrict__ status) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= e_stride) return;
   double o[9];
@@ -89,7 +89,9 @@ ephemeris_observer_kernel(EphemDev E, size_t n_epochs, size_t e_stride, const do
   for (int q = 0; q < 9; ++q) o[q] = NAN;
   int st = 0;
   if (e < n_epochs) {
-    const V3 geo = pvobs_position(mjd_tt[e], mjd_ut1[e], V3{bfx, bfy, bfz});
+    // bf_epoch: [3][n_epochs] per-epoch body-fixed position (a request with several observers) or null
+    const V3 bfv = bf_epoch ? V3{bf_epoch[e], bf_epoch[n_epochs + e], bf_epoch[2 * n_epochs + e]} : V3{bfx, bfy, bfz};
+    const V3 geo = pvobs_position(mjd_tt[e], mjd_ut1[e], bfv);
     V3 ep, ev;
     if (earth_posvel(E, mjd_tt[e], ep, ev)) {
       const V3 op = ep + ecl_to_equ(geo);

@@ -13,7 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <functional>
+#include <thread>
 #include <mutex>
 #include <new>
 #include <string>
@@ -51,6 +51,7 @@ struct IodBatchDev {
   const double *helio;   // [3][n_obs]
   const double *scorer;  // [3][n_obs]
   const double *noise_z; // [n_traj][max_triplets][n_noise][6] or null
+  const int *obs_status; // [n_obs] 0 | OUTFIT_ST_EPHEM_OUT_OF_RANGE (observer kernels)
 };
 
 struct IodScratch {
@@ -411,6 +412,19 @@ select_kernel(IodBatchDev B, IodDevParams P, IodScratch S, OutfitIodResult *__re
   OutfitIodResult res;
   memset(&res, 0, sizeof res);
   res.rms = NAN;
+  {
+    // An observation epoch outside the loaded ephemeris: the reference panics ("Time outside ephemeris
+    // range", horizon_data.rs:722); here the trajectory carries the error as a value and the others go on.
+    int bad = 0;
+    for (unsigned i = lane; i < n_obs; i += 32) bad |= B.obs_status[o0 + i];
+    if (__any_sync(0xffffffffu, bad != 0)) {
+      if (lane == 0) {
+        res.status = OUTFIT_ST_EPHEM_OUT_OF_RANGE;
+        out[tr] = res;
+      }
+      return;
+    }
+  }
   if (K == 0) {
     if (lane == 0) {
       res.status = OUTFIT_ST_NO_FEASIBLE_TRIPLETS;
@@ -628,6 +642,7 @@ struct LsqBatchDev {
   const unsigned long long *traj_offset;
   const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
   const double *scorer;  // [3][n_obs] observer position, equatorial J2000 (scorer_observer_kernel)
+  const int *obs_status; // [n_obs] 0 | OUTFIT_ST_EPHEM_OUT_OF_RANGE
 };
 
 // Scheduling: a persistent grid whose lanes fetch trajectories from a work counter and advance them ONE
@@ -673,7 +688,9 @@ lsq_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ iod, 
           double *z = reinterpret_cast<double *>(res);
           for (unsigned i = 0; i < sizeof(OutfitLsqResult) / 8; ++i) z[i] = 0.0;
         }
-        const int ist = iod[tr].status;
+        int ist = iod[tr].status;
+        for (unsigned i = 0; i < n_obs; ++i)
+          if (B.obs_status[o0 + i] != 0) ist = OUTFIT_ST_EPHEM_OUT_OF_RANGE;  // the reference panics (horizon_data.rs:722)
         if (ist != OUTFIT_ST_OK) {
           res->status = ist; res->kind = OUTFIT_LSQ_NONE;
         } else {
@@ -922,13 +939,15 @@ struct OutfitCtx {
   // scratch owned by the context (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
-  void *h_scratch = nullptr;
+  void *h_scratch = nullptr;  // page-locked staging (re-based offsets of a trajectory range)
+  size_t h_scratch_bytes = 0;
   void *iod_scratch = nullptr;  // per-candidate arrays of the phase pipeline
   size_t iod_scratch_bytes = 0;
   // host entry point: cached input arena, copy / compute streams, per-slice copy events
   unsigned char *arena = nullptr;
   size_t arena_bytes = 0;
-  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ring_ev[9] = {};  // bulk host entries: (uploaded, computed, downloaded) per ring slot
   std::vector<cudaEvent_t> copy_ev;
   double *d_zig = nullptr;  // ziggurat tables x[257], f[257] of the on-device StandardNormal (dev_rng.cuh)
   bool triplets_per_thread = true;  // OUTFIT_B200_TRIPLETS_WARP=1: the warp-per-trajectory selection kernel
@@ -1079,6 +1098,9 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  for (cudaEvent_t e : ctx->ring_ev)
+    if (e) cudaEventDestroy(e);
   for (int i = 0; i < 7; ++i) {
     if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
     if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
@@ -1148,9 +1170,22 @@ static IodDevParams to_dev_params(const OutfitIodParams &p) {
 constexpr unsigned kMaxObsPerTraj = 448;
 constexpr unsigned kMaxTriplets = 1024;
 
+// The host entry copies the noise deviates in trajectory slices; a pass waits for the slice holding its last
+// trajectory (events recorded on the copy stream, one per slice).
+struct SliceWait {
+  const cudaEvent_t *ev;  // [n_slices] or null (nothing to wait for)
+  unsigned long long slice;
+  size_t n_slices;
+  void wait(unsigned long long t0, unsigned long long tn, cudaStream_t s) const {
+    if (!ev) return;
+    const size_t last = (size_t)((t0 + tn - 1) / slice);
+    cudaStreamWaitEvent(s, ev[last < n_slices ? last : n_slices - 1], 0);
+  }
+};
+
 // Launch the device pipeline on device-resident buffers.  `max_obs` = longest trajectory.
 // `max_chunk` (0 = as large as the scratch budget allows) bounds the trajectories per pipeline pass;
-// `before_chunk(t0, tn, s)` is called before the kernels of trajectories [t0, t0 + tn) are enqueued on
+// `before_chunk->wait(t0, tn, s)` is called before the kernels of trajectories [t0, t0 + tn) are enqueued on
 // stream s (the host entry point uses it to make s wait for that slice of the input copy).
 // With `stream2` the passes alternate between the two streams (each with its own candidate scratch):
 // a handful of candidates per pass run ~100x longer than the rest (f-g loops whose every Kepler solve
@@ -1158,9 +1193,7 @@ constexpr unsigned kMaxTriplets = 1024;
 // GPU idle until they finish; on two streams the next pass fills the machine meanwhile.
 static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *b,
                       OutfitIodResult *d_out, unsigned max_obs, cudaStream_t stream,
-                      unsigned long long max_chunk = 0,
-                      const std::function<void(unsigned long long, unsigned long long, cudaStream_t)> *before_chunk = nullptr,
-                      int n_streams = 1) {
+                      unsigned long long max_chunk = 0, const SliceWait *before_chunk = nullptr, int n_streams = 1) {
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
   if (max_obs > kMaxObsPerTraj) return fail(ctx, OUTFIT_E_UNSUPPORTED, "trajectory longer than 448 observations");
   if (params->max_triplets > kMaxTriplets) return fail(ctx, OUTFIT_E_UNSUPPORTED, "max_triplets > 1024");
@@ -1243,12 +1276,12 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
   for (unsigned long long t0 = 0; t0 < b->n_traj; t0 += chunk) {
     const unsigned long long tn = b->n_traj - t0 < chunk ? b->n_traj - t0 : chunk;
     cudaStream_t stream = st[n_chunks % ns];  // shadows the argument inside the pass
-    if (before_chunk) (*before_chunk)(t0, tn, stream);
+    if (before_chunk) before_chunk->wait(t0, tn, stream);
     IodBatchDev B;
     B.n_traj = tn; B.n_obs = n;
     B.traj_offset = reinterpret_cast<const unsigned long long *>(b->traj_offset) + t0;
     B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
-    B.helio = d_helio; B.scorer = d_scorer;
+    B.helio = d_helio; B.scorer = d_scorer; B.obs_status = d_status;
     B.noise_z = b->noise_z ? b->noise_z + (size_t)t0 * P.max_triplets * P.n_noise * 6 : nullptr;
     IodScratch S;
     S.n_cand = tn * cand_per_traj;
@@ -1274,24 +1307,32 @@ static int launch_iod(OutfitCtx *ctx, const OutfitIodParams *params, const Outfi
     }
     const unsigned tblocks = (unsigned)((tn + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const unsigned cblocks = (unsigned)((S.n_cand + kCandThreads - 1) / kCandThreads);
-    // thread per trajectory while a 128-thread block's heap columns fit in shared memory (K <= ~1300),
-    // else the warp-per-trajectory kernel
-    if ((size_t)P.max_triplets * 12 * 128 <= 160 * 1024 && ctx->triplets_per_thread) {
-      const size_t tsm = (size_t)P.max_triplets * 12 * 128;
-      if (tsm > 48 * 1024) CK(cudaFuncSetAttribute(triplets_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-      triplets_thread_kernel<<<(unsigned)((tn + 127) / 128), 128, tsm, stream>>>(B, P, S);
+    if (S.n_cand == 0) {
+      // max_triplets == 0: no candidate exists; select_kernel reports NoFeasibleTriplets like the reference
+      CK(cudaMemsetAsync(S.ktraj, 0, tn * 4, stream));
+      for (int q = 0; q < 4; ++q) mark();
     } else {
-      triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+      // thread per trajectory while the block's heap columns (12 B per slot and thread) fit in shared memory:
+      // 128 threads up to K = 106, 64 up to 213, 32 up to 426; beyond that the warp-per-trajectory kernel
+      unsigned ttpb = 128;
+      while (ttpb > 32 && (size_t)P.max_triplets * 12 * ttpb > 160 * 1024) ttpb >>= 1;
+      if ((size_t)P.max_triplets * 12 * ttpb <= 160 * 1024 && ctx->triplets_per_thread) {
+        const size_t tsm = (size_t)P.max_triplets * 12 * ttpb;
+        if (tsm > 48 * 1024) CK(cudaFuncSetAttribute(triplets_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        triplets_thread_kernel<<<(unsigned)((tn + ttpb - 1) / ttpb), ttpb, tsm, stream>>>(B, P, S);
+      } else {
+        triplets_kernel<<<tblocks, kWarpsPerBlock * 32, smem0, stream>>>(B, P, S, cap);
+      }
+      mark();
+      roots_kernel<<<cblocks, kCandThreads, 32 * kCandThreads * sizeof(double), stream>>>(B, P, S, ctx->d_counters + 1);
+      mark();
+      if (ctx->count_work) correct_kernel<true><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
+      else correct_kernel<false><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
+      mark();
+      if (ctx->count_work) score_kernel<true><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+      else score_kernel<false><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
+      mark();
     }
-    mark();
-    roots_kernel<<<cblocks, kCandThreads, 32 * kCandThreads * sizeof(double), stream>>>(B, P, S, ctx->d_counters + 1);
-    mark();
-    if (ctx->count_work) correct_kernel<true><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
-    else correct_kernel<false><<<cblocks, kCorrectThreads, kCorrectSmemBytes, stream>>>(B, P, S, ctx->d_counters + 1);
-    mark();
-    if (ctx->count_work) score_kernel<true><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
-    else score_kernel<false><<<cblocks, kCandThreads, 0, stream>>>(B, P, S, ctx->d_counters + 1);
-    mark();
     select_kernel<<<tblocks, kWarpsPerBlock * 32, 0, stream>>>(B, P, S, d_out + t0);
     mark();
     ++n_chunks;
@@ -1338,61 +1379,120 @@ extern "C" int outfit_b200_fit_full_iod_device(OutfitCtx *ctx, const OutfitIodPa
   return launch_iod(ctx, params, batch, out, max_obs, stream);
 }
 
-extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *params,
-                                        const OutfitObsBatch *hb, OutfitIodResult *out) {
-  if (!ctx || !params || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
-  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-  int rc = outfit_b200_iod_params_validate(params);
-  if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
-  if (hb->n_traj && (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec))
-    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
-  CK(cudaSetDevice(ctx->device));
-  const size_t T = hb->n_traj, n = hb->n_obs;
-  if (T == 0) return OUTFIT_OK;
-  unsigned max_obs = 0;
-  for (size_t t = 0; t < T; ++t) {
-    if (hb->traj_offset[t + 1] < hb->traj_offset[t] || hb->traj_offset[t + 1] > n)
+// (outfit_b200_fit_iod is defined after fit_full_iod_range below)
+// ---- host-buffer plumbing shared by the host entry points ---------------------------------------------
+// A host entry works on the trajectory range [tb, te) of the caller's batch (the whole batch for the
+// single-GPU entries, one shard of it for the multi-GPU group): the per-observation arrays of the range are a
+// contiguous slice [o0, o1) of the caller's arrays, the plane-major 3-vectors are three such slices at the
+// caller's plane stride (one 2-D copy), and traj_offset is re-based into a page-locked staging buffer.
+static int ensure_arena(OutfitCtx *ctx, size_t bytes) {
+  if (ctx->arena_bytes >= bytes) return OUTFIT_OK;
+  if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+  if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(batch arena)");
+  ctx->arena_bytes = bytes;
+  return OUTFIT_OK;
+}
+static int ensure_host_staging(OutfitCtx *ctx, size_t bytes) {
+  if (ctx->h_scratch_bytes >= bytes) return OUTFIT_OK;
+  if (ctx->h_scratch) { cudaFreeHost(ctx->h_scratch); ctx->h_scratch = nullptr; ctx->h_scratch_bytes = 0; }
+  if (cudaMallocHost(&ctx->h_scratch, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMallocHost(staging)");
+  ctx->h_scratch_bytes = bytes;
+  return OUTFIT_OK;
+}
+static int ensure_host_streams(OutfitCtx *ctx) {
+  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+  return OUTFIT_OK;
+}
+
+// traj_offset monotone within n_obs over [tb, te]; longest trajectory of the range
+static int check_offsets(OutfitCtx *ctx, const OutfitObsBatch *hb, size_t tb, size_t te, unsigned *max_obs) {
+  unsigned mo = 0;
+  for (size_t t = tb; t < te; ++t) {
+    if (hb->traj_offset[t + 1] < hb->traj_offset[t] || hb->traj_offset[t + 1] > hb->n_obs)
       return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "traj_offset is not monotone within n_obs");
     const unsigned long long c = hb->traj_offset[t + 1] - hb->traj_offset[t];
-    if (c > max_obs) max_obs = c > 0xffffffffull ? 0xffffffffu : (unsigned)c;
+    if (c > mo) mo = c > 0xffffffffull ? 0xffffffffu : (unsigned)c;
   }
+  if (max_obs) *max_obs = mo;
+  return OUTFIT_OK;
+}
+
+// carves the arena and enqueues the H2D copies of a trajectory range on `cs`
+struct ArenaPut {
+  unsigned char *arena;
+  size_t off = 0;
+  cudaStream_t cs;
+  cudaError_t err = cudaSuccess;
+  void *raw(size_t nbytes) {
+    void *dst = arena + off;
+    off += (nbytes + 255) & ~(size_t)255;
+    return dst;
+  }
+  void *put(const void *src, size_t nbytes) {
+    void *dst = raw(nbytes);
+    if (src && nbytes && err == cudaSuccess) err = cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs);
+    return dst;
+  }
+  // [3][n_all] plane-major source, columns [o0, o0 + n) -> [3][n]
+  void *put_planes(const double *src, size_t n_all, size_t o0, size_t n, int planes = 3) {
+    void *dst = raw((size_t)planes * n * 8);
+    if (src && n && err == cudaSuccess)
+      err = cudaMemcpy2DAsync(dst, n * 8, src + o0, n_all * 8, n * 8, (size_t)planes, cudaMemcpyHostToDevice, cs);
+    return dst;
+  }
+};
+
+static size_t iod_arena_bytes(const OutfitIodParams *params, const OutfitObsBatch *hb, size_t T, size_t n) {
+  const bool have_cache = hb->obs_helio_equ && hb->obs_geo_ecl;
+  const size_t n_noise_doubles = hb->noise_z ? T * (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
+  return (T + 1) * 8 + T * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 + T * sizeof(OutfitIodResult) + 16 * 256;
+}
+
+// FitIOD::fit_full_iod on the trajectories [tb, te) of the host batch; out = &results[tb]
+static int fit_full_iod_range(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *hb, size_t tb, size_t te,
+                              OutfitIodResult *out) {
+  const size_t T = te - tb;
+  if (T == 0) return OUTFIT_OK;
+  unsigned max_obs = 0;
+  int rc = check_offsets(ctx, hb, tb, te, &max_obs);
+  if (rc) return rc;
+  const size_t o0 = hb->traj_offset[tb], n = hb->traj_offset[te] - o0, n_all = hb->n_obs;
   const bool have_cache = hb->obs_helio_equ && hb->obs_geo_ecl;
   const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
   if (!have_cache && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_helio_equ+obs_geo_ecl or observer_body_fixed+mjd_ut1");
-  const size_t n_noise_doubles = hb->noise_z ? T * (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
+  const size_t per_traj_noise = hb->noise_z ? (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6 : 0;
+  const size_t n_noise_doubles = T * per_traj_noise;
   // one cached device arena for the inputs and the results (every sub-buffer 256-B aligned)
-  const size_t bytes = (T + 1) * 8 + T * 8 + 5 * n * 8 + (have_cache ? 6 : 4) * n * 8 + n_noise_doubles * 8 +
-                       T * sizeof(OutfitIodResult) + 16 * 256;
-  if (ctx->arena_bytes < bytes) {
-    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
-    if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(batch arena)");
-    ctx->arena_bytes = bytes;
-  }
-  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
-  unsigned char *arena = ctx->arena;
+  rc = ensure_arena(ctx, iod_arena_bytes(params, hb, T, n));
+  if (rc) return rc;
+  rc = ensure_host_streams(ctx);
+  if (rc) return rc;
   cudaStream_t cs = ctx->copy_stream, stream = ctx->compute_stream;
-  size_t off = 0;
-  auto put = [&](const void *src, size_t nbytes) -> void * {
-    void *dst = arena + off;
-    off += (nbytes + 255) & ~(size_t)255;
-    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, cs);
-    return dst;
-  };
+  ArenaPut A{ctx->arena, 0, cs};
   OutfitObsBatch db = *hb;
-  db.traj_offset = (const uint64_t *)put(hb->traj_offset, (T + 1) * 8);
-  db.mjd_tt = (const double *)put(hb->mjd_tt, n * 8);
-  db.ra = (const double *)put(hb->ra, n * 8);
-  db.dec = (const double *)put(hb->dec, n * 8);
-  db.sigma_ra = (const double *)put(hb->sigma_ra, n * 8);
-  db.sigma_dec = (const double *)put(hb->sigma_dec, n * 8);
+  db.n_traj = T; db.n_obs = n; db.max_obs_per_traj = max_obs;
+  if (o0 == 0) {
+    db.traj_offset = (const uint64_t *)A.put(hb->traj_offset + tb, (T + 1) * 8);
+  } else {  // re-base the offsets of the range
+    rc = ensure_host_staging(ctx, (T + 1) * 8);
+    if (rc) return rc;
+    uint64_t *h = reinterpret_cast<uint64_t *>(ctx->h_scratch);
+    for (size_t t = 0; t <= T; ++t) h[t] = hb->traj_offset[tb + t] - o0;
+    db.traj_offset = (const uint64_t *)A.put(h, (T + 1) * 8);
+  }
+  db.mjd_tt = (const double *)A.put(hb->mjd_tt + o0, n * 8);
+  db.ra = (const double *)A.put(hb->ra + o0, n * 8);
+  db.dec = (const double *)A.put(hb->dec + o0, n * 8);
+  db.sigma_ra = (const double *)A.put(hb->sigma_ra + o0, n * 8);
+  db.sigma_dec = (const double *)A.put(hb->sigma_dec + o0, n * 8);
   if (have_cache) {
-    db.obs_helio_equ = (const double *)put(hb->obs_helio_equ, 3 * n * 8);
-    db.obs_geo_ecl = (const double *)put(hb->obs_geo_ecl, 3 * n * 8);
+    db.obs_helio_equ = (const double *)A.put_planes(hb->obs_helio_equ, n_all, o0, n);
+    db.obs_geo_ecl = (const double *)A.put_planes(hb->obs_geo_ecl, n_all, o0, n);
     db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
   } else {
-    db.observer_body_fixed = (const double *)put(hb->observer_body_fixed, 3 * n * 8);
-    db.mjd_ut1 = (const double *)put(hb->mjd_ut1, n * 8);
+    db.observer_body_fixed = (const double *)A.put_planes(hb->observer_body_fixed, n_all, o0, n);
+    db.mjd_ut1 = (const double *)A.put(hb->mjd_ut1 + o0, n * 8);
     db.obs_helio_equ = nullptr; db.obs_geo_ecl = nullptr;
   }
   // The observation stream is small (88 B per observation); the noise deviates are the bulk of the
@@ -1410,28 +1510,24 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
     CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->copy_ev.push_back(e);
   }
-  db.traj_seed = (!n_noise_doubles && hb->traj_seed) ? (const uint64_t *)put(hb->traj_seed, T * 8) : nullptr;
+  db.traj_seed = (!n_noise_doubles && hb->traj_seed) ? (const uint64_t *)A.put(hb->traj_seed + tb, T * 8) : nullptr;
   CK(cudaEventRecord(ctx->copy_ev[0], cs));  // observation arrays (and seeds) are in flight up to here
   double *d_noise = nullptr;
   if (n_noise_doubles) {
-    d_noise = (double *)put(nullptr, n_noise_doubles * 8);
-    const size_t per_traj = (size_t)params->max_triplets * (size_t)params->n_noise_realizations * 6;
+    d_noise = (double *)A.raw(n_noise_doubles * 8);
+    const double *h_noise = hb->noise_z + tb * per_traj_noise;
     for (size_t sidx = 0; sidx < n_slices; ++sidx) {
       const size_t t0 = sidx * slice, t1 = t0 + slice < T ? t0 + slice : T;
-      if (t1 > t0)
-        cudaMemcpyAsync(d_noise + t0 * per_traj, hb->noise_z + t0 * per_traj, (t1 - t0) * per_traj * 8, cudaMemcpyHostToDevice, cs);
+      if (t1 > t0 && A.err == cudaSuccess)
+        A.err = cudaMemcpyAsync(d_noise + t0 * per_traj_noise, h_noise + t0 * per_traj_noise, (t1 - t0) * per_traj_noise * 8, cudaMemcpyHostToDevice, cs);
       CK(cudaEventRecord(ctx->copy_ev[sidx + 1], cs));
     }
   }
   db.noise_z = d_noise;
-  OutfitIodResult *d_out = (OutfitIodResult *)put(nullptr, T * sizeof(OutfitIodResult));
+  OutfitIodResult *d_out = (OutfitIodResult *)A.raw(T * sizeof(OutfitIodResult));
+  if (A.err != cudaSuccess) { cudaStreamSynchronize(cs); return fail(ctx, OUTFIT_E_CUDA, "fit_full_iod: H2D", A.err); }
   CK(cudaStreamWaitEvent(stream, ctx->copy_ev[0], 0));
-  const std::function<void(unsigned long long, unsigned long long, cudaStream_t)> wait_slice =
-      [&](unsigned long long t0, unsigned long long tn, cudaStream_t s) {
-        if (!n_noise_doubles) return;
-        const size_t last = (size_t)((t0 + tn - 1) / slice);
-        cudaStreamWaitEvent(s, ctx->copy_ev[(last < n_slices ? last : n_slices - 1) + 1], 0);
-      };
+  const SliceWait wait_slice{n_noise_doubles ? ctx->copy_ev.data() + 1 : nullptr, slice, n_slices};
   rc = launch_iod(ctx, params, &db, d_out, max_obs, stream, n_slices > 1 ? slice : 0, &wait_slice,
                   n_slices > 1 ? ctx->n_streams : 1);
   if (rc == OUTFIT_OK) {
@@ -1443,6 +1539,25 @@ extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *p
     cudaStreamSynchronize(cs);
   }
   return rc;
+}
+
+static int check_iod_host_args(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *hb, const void *out) {
+  if (!ctx || !params || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  int rc = outfit_b200_iod_params_validate(params);
+  if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
+  if (hb->n_traj && (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec))
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_fit_full_iod(OutfitCtx *ctx, const OutfitIodParams *params,
+                                        const OutfitObsBatch *hb, OutfitIodResult *out) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int rc = check_iod_host_args(ctx, params, hb, out);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return fit_full_iod_range(ctx, params, hb, 0, hb->n_traj, out);
 }
 
 extern "C" void outfit_b200_lsq_config_default(OutfitLsqConfig *c) {  // diff_cor.rs:175-192
@@ -1518,7 +1633,7 @@ extern "C" int outfit_b200_fit_lsq_device(OutfitCtx *ctx, const OutfitLsqConfig 
   LsqBatchDev B;
   B.n_traj = b->n_traj; B.n_obs = n; B.traj_offset = (const unsigned long long *)b->traj_offset;
   B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
-  B.scorer = d_scorer;
+  B.scorer = d_scorer; B.obs_status = d_status;
   unsigned long long *d_next = reinterpret_cast<unsigned long long *>(d_status + ((n + 1) & ~(size_t)1));
   CK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream));
   const unsigned long long want = (b->n_traj + 63) / 64;
@@ -1528,69 +1643,82 @@ extern "C" int outfit_b200_fit_lsq_device(OutfitCtx *ctx, const OutfitLsqConfig 
   return OUTFIT_OK;
 }
 
-extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
-                                   const OutfitObsBatch *hb, const OutfitIodResult *iod, OutfitLsqResult *out,
-                                   OutfitObsFit *fit) {
-  if (!ctx || !cfg || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
-  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-  if (!iod && !iod_params) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq: iod results or iod_params are required");
-  const size_t T = hb->n_traj, n = hb->n_obs;
+// FitLSQ::fit_lsq on the trajectories [tb, te) of the host batch; iod / out = &records[tb], fit = &fit[0]
+// (indexed by the batch's global observation index).  The results (776 B per trajectory + 32 B per
+// observation) are ~8x the input: the two arrays come back concurrently on two streams.
+static int fit_lsq_range(OutfitCtx *ctx, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
+                         const OutfitObsBatch *hb, size_t tb, size_t te, const OutfitIodResult *iod,
+                         OutfitLsqResult *out, OutfitObsFit *fit) {
+  const size_t T = te - tb;
   if (T == 0) return OUTFIT_OK;
-  if (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec)
-    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  int rc = check_offsets(ctx, hb, tb, te, nullptr);
+  if (rc) return rc;
   std::vector<OutfitIodResult> own_iod;
   if (!iod) {  // initial_orbits = None: run the IOD first (mod.rs:80)
     own_iod.resize(T);
-    const int rc = outfit_b200_fit_full_iod(ctx, iod_params, hb, own_iod.data());
+    rc = fit_full_iod_range(ctx, iod_params, hb, tb, te, own_iod.data());
     if (rc) return rc;
     iod = own_iod.data();
   }
-  CK(cudaSetDevice(ctx->device));
+  const size_t o0 = hb->traj_offset[tb], n = hb->traj_offset[te] - o0, n_all = hb->n_obs;
   const bool have_geo = hb->obs_geo_ecl != nullptr;
   const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
   if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
-  if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
-  cudaStream_t stream = ctx->compute_stream;
+  rc = ensure_host_streams(ctx);
+  if (rc) return rc;
+  cudaStream_t stream = ctx->compute_stream, cs = ctx->copy_stream;
   const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_geo ? 3 : 4) * n * 8 + T * sizeof(OutfitIodResult) +
                        T * sizeof(OutfitLsqResult) + n * sizeof(OutfitObsFit) + 16 * 256;
   // the context's cached input arena (shared with the IOD host entry, whose use of it has ended by now)
-  if (ctx->arena_bytes < bytes) {
-    if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
-    if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(fit_lsq arena)");
-    ctx->arena_bytes = bytes;
-  }
-  unsigned char *arena = ctx->arena;
-  size_t off = 0;
-  auto put = [&](const void *src, size_t nbytes) -> void * {
-    void *dst = arena + off;
-    off += (nbytes + 255) & ~(size_t)255;
-    if (src && nbytes) cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream);
-    return dst;
-  };
+  rc = ensure_arena(ctx, bytes);
+  if (rc) return rc;
+  ArenaPut A{ctx->arena, 0, stream};
   OutfitObsBatch db = *hb;
-  db.traj_offset = (const uint64_t *)put(hb->traj_offset, (T + 1) * 8);
-  db.mjd_tt = (const double *)put(hb->mjd_tt, n * 8);
-  db.ra = (const double *)put(hb->ra, n * 8);
-  db.dec = (const double *)put(hb->dec, n * 8);
-  db.sigma_ra = (const double *)put(hb->sigma_ra, n * 8);
-  db.sigma_dec = (const double *)put(hb->sigma_dec, n * 8);
+  db.n_traj = T; db.n_obs = n;
+  if (o0 == 0) {
+    db.traj_offset = (const uint64_t *)A.put(hb->traj_offset + tb, (T + 1) * 8);
+  } else {
+    rc = ensure_host_staging(ctx, (T + 1) * 8);
+    if (rc) return rc;
+    uint64_t *h = reinterpret_cast<uint64_t *>(ctx->h_scratch);
+    for (size_t t = 0; t <= T; ++t) h[t] = hb->traj_offset[tb + t] - o0;
+    db.traj_offset = (const uint64_t *)A.put(h, (T + 1) * 8);
+  }
+  db.mjd_tt = (const double *)A.put(hb->mjd_tt + o0, n * 8);
+  db.ra = (const double *)A.put(hb->ra + o0, n * 8);
+  db.dec = (const double *)A.put(hb->dec + o0, n * 8);
+  db.sigma_ra = (const double *)A.put(hb->sigma_ra + o0, n * 8);
+  db.sigma_dec = (const double *)A.put(hb->sigma_dec + o0, n * 8);
   db.obs_helio_equ = nullptr; db.noise_z = nullptr; db.traj_seed = nullptr;
   if (have_geo) {
-    db.obs_geo_ecl = (const double *)put(hb->obs_geo_ecl, 3 * n * 8);
+    db.obs_geo_ecl = (const double *)A.put_planes(hb->obs_geo_ecl, n_all, o0, n);
     db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
   } else {
     db.obs_geo_ecl = nullptr;
-    db.observer_body_fixed = (const double *)put(hb->observer_body_fixed, 3 * n * 8);
-    db.mjd_ut1 = (const double *)put(hb->mjd_ut1, n * 8);
+    db.observer_body_fixed = (const double *)A.put_planes(hb->observer_body_fixed, n_all, o0, n);
+    db.mjd_ut1 = (const double *)A.put(hb->mjd_ut1 + o0, n * 8);
   }
-  const OutfitIodResult *d_iod = (const OutfitIodResult *)put(iod, T * sizeof(OutfitIodResult));
-  OutfitLsqResult *d_out = (OutfitLsqResult *)put(nullptr, T * sizeof(OutfitLsqResult));
-  OutfitObsFit *d_fit = (OutfitObsFit *)put(nullptr, n * sizeof(OutfitObsFit));
-  int rc = outfit_b200_fit_lsq_device(ctx, cfg, &db, d_iod, d_out, d_fit, stream);
+  const OutfitIodResult *d_iod = (const OutfitIodResult *)A.put(iod, T * sizeof(OutfitIodResult));
+  OutfitLsqResult *d_out = (OutfitLsqResult *)A.raw(T * sizeof(OutfitLsqResult));
+  OutfitObsFit *d_fit = (OutfitObsFit *)A.raw(n * sizeof(OutfitObsFit));
+  if (A.err != cudaSuccess) { cudaStreamSynchronize(stream); return fail(ctx, OUTFIT_E_CUDA, "fit_lsq: H2D", A.err); }
+  rc = outfit_b200_fit_lsq_device(ctx, cfg, &db, d_iod, d_out, d_fit, stream);
   if (rc == OUTFIT_OK) {
-    cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitLsqResult), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && fit) e = cudaMemcpyAsync(fit, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, stream);
+    // two copy engines: the per-trajectory records on the compute stream, the per-observation fit array on the
+    // copy stream behind an event
+    while (ctx->copy_ev.size() < 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->copy_ev.push_back(e);
+    }
+    cudaError_t e = cudaEventRecord(ctx->copy_ev[0], stream);
+    if (e == cudaSuccess && fit) {
+      e = cudaStreamWaitEvent(cs, ctx->copy_ev[0], 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(fit + o0, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, cs);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitLsqResult), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
     if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "fit_lsq: copy back / kernel", e);
   } else {
     cudaStreamSynchronize(stream);
@@ -1598,11 +1726,48 @@ extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_pa
   return rc;
 }
 
+extern "C" int outfit_b200_fit_iod(OutfitCtx *ctx, const OutfitIodParams *params, const OutfitObsBatch *hb,
+                                   uint64_t traj_index, OutfitIodResult *out) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int rc = check_iod_host_args(ctx, params, hb, out);
+  if (rc) return rc;
+  if (traj_index >= hb->n_traj) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_iod: no such trajectory");
+  CK(cudaSetDevice(ctx->device));
+  return fit_full_iod_range(ctx, params, hb, traj_index, traj_index + 1, out);
+}
+
+static int check_lsq_host_args(OutfitCtx *ctx, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
+                               const OutfitObsBatch *hb, const OutfitIodResult *iod, const void *out) {
+  if (!ctx || !cfg || !hb || (!out && hb->n_traj)) return OUTFIT_E_INVALID_ARGUMENT;
+  if (!iod && !iod_params) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq: iod results or iod_params are required");
+  if (!iod) {
+    const int rc = outfit_b200_iod_params_validate(iod_params);
+    if (rc) return fail(ctx, rc, "IODParams validation failed (mod.rs:544-624)");
+  }
+  if (hb->n_traj && (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec))
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_fit_lsq(OutfitCtx *ctx, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
+                                   const OutfitObsBatch *hb, const OutfitIodResult *iod, OutfitLsqResult *out,
+                                   OutfitObsFit *fit) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int rc = check_lsq_host_args(ctx, iod_params, cfg, hb, iod, out);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return fit_lsq_range(ctx, iod_params, cfg, hb, 0, hb->n_traj, iod, out, fit);
+}
+
 extern "C" int outfit_b200_last_iod_counters(OutfitCtx *ctx, OutfitIodCounters *out) {
   if (!ctx || !out) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   unsigned long long h[32];
+  // the launch may sit on non-blocking streams, which a legacy-stream copy does not wait for
+  CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
   // order of struct Work (dev_kepler.cuh)
   out->gauss_solves = h[1]; out->aberth_sweeps = h[2]; out->roots_accepted = h[3]; out->fg_iterations = h[4];
@@ -1686,36 +1851,114 @@ extern "C" int outfit_b200_propagate_universal_device(OutfitCtx *ctx, size_t n, 
   return OUTFIT_OK;
 }
 
+// ---- three-stage ring for the bulk host entries: H2D (copy stream) -> kernels (compute stream) -> D2H
+// (d2h stream), kRing chunks in flight, every chunk in its own slot of the cached arena.  PCIe is full duplex,
+// so the upload of chunk j+1 and the download of chunk j-1 run under the kernels of chunk j.
+constexpr int kRing = 3;
+static int ensure_ring(OutfitCtx *ctx) {
+  int rc = ensure_host_streams(ctx);
+  if (rc) return rc;
+  if (!ctx->d2h_stream) CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 3 * kRing; ++i)
+    if (!ctx->ring_ev[i]) CK(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+  return OUTFIT_OK;
+}
+
+// kepler::propagate_universal over the columns [i0, i1) of the caller's plane-major arrays (n_all columns)
+static int propagate_range(OutfitCtx *ctx, size_t n_all, size_t i0, size_t i1, const double *rv, const double *t0,
+                           const double *t1, const double *psi_guess, const OutfitSolverType *solver, double *out,
+                           int32_t *status) {
+  if (i1 <= i0) return OUTFIT_OK;
+  int rc = ensure_ring(ctx);
+  if (rc) return rc;
+  const size_t n = i1 - i0;
+  size_t chunk = (size_t)1 << 20;
+  if (const char *ev = getenv("OUTFIT_B200_PROP_CHUNK")) { const long v = atol(ev); if (v >= 1024) chunk = (size_t)v; }
+  if (chunk > n) chunk = n;
+  const size_t in_pl = 8 + (psi_guess ? 1 : 0);
+  const size_t slot_bytes = ((in_pl + 11) * chunk * 8 + chunk * 4 + 4 * 256 + 255) & ~(size_t)255;
+  rc = ensure_arena(ctx, slot_bytes * kRing);
+  if (rc) return rc;
+  cudaStream_t up = ctx->copy_stream, run = ctx->compute_stream, down = ctx->d2h_stream;
+  cudaError_t e = cudaSuccess;
+  size_t j = 0;
+  for (size_t c0 = i0; c0 < i1 && e == cudaSuccess; c0 += chunk, ++j) {
+    const size_t c = i1 - c0 < chunk ? i1 - c0 : chunk;
+    const int sl = (int)(j % kRing);
+    cudaEvent_t ev_up = ctx->ring_ev[3 * sl], ev_run = ctx->ring_ev[3 * sl + 1], ev_down = ctx->ring_ev[3 * sl + 2];
+    unsigned char *base = ctx->arena + (size_t)sl * slot_bytes;
+    double *d_rv = reinterpret_cast<double *>(base), *d_t0 = d_rv + 6 * c, *d_t1 = d_rv + 7 * c;
+    double *d_pg = psi_guess ? d_rv + 8 * c : nullptr, *d_out = d_rv + in_pl * c;
+    int *d_st = reinterpret_cast<int *>(d_out + 11 * c);
+    if (j >= (size_t)kRing) e = cudaStreamWaitEvent(up, ev_down, 0);  // the slot's previous results have left
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_rv, c * 8, rv + c0, n_all * 8, c * 8, 6, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t0, t0 + c0, c * 8, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t1, t1 + c0, c * 8, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess && psi_guess) e = cudaMemcpyAsync(d_pg, psi_guess + c0, c * 8, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_up, up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(run, ev_up, 0);
+    if (e != cudaSuccess) break;
+    rc = outfit_b200_propagate_universal_device(ctx, c, d_rv, d_t0, d_t1, d_pg, solver, d_out, d_st, run);
+    if (rc) break;
+    e = cudaEventRecord(ev_run, run);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(down, ev_run, 0);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(out + c0, n_all * 8, d_out, c * 8, c * 8, 11, cudaMemcpyDeviceToHost, down);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status + c0, d_st, c * sizeof(int), cudaMemcpyDeviceToHost, down);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_down, down);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(up);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(run);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(down);
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "propagate_universal: copy / kernel", e != cudaSuccess ? e : e2);
+  return OUTFIT_OK;
+}
+
 extern "C" int outfit_b200_propagate_universal(OutfitCtx *ctx, size_t n, const double *rv, const double *t0,
                                                const double *t1, const double *psi_guess,
                                                const OutfitSolverType *solver, double *out, int32_t *status) {
   if (!ctx || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
-  if (n == 0) return OUTFIT_OK;
-  const size_t in_d = (8 + (psi_guess ? 1 : 0)) * n, out_d = 11 * n;
-  double *d = nullptr;
-  if (cudaMalloc(&d, (in_d + out_d) * 8 + n * sizeof(int)) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(propagation)");
-  double *d_rv = d, *d_t0 = d + 6 * n, *d_t1 = d + 7 * n, *d_pg = psi_guess ? d + 8 * n : nullptr, *d_out = d + in_d;
-  int *d_st = reinterpret_cast<int *>(d_out + out_d);
-  int rc = OUTFIT_OK;
-  cudaError_t e = cudaMemcpyAsync(d_rv, rv, 6 * n * 8, cudaMemcpyHostToDevice, 0);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t0, t0, n * 8, cudaMemcpyHostToDevice, 0);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t1, t1, n * 8, cudaMemcpyHostToDevice, 0);
-  if (e == cudaSuccess && psi_guess) e = cudaMemcpyAsync(d_pg, psi_guess, n * 8, cudaMemcpyHostToDevice, 0);
-  if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_universal: H2D", e);
-  if (rc == OUTFIT_OK) rc = outfit_b200_propagate_universal_device(ctx, n, d_rv, d_t0, d_t1, d_pg, solver, d_out, d_st, nullptr);
-  if (rc == OUTFIT_OK) {
-    e = cudaMemcpyAsync(out, d_out, out_d * 8, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n * sizeof(int), cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_universal: D2H / kernel", e);
-  }
-  cudaFree(d);
-  return rc;
+  return propagate_range(ctx, n, 0, n, rv, t0, t1, psi_guess, solver, out, status);
 }
 
 // ---- two-body Combined ephemeris (ephemeris/mod.rs:189-292) -------------------------------------------
+// observer table [9][e_stride] + status[e_stride] in the context scratch (rows 16-byte aligned), one thread per
+// epoch.  d_bf = device [3][n_epochs] per-epoch body-fixed positions (a request with several observers) or null
+// (one observer: bf[3]).
+static int ephemeris_observer_table(OutfitCtx *ctx, size_t n_epochs, const double *mjd_tt, const double *mjd_ut1,
+                                    const double *d_bf, const double bf[3], cudaStream_t stream, size_t *e_stride_out,
+                                    double **d_table_out, int **d_ost_out) {
+  const size_t e_stride = (n_epochs + 1) & ~(size_t)1;
+  int rc = ensure_scratch(ctx, 9 * e_stride * sizeof(double) + e_stride * sizeof(int) + 256);
+  if (rc) return rc;
+  double *d_table = reinterpret_cast<double *>(ctx->scratch);
+  int *d_ost = reinterpret_cast<int *>(d_table + 9 * e_stride);
+  ephemeris_observer_kernel<<<(unsigned)((e_stride + 127) / 128), 128, 0, stream>>>(
+      ctx->eph, n_epochs, e_stride, mjd_tt, mjd_ut1, d_bf, bf ? bf[0] : 0.0, bf ? bf[1] : 0.0, bf ? bf[2] : 0.0, d_table, d_ost);
+  *e_stride_out = e_stride; *d_table_out = d_table; *d_ost_out = d_ost;
+  return OUTFIT_OK;
+}
+
+static int ephemeris_device_impl(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                 const double *elem, size_t n_epochs, const double *mjd_tt, const double *mjd_ut1,
+                                 const double *d_bf, const double bf[3], double *out, int32_t *status, cudaStream_t stream) {
+  if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  CK(cudaSetDevice(ctx->device));
+  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
+  size_t e_stride;
+  double *d_table;
+  int *d_ost;
+  int rc = ephemeris_observer_table(ctx, n_epochs, mjd_tt, mjd_ut1, d_bf, bf, stream, &e_stride, &d_table, &d_ost);
+  if (rc) return rc;
+  ephemeris_twobody_kernel<<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
+      n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
 extern "C" int outfit_b200_ephemeris_twobody_device(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind,
                                                     const double *epoch, const double *elem, size_t n_epochs,
                                                     const double *mjd_tt, const double *mjd_ut1,
@@ -1723,22 +1966,85 @@ extern "C" int outfit_b200_ephemeris_twobody_device(OutfitCtx *ctx, size_t n_orb
                                                     void *cuda_stream) {
   if (!ctx || !body_fixed) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-  if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  return ephemeris_device_impl(ctx, n_orbits, kind, epoch, elem, n_epochs, mjd_tt, mjd_ut1, nullptr, body_fixed, out, status,
+                               reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int outfit_b200_ephemeris_request_device(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind,
+                                                    const double *epoch, const double *elem, size_t n_epochs,
+                                                    const double *mjd_tt, const double *mjd_ut1,
+                                                    const double *epoch_body_fixed, double *out, int32_t *status,
+                                                    void *cuda_stream) {
+  if (!ctx || (n_epochs && !epoch_body_fixed)) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  return ephemeris_device_impl(ctx, n_orbits, kind, epoch, elem, n_epochs, mjd_tt, mjd_ut1, epoch_body_fixed, nullptr, out, status,
+                               reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+// Host entry over the orbits [i0, i1) of the caller's arrays (n_all orbits = the plane stride of elem / out /
+// status): epochs and the observer table once, then the orbits in chunks through the three-stage ring.  The
+// output is 76 B per (orbit, epoch) entry against ~600 flop: end to end this call is bound by the D2H copy.
+// h_bf: host [3][n_epochs] per-epoch body-fixed observer positions (several observers) or null (-> bf[3]).
+static int ephemeris_range(OutfitCtx *ctx, size_t n_all, size_t i0, size_t i1, const int32_t *kind, const double *epoch,
+                           const double *elem, size_t n_epochs, const double *mjd_tt, const double *mjd_ut1,
+                           const double *h_bf, const double bf[3], double *out, int32_t *status) {
+  if (i1 <= i0 || n_epochs == 0) return OUTFIT_OK;
   if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
-  CK(cudaSetDevice(ctx->device));
-  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-  // observer table [9][e_stride] + status[e_stride] in the context scratch (rows 16-byte aligned)
-  const size_t e_stride = (n_epochs + 1) & ~(size_t)1;
-  int rc = ensure_scratch(ctx, 9 * e_stride * sizeof(double) + e_stride * sizeof(int) + 256);
+  int rc = ensure_ring(ctx);
   if (rc) return rc;
-  double *d_table = reinterpret_cast<double *>(ctx->scratch);
-  int *d_ost = reinterpret_cast<int *>(d_table + 9 * e_stride);
-  ephemeris_observer_kernel<<<(unsigned)((e_stride + 127) / 128), 128, 0, stream>>>(
-      ctx->eph, n_epochs, e_stride, mjd_tt, mjd_ut1, body_fixed[0], body_fixed[1], body_fixed[2], d_table, d_ost);
-  ephemeris_twobody_kernel<<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
-      n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
-  CK(cudaGetLastError());
+  const size_t n = i1 - i0;
+  // chunk: ~256 MB of output per slot
+  size_t chunk = ((size_t)256 << 20) / (76 * n_epochs);
+  chunk = chunk < 1024 ? 1024 : (chunk & ~(size_t)127);
+  if (const char *ev = getenv("OUTFIT_B200_EPH_CHUNK")) { const long v = atol(ev); if (v >= 128) chunk = (size_t)v; }
+  if (chunk > n) chunk = n;
+  const size_t head_bytes = ((5 * n_epochs * 8 + 255) & ~(size_t)255) + 256;
+  const size_t slot_bytes = ((chunk * 4 + 255) & ~(size_t)255) + ((7 * chunk * 8 + 255) & ~(size_t)255) +
+                            ((9 * n_epochs * chunk * 8 + 255) & ~(size_t)255) + ((n_epochs * chunk * 4 + 255) & ~(size_t)255);
+  rc = ensure_arena(ctx, head_bytes + slot_bytes * kRing);
+  if (rc) return rc;
+  cudaStream_t up = ctx->copy_stream, run = ctx->compute_stream, down = ctx->d2h_stream;
+  double *d_tt = reinterpret_cast<double *>(ctx->arena), *d_ut = d_tt + n_epochs, *d_bf = h_bf ? d_ut + n_epochs : nullptr;
+  cudaError_t e = cudaMemcpyAsync(d_tt, mjd_tt, n_epochs * 8, cudaMemcpyHostToDevice, run);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ut, mjd_ut1, n_epochs * 8, cudaMemcpyHostToDevice, run);
+  if (e == cudaSuccess && h_bf) e = cudaMemcpyAsync(d_bf, h_bf, 3 * n_epochs * 8, cudaMemcpyHostToDevice, run);
+  if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: H2D", e);
+  size_t e_stride;
+  double *d_table;
+  int *d_ost;
+  rc = ephemeris_observer_table(ctx, n_epochs, d_tt, d_ut, d_bf, bf, run, &e_stride, &d_table, &d_ost);
+  if (rc) return rc;
+  size_t j = 0;
+  for (size_t c0 = i0; c0 < i1 && e == cudaSuccess; c0 += chunk, ++j) {
+    const size_t c = i1 - c0 < chunk ? i1 - c0 : chunk;
+    const int sl = (int)(j % kRing);
+    cudaEvent_t ev_up = ctx->ring_ev[3 * sl], ev_run = ctx->ring_ev[3 * sl + 1], ev_down = ctx->ring_ev[3 * sl + 2];
+    unsigned char *base = ctx->arena + head_bytes + (size_t)sl * slot_bytes;
+    int32_t *d_kind = reinterpret_cast<int32_t *>(base);
+    double *d_epoch = reinterpret_cast<double *>(base + ((chunk * 4 + 255) & ~(size_t)255));
+    double *d_elem = d_epoch + c;
+    double *d_out = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(d_epoch) + ((7 * chunk * 8 + 255) & ~(size_t)255));
+    int32_t *d_st = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(d_out) + ((9 * n_epochs * chunk * 8 + 255) & ~(size_t)255));
+    if (j >= (size_t)kRing) e = cudaStreamWaitEvent(up, ev_down, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_kind, kind + c0, c * 4, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_epoch, epoch + c0, c * 8, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_elem, c * 8, elem + c0, n_all * 8, c * 8, 6, cudaMemcpyHostToDevice, up);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_up, up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(run, ev_up, 0);
+    if (e != cudaSuccess) break;
+    ephemeris_twobody_kernel<<<(unsigned)((c + kEphThreads - 1) / kEphThreads), kEphThreads, 0, run>>>(
+        c, d_kind, d_epoch, d_elem, n_epochs, e_stride, d_tt, d_table, d_ost, d_out, d_st);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventRecord(ev_run, run);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(down, ev_run, 0);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(out + c0, n_all * 8, d_out, c * 8, c * 8, 9 * n_epochs, cudaMemcpyDeviceToHost, down);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(status + c0, n_all * 4, d_st, c * 4, c * 4, n_epochs, cudaMemcpyDeviceToHost, down);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_down, down);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(up);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(run);
+  if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(down);
+  if (e != cudaSuccess || e2 != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: copy / kernel", e != cudaSuccess ? e : e2);
   return OUTFIT_OK;
 }
 
@@ -1750,38 +2056,256 @@ extern "C" int outfit_b200_ephemeris_twobody(OutfitCtx *ctx, size_t n_orbits, co
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
-  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
-  const size_t n_ent = n_orbits * n_epochs;
-  const size_t in_bytes = ((n_orbits * 4 + 255) & ~(size_t)255) + ((n_orbits * 8 + 255) & ~(size_t)255) +
-                          ((6 * n_orbits * 8 + 255) & ~(size_t)255) + 2 * ((n_epochs * 8 + 255) & ~(size_t)255);
-  unsigned char *d = nullptr;
-  if (cudaMalloc(&d, in_bytes + 9 * n_ent * 8 + n_ent * 4 + 1024) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(ephemeris)");
-  size_t off = 0;
-  cudaError_t e = cudaSuccess;
-  auto put = [&](const void *src, size_t nbytes) -> void * {
-    void *dst = d + off;
-    off += (nbytes + 255) & ~(size_t)255;
-    if (src && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, 0);
-    return dst;
-  };
-  const int32_t *d_kind = (const int32_t *)put(kind, n_orbits * 4);
-  const double *d_epoch = (const double *)put(epoch, n_orbits * 8);
-  const double *d_elem = (const double *)put(elem, 6 * n_orbits * 8);
-  const double *d_tt = (const double *)put(mjd_tt, n_epochs * 8);
-  const double *d_ut1 = (const double *)put(mjd_ut1, n_epochs * 8);
-  double *d_out = (double *)put(nullptr, 9 * n_ent * 8);
-  int32_t *d_st = (int32_t *)put(nullptr, n_ent * 4);
-  int rc = e == cudaSuccess ? OUTFIT_OK : fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: H2D", e);
-  if (rc == OUTFIT_OK)
-    rc = outfit_b200_ephemeris_twobody_device(ctx, n_orbits, d_kind, d_epoch, d_elem, n_epochs, d_tt, d_ut1, body_fixed, d_out, d_st, nullptr);
-  if (rc == OUTFIT_OK) {
-    e = cudaMemcpyAsync(out, d_out, 9 * n_ent * 8, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n_ent * 4, cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "ephemeris_twobody: D2H / kernel", e);
+  return ephemeris_range(ctx, n_orbits, 0, n_orbits, kind, epoch, elem, n_epochs, mjd_tt, mjd_ut1, nullptr, body_fixed, out, status);
+}
+
+// EphemerisRequest with several (observer, epochs) pairs (ephemeris/request.rs:276-340, mod.rs:242-290): the
+// epochs of all observers concatenated in request order, observer o owning [epoch_offset[o], epoch_offset[o+1]).
+static int expand_request(OutfitCtx *ctx, size_t n_observers, const double *observer_body_fixed, const uint64_t *epoch_offset,
+                          std::vector<double> &bf_planes, size_t *n_epochs) {
+  if (!observer_body_fixed || !epoch_offset || epoch_offset[0] != 0) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "ephemeris_request: observers / epoch_offset");
+  for (size_t o = 0; o < n_observers; ++o)
+    if (epoch_offset[o + 1] < epoch_offset[o]) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "ephemeris_request: epoch_offset is not monotone");
+  const size_t E = epoch_offset[n_observers];
+  bf_planes.resize(3 * E);
+  for (size_t o = 0; o < n_observers; ++o)
+    for (size_t e = epoch_offset[o]; e < epoch_offset[o + 1]; ++e)
+      for (int q = 0; q < 3; ++q) bf_planes[(size_t)q * E + e] = observer_body_fixed[3 * o + q];
+  *n_epochs = E;
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_ephemeris_request(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                             const double *elem, size_t n_observers, const double *observer_body_fixed,
+                                             const uint64_t *epoch_offset, const double *mjd_tt, const double *mjd_ut1,
+                                             double *out, int32_t *status) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (n_observers == 0 || n_orbits == 0) return OUTFIT_OK;
+  std::vector<double> bfp;
+  size_t E = 0;
+  int rc = expand_request(ctx, n_observers, observer_body_fixed, epoch_offset, bfp, &E);
+  if (rc) return rc;
+  if (E && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  return ephemeris_range(ctx, n_orbits, 0, n_orbits, kind, epoch, elem, E, mjd_tt, mjd_ut1, bfp.data(), nullptr, out, status);
+}
+
+// =================================================================================================
+// multi-GPU group: ONE call drives every GPU of the box, like fit_full_iod_parallel drives every core
+// (obs_dataset_api.rs:175-207).  Trajectories are independent, so the batch is cut into contiguous
+// trajectory ranges of near-equal estimated work, one per GPU; one host thread per GPU runs the
+// single-GPU host entry on its range (own context, arena, streams), and every result lands at its global
+// trajectory index in the caller's array.  No collective, no peer traffic: the only shared resource is the
+// host memory the ranges are read from.
+// =================================================================================================
+struct OutfitGroup {
+  std::vector<OutfitCtx *> ctx;
+  std::vector<float> shard_ms;                 // wall time of every shard in the last group call
+  std::vector<unsigned long long> shard_cut;   // trajectory / item cuts of the last group call [n + 1]
+  std::string last_error;
+  std::mutex mu;
+};
+
+// Relative cost of a trajectory of n observations: candidates x (Gauss solve + f-g + arc scoring) + enumeration
+static double traj_work(double n, double K, double M) {
+  const double feasible = n * (n - 1.0) * (n - 2.0) / 6.0;
+  const double k = feasible < K ? (feasible > 0.0 ? feasible : 0.0) : K;
+  return k * M * (60.0 + n) + 0.05 * (feasible > 0.0 ? feasible : 0.0) + 1.0;
+}
+
+extern "C" int outfit_b200_shard_ranges(uint64_t n_traj, const uint64_t *traj_offset, uint32_t max_triplets,
+                                        uint64_t n_noise_realizations, int n_parts, uint64_t *cuts) {
+  if (n_parts < 1 || !cuts || (n_traj && !traj_offset)) return OUTFIT_E_INVALID_ARGUMENT;
+  const double K = (double)max_triplets, M = 1.0 + (double)n_noise_realizations;
+  double total = 0.0;
+  for (uint64_t t = 0; t < n_traj; ++t) total += traj_work((double)(traj_offset[t + 1] - traj_offset[t]), K, M);
+  cuts[0] = 0;
+  double acc = 0.0;
+  int r = 1;
+  for (uint64_t t = 0; t < n_traj && r < n_parts; ++t) {
+    acc += traj_work((double)(traj_offset[t + 1] - traj_offset[t]), K, M);
+    // first prefix that reaches r / n_parts of the total work ends part r - 1 BEFORE trajectory t
+    // (numpy searchsorted(cumsum, total * r / n, side="left") of outfit_b200/shard.py)
+    while (r < n_parts && acc >= total * (double)r / (double)n_parts) cuts[r++] = t;
   }
-  cudaFree(d);
-  return rc;
+  while (r < n_parts) cuts[r++] = n_traj;
+  cuts[n_parts] = n_traj;
+  for (int i = 1; i <= n_parts; ++i)
+    if (cuts[i] < cuts[i - 1]) cuts[i] = cuts[i - 1];
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_init_multi(int n_gpus, const int *device_ids, OutfitGroup **out) {
+  if (!out) return OUTFIT_E_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return OUTFIT_E_NO_DEVICE;
+  if (n_gpus <= 0) { n_gpus = n_dev; device_ids = nullptr; }
+  if (!device_ids && n_gpus > n_dev) return OUTFIT_E_INVALID_ARGUMENT;
+  OutfitGroup *g = new (std::nothrow) OutfitGroup();
+  if (!g) return OUTFIT_E_ALLOC;
+  for (int i = 0; i < n_gpus; ++i) {
+    const int dev = device_ids ? device_ids[i] : i;
+    OutfitCtx *c = nullptr;
+    const int rc = (dev < 0 || dev >= n_dev) ? OUTFIT_E_INVALID_ARGUMENT : outfit_b200_init(dev, &c);
+    if (rc) {
+      for (OutfitCtx *q : g->ctx) outfit_b200_destroy(q);
+      delete g;
+      return rc;
+    }
+    g->ctx.push_back(c);
+  }
+  g->shard_ms.assign(n_gpus, 0.f);
+  g->shard_cut.assign(n_gpus + 1, 0ull);
+  *out = g;
+  return OUTFIT_OK;
+}
+extern "C" void outfit_b200_group_destroy(OutfitGroup *g) {
+  if (!g) return;
+  for (OutfitCtx *c : g->ctx) outfit_b200_destroy(c);
+  delete g;
+}
+extern "C" int outfit_b200_group_size(OutfitGroup *g) { return g ? (int)g->ctx.size() : 0; }
+extern "C" OutfitCtx *outfit_b200_group_ctx(OutfitGroup *g, int i) {
+  return (g && i >= 0 && (size_t)i < g->ctx.size()) ? g->ctx[i] : nullptr;
+}
+extern "C" const char *outfit_b200_group_last_error(OutfitGroup *g) { return g ? g->last_error.c_str() : ""; }
+extern "C" int outfit_b200_group_last_shards(OutfitGroup *g, uint64_t *cuts, float *ms) {
+  if (!g) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  for (size_t i = 0; i < g->ctx.size(); ++i) {
+    if (ms) ms[i] = g->shard_ms[i];
+    if (cuts) cuts[i] = g->shard_cut[i];
+  }
+  if (cuts) cuts[g->ctx.size()] = g->shard_cut[g->ctx.size()];
+  return OUTFIT_OK;
+}
+
+extern "C" int outfit_b200_group_load_ephemeris(OutfitGroup *g, const double *cheb, size_t n_blocks, size_t block_stride,
+                                                double jd_start, double block_days, const uint32_t ipt[3][3], double emrat) {
+  if (!g) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  for (OutfitCtx *c : g->ctx) {  // replicated: 0.5 - 46 MB, read-only
+    const int rc = outfit_b200_load_ephemeris(c, cheb, n_blocks, block_stride, jd_start, block_days, ipt, emrat);
+    if (rc) { g->last_error = c->last_error; return rc; }
+  }
+  return OUTFIT_OK;
+}
+extern "C" int outfit_b200_group_set_pass_streams(OutfitGroup *g, int n_streams) {
+  if (!g) return OUTFIT_E_INVALID_ARGUMENT;
+  for (OutfitCtx *c : g->ctx) {
+    const int rc = outfit_b200_set_pass_streams(c, n_streams);
+    if (rc) return rc;
+  }
+  return OUTFIT_OK;
+}
+
+// run fn(i, ctx, begin, end) for every shard on its own host thread; first failure wins
+template <class F>
+static int group_run(OutfitGroup *g, const std::vector<unsigned long long> &cuts, F fn) {
+  const size_t n = g->ctx.size();
+  std::vector<int> rcs(n, OUTFIT_OK);
+  std::vector<std::thread> th;
+  g->shard_cut = cuts;
+  auto body = [&](size_t i) {
+    OutfitCtx *c = g->ctx[i];
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    if (cudaSetDevice(c->device) != cudaSuccess) rcs[i] = fail(c, OUTFIT_E_CUDA, "cudaSetDevice");
+    else rcs[i] = fn(i, c, cuts[i], cuts[i + 1]);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    g->shard_ms[i] = (float)((b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6);
+  };
+  for (size_t i = 1; i < n; ++i) th.emplace_back(body, i);
+  body(0);
+  for (std::thread &t : th) t.join();
+  for (size_t i = 0; i < n; ++i)
+    if (rcs[i]) { g->last_error = "shard " + std::to_string(i) + ": " + g->ctx[i]->last_error; return rcs[i]; }
+  return OUTFIT_OK;
+}
+
+static std::vector<unsigned long long> even_cuts(size_t n_items, size_t parts, size_t align) {
+  std::vector<unsigned long long> cuts(parts + 1, n_items);
+  cuts[0] = 0;
+  for (size_t i = 1; i < parts; ++i) {
+    size_t c = n_items * i / parts;
+    c = (c + align - 1) / align * align;
+    cuts[i] = c < n_items ? c : n_items;
+  }
+  return cuts;
+}
+
+extern "C" int outfit_b200_group_fit_full_iod(OutfitGroup *g, const OutfitIodParams *params, const OutfitObsBatch *hb,
+                                              OutfitIodResult *out) {
+  if (!g || g->ctx.empty()) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  int rc = check_iod_host_args(g->ctx[0], params, hb, out);
+  if (rc == OUTFIT_OK && hb->n_traj) rc = check_offsets(g->ctx[0], hb, 0, hb->n_traj, nullptr);
+  if (rc) { g->last_error = g->ctx[0]->last_error; return rc; }
+  std::vector<unsigned long long> cuts(g->ctx.size() + 1, 0ull);
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "cut type");
+  outfit_b200_shard_ranges(hb->n_traj, hb->traj_offset, params->max_triplets, params->n_noise_realizations, (int)g->ctx.size(),
+                           reinterpret_cast<uint64_t *>(cuts.data()));
+  return group_run(g, cuts, [&](size_t, OutfitCtx *c, unsigned long long tb, unsigned long long te) {
+    return fit_full_iod_range(c, params, hb, tb, te, out + tb);
+  });
+}
+
+extern "C" int outfit_b200_group_fit_lsq(OutfitGroup *g, const OutfitIodParams *iod_params, const OutfitLsqConfig *cfg,
+                                         const OutfitObsBatch *hb, const OutfitIodResult *iod, OutfitLsqResult *out,
+                                         OutfitObsFit *fit) {
+  if (!g || g->ctx.empty()) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  int rc = check_lsq_host_args(g->ctx[0], iod_params, cfg, hb, iod, out);
+  if (rc == OUTFIT_OK && hb->n_traj) rc = check_offsets(g->ctx[0], hb, 0, hb->n_traj, nullptr);
+  if (rc) { g->last_error = g->ctx[0]->last_error; return rc; }
+  std::vector<unsigned long long> cuts(g->ctx.size() + 1, 0ull);
+  // the IOD dominates when it runs first; the correction alone costs ~ the number of observations
+  outfit_b200_shard_ranges(hb->n_traj, hb->traj_offset, iod ? 1u : iod_params->max_triplets, iod ? 0ull : iod_params->n_noise_realizations,
+                           (int)g->ctx.size(), reinterpret_cast<uint64_t *>(cuts.data()));
+  return group_run(g, cuts, [&](size_t, OutfitCtx *c, unsigned long long tb, unsigned long long te) {
+    return fit_lsq_range(c, iod_params, cfg, hb, tb, te, iod ? iod + tb : nullptr, out + tb, fit);
+  });
+}
+
+extern "C" int outfit_b200_group_propagate_universal(OutfitGroup *g, size_t n, const double *rv, const double *t0,
+                                                     const double *t1, const double *psi_guess, const OutfitSolverType *solver,
+                                                     double *out, int32_t *status) {
+  if (!g || g->ctx.empty() || !solver || (n && (!rv || !t0 || !t1 || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  return group_run(g, even_cuts(n, g->ctx.size(), 128), [&](size_t, OutfitCtx *c, unsigned long long i0, unsigned long long i1) {
+    return propagate_range(c, n, i0, i1, rv, t0, t1, psi_guess, solver, out, status);
+  });
+}
+
+extern "C" int outfit_b200_group_ephemeris_request(OutfitGroup *g, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                                   const double *elem, size_t n_observers, const double *observer_body_fixed,
+                                                   const uint64_t *epoch_offset, const double *mjd_tt, const double *mjd_ut1,
+                                                   double *out, int32_t *status) {
+  if (!g || g->ctx.empty()) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  if (n_observers == 0 || n_orbits == 0) return OUTFIT_OK;
+  std::vector<double> bfp;
+  size_t E = 0;
+  int rc = expand_request(g->ctx[0], n_observers, observer_body_fixed, epoch_offset, bfp, &E);
+  if (rc) { g->last_error = g->ctx[0]->last_error; return rc; }
+  if (E && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !out || !status)) return OUTFIT_E_INVALID_ARGUMENT;
+  return group_run(g, even_cuts(n_orbits, g->ctx.size(), 128), [&](size_t, OutfitCtx *c, unsigned long long i0, unsigned long long i1) {
+    return ephemeris_range(c, n_orbits, i0, i1, kind, epoch, elem, E, mjd_tt, mjd_ut1, bfp.data(), nullptr, out, status);
+  });
+}
+
+// page-locked host buffers for callers without their own pinned allocator (the host entries copy
+// asynchronously only from / to page-locked memory); portable across the GPUs of a group
+extern "C" void *outfit_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void outfit_b200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" int outfit_b200_selftest_arith(OutfitCtx *ctx, unsigned long long n, unsigned long long seed, int exp_range,

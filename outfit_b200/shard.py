@@ -46,8 +46,11 @@ def slice_batch(batch, t_begin, t_end):
     for k in ("helio_equ", "geo_ecl", "body_fixed"):
         if batch.get(k) is not None:
             out[k] = np.ascontiguousarray(batch[k][:, o0:o1])
-    if batch.get("noise_z") is not None:
-        out["noise_z"] = np.ascontiguousarray(batch["noise_z"][t_begin:t_end])
+    for k in ("noise_z", "traj_seed"):  # per-trajectory inputs travel with their shard
+        if batch.get(k) is not None:
+            out[k] = np.ascontiguousarray(batch[k][t_begin:t_end])
+    if t_end > t_begin:
+        out["max_obs_per_traj"] = int(np.diff(off[t_begin:t_end + 1]).max())
     for k in ("table", "max_triplets", "n_noise"):
         if k in batch:
             out[k] = batch[k]

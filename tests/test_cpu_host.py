@@ -51,7 +51,7 @@ def test_c_abi_exports_every_declared_symbol(lib):
     assert sorted(ABI_SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.outfit_b200_abi_version() == 3  # v3: + fit_lsq
+    assert lib.outfit_b200_abi_version() == 4  # v4: + OutfitGroup (multi-GPU), fit_iod, ephemeris_request
 
 
 def test_struct_layouts_match_the_oracle_and_numpy_views(lib, oracle):
@@ -165,6 +165,31 @@ def test_shard_ranges_cover_and_balance():
         assert per.max() / per.mean() < 1.02
     assert shard.shard_ranges(np.array([0, 5, 9], dtype=np.uint64), 4) [-1][1] == 2
     assert shard.shard_ranges(np.zeros(1, dtype=np.uint64), 2) == [(0, 0), (0, 0)]
+
+
+def test_library_cut_equals_the_python_cut(lib):
+    """outfit_b200_shard_ranges (the cut OutfitGroup uses inside the C-ABI; pure host arithmetic, no device
+    needed) == outfit_b200/shard.py on ragged, uniform, tiny and empty batches."""
+    from outfit_b200 import shard, shard_ranges
+    rng = np.random.default_rng(3)
+    for T, lo, hi, K, nn in ((10_000, 8, 31, 30, 10), (1000, 12, 13, 30, 10), (7, 0, 6, 10, 20), (3, 3, 4, 10, 0),
+                             (50_000, 3, 60, 10, 20)):
+        off = np.concatenate([[0], np.cumsum(rng.integers(lo, hi, T))]).astype(np.uint64)
+        for parts in (1, 2, 3, 4, 8):
+            assert shard_ranges(off, parts, K, nn) == shard.shard_ranges(off, parts, K, nn), (T, parts)
+    assert shard_ranges(np.zeros(1, dtype=np.uint64), 2) == [(0, 0), (0, 0)]
+
+
+def test_slice_batch_carries_seeds_and_longest_trajectory():
+    from outfit_b200 import shard
+    off = np.array([0, 3, 10, 14, 30], dtype=np.uint64)
+    n = 30
+    batch = {"traj_offset": off, "mjd_tt": np.arange(n, dtype=float), "ra": np.zeros(n), "dec": np.zeros(n),
+             "sigma_ra": np.ones(n), "sigma_dec": np.ones(n), "helio_equ": np.zeros((3, n)), "geo_ecl": np.zeros((3, n)),
+             "noise_z": None, "traj_seed": np.array([11, 22, 33, 44], dtype=np.uint64), "max_obs_per_traj": 16}
+    s = shard.slice_batch(batch, 1, 3)
+    assert list(s["traj_seed"]) == [22, 33] and s["max_obs_per_traj"] == 7
+    assert list(s["traj_offset"]) == [0, 7, 11] and s["mjd_tt"][0] == 3.0
 
 
 WORKER = r'''

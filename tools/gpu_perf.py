@@ -30,7 +30,8 @@ try:
     print("   phases ms:", " ".join(f"{k[:-3]}={v:.2f}" for k, v in ph.items() if k.endswith("_ms")))
 except Exception as e:
     print("   phases: n/a (two-stream passes)")
-print(f"LIB={os.environ.get('OUTFIT_B200_LIB','default')} T={T} {ms:.1f} ms  {T/ms*1e3:.0f} traj/s  ok={np.mean(res['status']==0):.4f}")
+import hashlib
+print(f"LIB={os.environ.get('OUTFIT_B200_LIB','default')} T={T} {ms:.1f} ms  {T/ms*1e3:.0f} traj/s  ok={np.mean(res['status']==0):.4f}  md5={hashlib.md5(res.tobytes()).hexdigest()[:12]}")
 if os.environ.get("PERF_COUNT", "0") == "1":
     print("   counters:", ctx.last_iod_counters())
 if os.environ.get("PERF_E2E", "0") == "1":

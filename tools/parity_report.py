@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""Full-configuration parity sweep: the CUDA path (through the C-ABI) against the CPU oracle on every
+BASELINE config at (or near) its full size, written as a JSON report (profiles/parity_rNN.json).
+
+  C3  100 000 trajectories x 12 observations, IODParams of examples/run_full_iod (K = 30, 10 noisy copies)
+  C4  ragged 8-30 observations (20 000 trajectories by default)
+  C2  10 M propagate_universal states (SolverKind::Auto)
+  C5  100 000 orbits x 100 epochs of the two-body Combined ephemeris
+  LSQ differential correction of the C3 orbits (first 20 000 trajectories)
+
+What is recorded per IOD config (north-star rule: same selected triplet, elements within 1e-10 relative, RMS
+within 1e-9 relative):
+  * the fraction of trajectories whose integer / index fields all equal the oracle's;
+  * every selection flip, with the proof that the ORACLE's own answer for that trajectory changes when its
+    RA/Dec inputs move by one ulp (four probes), and whether the GPU landed on one of those answers;
+  * the fraction inside the plain tolerance, p50 / p99 / p99.9 / max errors;
+  * for the trajectories outside the plain tolerance: the oracle's own 1-ulp sensitivity (computed on exactly
+    those trajectories), how many sit within 256 x that floor, how many are near-parabolic (e > 0.99).
+
+The oracle is test infrastructure: this tool lives under tools/ and is run by tests/test_parity_sweep.py.
+Usage: python tools/parity_report.py [--scale 1.0] [--out profiles/parity_r02.json]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ELEM_TOL, RMS_TOL, FLOOR_FACTOR = 1e-10, 1e-9, 256.0
+INT_FIELDS = ("status", "cause", "attempts", "corrected", "element_kind", "triplet_idx", "triplet_rank", "realization")
+PROBES = ((np.inf, -np.inf), (-np.inf, np.inf), (np.inf, np.inf), (-np.inf, -np.inf))
+
+
+def pct(x, q):
+    return float(np.quantile(x, q)) if len(x) else 0.0
+
+
+def int_mismatch(a, b):
+    m = np.zeros(len(b), dtype=bool)
+    for f in INT_FIELDS:
+        d = a[f] != b[f]
+        m |= d if d.ndim == 1 else d.any(axis=1)
+    return m
+
+
+def take_trajectories(batch, idx):
+    """Sub-batch holding the trajectories `idx` (in that order), offsets re-based."""
+    off = batch["traj_offset"].astype(np.int64)
+    lens = (off[1:] - off[:-1])[idx]
+    sel = np.concatenate([np.arange(off[t], off[t + 1]) for t in idx]) if len(idx) else np.zeros(0, dtype=np.int64)
+    out = dict(batch)
+    out["traj_offset"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "mjd_ut1"):
+        out[k] = np.ascontiguousarray(batch[k][sel])
+    for k in ("helio_equ", "geo_ecl", "body_fixed"):
+        out[k] = np.ascontiguousarray(batch[k][:, sel])
+    if batch.get("noise_z") is not None:
+        out["noise_z"] = np.ascontiguousarray(batch["noise_z"][idx])
+    return out
+
+
+def probe_oracle(O, sub, et, op, base):
+    """1-ulp probes of the oracle on a sub-batch: per trajectory (elem floor, rms floor, integer-unstable, the
+    probe answers)."""
+    from parity_util import elem_err
+    n = len(base)
+    ef, rf = np.zeros(n), np.zeros(n)
+    unstable = np.zeros(n, dtype=bool)
+    answers = []
+    for s_ra, s_dec in PROBES:
+        ob = O.from_soa_batch(sub)
+        ob["ra"] = np.nextafter(ob["ra"], s_ra)
+        ob["dec"] = np.nextafter(ob["dec"], s_dec)
+        pert = O.fit_full_iod(ob, et, op, n_threads=0)
+        answers.append(pert)
+        flip = int_mismatch(pert, base)
+        unstable |= flip
+        both = (pert["status"] == 0) & (base["status"] == 0) & ~flip
+        # an f-g loop that commits or not changes the epoch (0.0 quirk, gauss.rs:1299): a discontinuity too
+        jump = both & (np.abs(pert["epoch"] - base["epoch"]) > 1e-8)
+        unstable |= jump
+        e = np.where(both & ~jump, elem_err(pert["elem"], base["elem"]), 0.0)
+        r = np.where(both & ~jump, np.abs(pert["rms"] - base["rms"]) / np.maximum(np.abs(base["rms"]), 1e-300), 0.0)
+        ef, rf = np.maximum(ef, e), np.maximum(rf, r)
+    return ef, rf, unstable, answers
+
+
+def iod_config_report(ctx, O, synth, table, et, name, T, n_obs, seed, K=30, nn=10, noise_scale=1.1, log=print):
+    from outfit_b200 import IODParams
+    from parity_util import elem_err
+    t0 = time.perf_counter()
+    batch = synth.make_trajectories(T, n_obs, seed=seed, table=table, max_triplets=K, n_noise=nn)
+    kw = dict(n_noise_realizations=nn, max_triplets=K, noise_scale=noise_scale)
+    got = ctx.fit_full_iod(batch, IODParams.builder(**kw))
+    t1 = time.perf_counter()
+    op = O.default_iod_params(**kw)
+    want = O.fit_full_iod(O.from_soa_batch(batch), et, op, n_threads=0)
+    t2 = time.perf_counter()
+    log(f"[{name}] {T} trajectories: gpu {t1 - t0:.1f} s (incl. synthesis), oracle {t2 - t1:.1f} s")
+    mism = int_mismatch(got, want)
+    flips = np.flatnonzero(mism)
+    rep = {"config": name, "n_trajectories": int(T), "n_obs": n_obs if isinstance(n_obs, int) else list(n_obs),
+           "max_triplets": K, "n_noise_realizations": nn, "seed": seed,
+           "oracle_ok": int((want["status"] == 0).sum()), "oracle_status_histogram":
+               {str(int(k)): int(v) for k, v in zip(*np.unique(want["status"], return_counts=True))},
+           "integer_fields_exact_fraction": float(1.0 - mism.mean()), "n_flips": int(len(flips))}
+    # error payloads of the failed trajectories
+    bad = (want["status"] != 0) & ~mism
+    rep["error_payloads_equal"] = bool(np.array_equal(got["span"][bad], want["span"][bad]) and
+                                       np.array_equal(np.nan_to_num(got["cause_value"][bad], nan=-1.0),
+                                                      np.nan_to_num(want["cause_value"][bad], nan=-1.0)))
+    # ---- flips: proof that the oracle itself is 1-ulp unstable there ------------------------------------
+    flip_rows = []
+    if len(flips):
+        sub = take_trajectories(batch, flips)
+        base = want[flips]
+        _, _, unstable, answers = probe_oracle(O, sub, et, op, base)
+        for j, t in enumerate(flips):
+            landed = any(not int_mismatch(got[t:t + 1], a[j:j + 1])[0] for a in answers)
+            flip_rows.append({"trajectory": int(t), "oracle_unstable_under_1ulp": bool(unstable[j]),
+                              "gpu_equals_a_probed_oracle_answer": bool(landed),
+                              "oracle": {"status": int(want["status"][t]), "triplet": [int(x) for x in want["triplet_idx"][t]],
+                                         "realization": int(want["realization"][t]), "rms": float(want["rms"][t])},
+                              "gpu": {"status": int(got["status"][t]), "triplet": [int(x) for x in got["triplet_idx"][t]],
+                                      "realization": int(got["realization"][t]), "rms": float(got["rms"][t])}})
+    rep["flips"] = flip_rows
+    rep["flips_proven_oracle_unstable"] = int(sum(r["oracle_unstable_under_1ulp"] for r in flip_rows))
+    # ---- floats on the agreeing, successful trajectories ------------------------------------------------
+    ok = (want["status"] == 0) & ~mism
+    idx_ok = np.flatnonzero(ok)
+    ee = elem_err(got["elem"][ok], want["elem"][ok])
+    er = np.abs(got["rms"][ok] - want["rms"][ok]) / np.maximum(np.abs(want["rms"][ok]), 1e-300)
+    ep = np.abs(got["epoch"][ok] - want["epoch"][ok])
+    plain = (ee <= ELEM_TOL) & (er <= RMS_TOL)
+    rep.update({"n_compared": int(ok.sum()),
+                "plain_tolerance": {"elements_rel": ELEM_TOL, "rms_rel": RMS_TOL},
+                "plain_elem_fraction": float((ee <= ELEM_TOL).mean()), "plain_rms_fraction": float((er <= RMS_TOL).mean()),
+                "plain_both_fraction": float(plain.mean()),
+                "elem_err": {"p50": pct(ee, .5), "p99": pct(ee, .99), "p99_9": pct(ee, .999), "max": float(ee.max())},
+                "rms_err": {"p50": pct(er, .5), "p99": pct(er, .99), "p99_9": pct(er, .999), "max": float(er.max())},
+                "epoch_abs_err_days_max": float(ep.max()), "bitwise_equal_fraction":
+                    float(((got["elem"][ok] == want["elem"][ok]).all(axis=1) & (got["rms"][ok] == want["rms"][ok])).mean())})
+    # ---- outside the plain tolerance: the oracle's own sensitivity on exactly those trajectories --------
+    out_idx = idx_ok[~plain]
+    rep["n_outside_plain"] = int(len(out_idx))
+    if len(out_idx):
+        sub = take_trajectories(batch, out_idx)
+        ef, rf, unstable, _ = probe_oracle(O, sub, et, op, want[out_idx])
+        e_o, r_o = ee[~plain], er[~plain]
+        within = (e_o <= np.maximum(ELEM_TOL, FLOOR_FACTOR * ef)) & (r_o <= np.maximum(RMS_TOL, FLOOR_FACTOR * rf))
+        near_parab = (want["elem"][out_idx][:, 1] > 0.99) | (got["elem"][out_idx][:, 1] > 0.99)
+        ratio = np.maximum(e_o / np.maximum(ef, 1e-300), r_o / np.maximum(rf, 1e-300))
+        unexplained = ~within & ~unstable & ~near_parab
+        rep["outside_plain"] = {"oracle_discontinuous_under_1ulp": int(unstable.sum()),
+                                "within_256x_oracle_1ulp_sensitivity": int((within & ~unstable).sum()),
+                                "near_parabolic_e_gt_0_99": int((near_parab & ~within & ~unstable).sum()),
+                                "unexplained": int(unexplained.sum()),
+                                "unexplained_trajectories": [int(x) for x in out_idx[unexplained][:20]],
+                                "error_over_oracle_sensitivity": {"p50": pct(ratio[~unstable], .5), "max": float(ratio[~unstable].max()) if (~unstable).any() else 0.0}}
+    else:
+        rep["outside_plain"] = {"oracle_discontinuous_under_1ulp": 0, "within_256x_oracle_1ulp_sensitivity": 0,
+                                "near_parabolic_e_gt_0_99": 0, "unexplained": 0, "unexplained_trajectories": []}
+    # ---- context: the ORACLE against itself with RA moved by one ulp, on a sample --------------------------
+    ns = min(T, 5000)
+    sb = take_trajectories(batch, np.arange(ns))
+    ob = O.from_soa_batch(sb)
+    ob["ra"] = np.nextafter(ob["ra"], np.inf)
+    pert = O.fit_full_iod(ob, et, op, n_threads=0)
+    base = want[:ns]
+    pm = int_mismatch(pert, base)
+    pk = (base["status"] == 0) & ~pm
+    pe = elem_err(pert["elem"][pk], base["elem"][pk])
+    pr = np.abs(pert["rms"][pk] - base["rms"][pk]) / np.maximum(np.abs(base["rms"][pk]), 1e-300)
+    rep["oracle_vs_itself_ra_plus_1ulp"] = {"n": int(ns), "n_flips": int(pm.sum()),
+                                            "plain_both_fraction": float(((pe <= ELEM_TOL) & (pr <= RMS_TOL)).mean()),
+                                            "elem_err": {"p50": pct(pe, .5), "p99": pct(pe, .99), "max": float(pe.max())},
+                                            "rms_err": {"p50": pct(pr, .5), "p99": pct(pr, .99), "max": float(pr.max())}}
+    rep["seconds"] = {"gpu_call_and_synthesis": t1 - t0, "oracle": t2 - t1, "total": time.perf_counter() - t0}
+    return rep, batch, got, want
+
+
+def lsq_report(ctx, O, et, batch, iod_got, n, log=print):
+    from outfit_b200 import DifferentialCorrectionConfig, IODParams, shard
+    from parity_util import _lsq_errs, lsq_int_mismatch, LSQ_ELEM_TOL, LSQ_RMS_TOL
+    sub = shard.slice_batch(batch, 0, n)
+    io = np.ascontiguousarray(iod_got[:n])
+    t0 = time.perf_counter()
+    got, gfit = ctx.fit_lsq(sub, IODParams.builder(n_noise_realizations=0), DifferentialCorrectionConfig.default(), initial_orbits=io)
+    ob = O.from_soa_batch(sub)
+    want, wfit = O.fit_lsq(ob, et, O.default_lsq_config(), np.ascontiguousarray(io.view(O.IOD_RESULT_DTYPE)), n_threads=0)
+    off = ob["traj_offset"]
+    mism = lsq_int_mismatch(got, want, gfit, wfit, off)
+    okm = ~mism & (want["kind"] == 1)
+    ee, er, ec, eo = _lsq_errs(got, want, gfit, wfit, off, (ob["sigma_ra"], ob["sigma_dec"]))
+    fb = ~mism & (want["kind"] == 2)
+    log(f"[lsq] {n} trajectories in {time.perf_counter() - t0:.1f} s")
+    return {"config": "FitLSQ on the C3 IOD orbits", "n_trajectories": int(n), "n_corrected": int(okm.sum()), "n_fallback": int(fb.sum()),
+            "outcome_exact_fraction": float(1.0 - mism.mean()), "n_outcome_flips": int(mism.sum()),
+            "fallback_orbits_bitwise_equal": bool(np.array_equal(got["elem"][fb], want["elem"][fb])),
+            "plain_fraction": float(((ee <= LSQ_ELEM_TOL) & (er <= LSQ_RMS_TOL))[okm].mean()) if okm.any() else 1.0,
+            "elem_err": {"p50": pct(ee[okm], .5), "p99": pct(ee[okm], .99), "max": float(ee[okm].max()) if okm.any() else 0.0},
+            "rms_err": {"p50": pct(er[okm], .5), "p99": pct(er[okm], .99), "max": float(er[okm].max()) if okm.any() else 0.0},
+            "covariance_rel_err": {"p50": pct(ec[okm], .5), "max": float(ec[okm].max()) if okm.any() else 0.0},
+            "residual_err_sigma_max": float(eo[okm].max()) if okm.any() else 0.0}
+
+
+def c2_report(ctx, O, synth, n, log=print):
+    from outfit_b200 import SolverType
+    t0 = time.perf_counter()
+    rv, ta, tb = synth.make_propagation_states(n, seed=20261018)
+    st = SolverType(kind=2)
+    got, gst = ctx.propagate_universal(rv, ta, tb, st)
+    t1 = time.perf_counter()
+    want, wst = O.propagate_universal_batch(rv, ta, tb, 2, st.convergency, 0)
+    log(f"[c2] {n} propagations: gpu+synth {t1 - t0:.1f} s, oracle {time.perf_counter() - t1:.1f} s")
+    ok = (wst == 0) & (gst == 0)
+    sr = np.linalg.norm(want[0:3, ok], axis=0)
+    sv = np.linalg.norm(want[3:6, ok], axis=0)
+    er = np.linalg.norm(got[0:3, ok] - want[0:3, ok], axis=0) / sr
+    ev = np.linalg.norm(got[3:6, ok] - want[3:6, ok], axis=0) / sv
+    efg = np.abs(got[6:10, ok] - want[6:10, ok]).max(axis=0)
+    return {"config": "C2 propagate_universal, SolverKind::Auto, convergency 100 eps", "n": int(n),
+            "status_exact_fraction": float((gst == wst).mean()), "n_status_mismatch": int((gst != wst).sum()),
+            "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(wst, return_counts=True))},
+            "ok_fraction": float(ok.mean()), "bitwise_equal_fraction": float((got[:, ok] == want[:, ok]).all(axis=0).mean()),
+            "tolerance": "1e-9 relative to |r1|, |v1| (the reference's own: 1e-9 / 1e-8 absolute, propagation.rs:245-262)",
+            "within_tolerance_fraction": float(((er <= 1e-9) & (ev <= 1e-9)).mean()),
+            "r_rel_err": {"p50": pct(er, .5), "p99_9": pct(er, .999), "max": float(er.max())},
+            "v_rel_err": {"p50": pct(ev, .5), "p99_9": pct(ev, .999), "max": float(ev.max())},
+            "fg_abs_err_max": float(efg.max())}
+
+
+def c5_report(ctx, O, synth, et, n_orb, n_ep, log=print):
+    t0 = time.perf_counter()
+    kind, epoch, elem = synth.make_ephemeris_orbits(n_orb, seed=20261018, mixed_kinds=True)
+    tt, ut1, bf = synth.make_ephemeris_epochs(n_ep)
+    got, gst = ctx.ephemeris_twobody(kind, epoch, elem, tt, ut1, bf)
+    t1 = time.perf_counter()
+    want, wst = O.ephemeris_twobody_batch(et, kind, epoch, elem, tt, ut1, bf)
+    log(f"[c5] {n_orb} x {n_ep}: gpu+synth {t1 - t0:.1f} s, oracle {time.perf_counter() - t1:.1f} s")
+    ok = (wst == 0) & (gst == 0)
+    names = ("ra", "dec", "geocentric_dist", "heliocentric_dist", "phase_angle", "solar_elongation", "radial_velocity", "d_ra_dt", "d_dec_dt")
+    tol = {"ra": 1e-11, "dec": 1e-11, "phase_angle": 1e-11, "solar_elongation": 1e-11, "geocentric_dist": 1e-12,
+           "heliocentric_dist": 1e-12, "radial_velocity": 1e-12, "d_ra_dt": 1e-12, "d_dec_dt": 1e-12}
+    errs, within = {}, np.ones(int(ok.sum()), dtype=bool)
+    for q, nm in enumerate(names):
+        g, w = got[q][ok], want[q][ok]
+        if nm == "ra":
+            d = np.abs((g - w + np.pi) % (2 * np.pi) - np.pi)
+        elif nm in ("geocentric_dist", "heliocentric_dist"):
+            d = np.abs(g - w) / np.abs(w)
+        else:
+            d = np.abs(g - w)
+        errs[nm] = {"p50": pct(d, .5), "max": float(d.max()), "tolerance": tol[nm]}
+        within &= d <= tol[nm]
+    return {"config": "C5 two-body Combined ephemeris, mixed element kinds, one topocentric observer", "orbits": int(n_orb), "epochs": int(n_ep),
+            "entries": int(n_orb * n_ep), "status_exact_fraction": float((gst == wst).mean()), "ok_fraction": float(ok.mean()),
+            "failed_entries_are_nan": bool(np.isnan(got[:, gst != 0]).all()),
+            "within_tolerance_fraction": float(within.mean()), "errors": errs,
+            "tolerance_note": "angles absolute (rad), distances relative, rates absolute (AU/day, rad/day)"}
+
+
+def run(scale=1.0, out_path=None, log=print):
+    from oracle import binding as O
+    from outfit_b200 import OutfitB200, synth
+    table = synth.make_ephemeris_table()
+    ctx = OutfitB200(0)
+    ctx.load_ephemeris(table)
+    et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    sz = lambda n, lo: max(lo, int(n * scale))
+    report = {"what": "GPU (C-ABI, liboutfit_b200.so) vs CPU oracle, full-configuration sweep", "scale": scale,
+              "host_threads": os.cpu_count()}
+    try:
+        report["git"] = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+    except Exception:
+        report["git"] = None
+    t0 = time.perf_counter()
+    c3, b3, g3, _ = iod_config_report(ctx, O, synth, table, et, "C3 100k x 12", sz(100_000, 500), 12, seed=20261018, log=log)
+    report["c3"] = c3
+    report["c4"], _, _, _ = iod_config_report(ctx, O, synth, table, et, "C4 ragged 8-30", sz(20_000, 200), (8, 30), seed=20261019, log=log)
+    report["c3_strict_no_noise"], _, _, _ = iod_config_report(ctx, O, synth, table, et, "C3 x12, n_noise_realizations = 0, K = 10",
+                                                              sz(50_000, 300), 12, seed=20261020, K=10, nn=0, log=log)
+    report["lsq"] = lsq_report(ctx, O, et, b3, g3, min(len(g3), sz(20_000, 300)), log=log)
+    report["c2"] = c2_report(ctx, O, synth, sz(10_000_000, 20_000), log=log)
+    report["c5"] = c5_report(ctx, O, synth, et, sz(100_000, 500), 100, log=log)
+    report["seconds_total"] = time.perf_counter() - t0
+    if out_path:
+        os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+        with open(out_path, "w") as f:
+            json.dump(report, f, indent=1)
+        log(f"wrote {out_path}")
+    return report
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "parity_r02.json"))
+    a = ap.parse_args()
+    r = run(a.scale, a.out)
+    print(json.dumps({k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items() if kk not in ("flips",)}) for k, v in r.items()}, indent=1)[:6000])
