@@ -4,7 +4,7 @@
 Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it
 is launched under torch.distributed.run, one rank per GPU.  Rank 0 prints ONE JSON line.
 
-Workload (BASELINE.json configs[2], the single-GPU full-IOD case): per GPU 100 000 synthetic
+Headline workload (BASELINE.json configs[2], the single-GPU full-IOD case): per GPU 100 000 synthetic
 trajectories x 12 observations, IODParams of the reference's examples/run_full_iod*.rs
 (n_noise_realizations=10, noise_scale=1.1, max_triplets=30), synthetic DE440-shaped ephemeris.
 A "step" is one fit_full_iod pass over the batch.  Weak scaling: every rank owns its own 100 k
@@ -16,11 +16,23 @@ gather of the per-trajectory results, inside the timed region.
             kernels -> D2H of the results), wall clock bracketed by synchronize, max over ranks
   roofline  FP64: algorithmic flop of the step (device event counters x the static weights of
             SURVEY 8d) / CUDA-event duration, against the DFMA peak measured live on this GPU
-            (MEASURED_PEAKS.json has no FP64 figure)
-  cpu_baseline  the C oracle (kind "port": the reference is Rust and cannot be built here) on all
+            (MEASURED_PEAKS.json has no FP64 figure); ncu evidence (DRAM bytes, FP64 pipe %, lanes per
+            instruction) from profiles/ncu_latest.json, accepted only if it was captured from the kernel
+            sources that are in the tree now
+  cpu_baseline  the C oracle, -O3 build (kind "port": the reference is Rust and cannot be built here) on all
             host cores over a bounded sample of the same workload (rank 0, N = 1 only)
+
+Further legs in the same line (each with its own device-resident and end-to-end figures):
+  c4_strong  BASELINE configs[3]: ONE seeded batch of 1 M trajectories x U[8,30] observations cut over the
+             `world` ranks by the work-balanced cut (strong scaling), plus -- on rank 0 while the other ranks
+             wait -- the same batch through ONE call of the multi-GPU group inside the C-ABI
+  kepler     configs[1]: 10 M propagate_universal, the reference bench's 8 named scenarios, host entry e2e
+  ephemeris  configs[4]: 1 M orbits x 100 epochs, host entry e2e
+  lsq        differential correction of the C3 orbits
+  fit_iod    configs[0]: latency of the single-trajectory entry on the reference's 37-observation quick start
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -37,16 +49,16 @@ WORKLOADS = {
     # name: (trajectories per GPU, n_obs, max_triplets, n_noise, noise_scale)
     "c3_100k_x12": (100_000, 12, 30, 10, 1.1),
     "c4_ragged_8_30": (100_000, (8, 30), 30, 10, 1.1),
-    "c4_125k_ragged_8_30": (125_000, (8, 30), 30, 10, 1.1),  # BASELINE configs[3]: 1 M trajectories over 8 GPUs
+    "c4_125k_ragged_8_30": (125_000, (8, 30), 30, 10, 1.1),
     "small": (4_000, 12, 30, 10, 1.1),
 }
+# BASELINE configs[3]: one batch of C4_BLOCKS x C4_BLOCK_T trajectories, block b seeded C4_SEED + b
+C4_BLOCKS, C4_BLOCK_T, C4_SEED, C4_NOBS = 8, 125_000, 20261100, (8, 30)
 # static flop weights per counted event; libm calls are reported separately
 W_FLOP = dict(sfunct_terms=12.0, newton_steps=15.0 + 9.0, fg_iterations=2 * 60.0 + 150.0,
               aberth_sweeps=1850.0, gauss_solves=120.0, roots_accepted=260.0, candidates=180.0,
               scorer_evals=127.0, scorer_newton_steps=10.0)
 W_LIBM = dict(gauss_solves=12.0, candidates=15.0, scorer_evals=4.0, scorer_newton_steps=2.0)
-
-
 # which kernel executes which counted events (phase pipeline, outfit_b200.cu)
 KERNEL_EVENTS = {
     "roots_kernel": ("gauss_solves", "aberth_sweeps"),
@@ -54,17 +66,40 @@ KERNEL_EVENTS = {
     "score_kernel": ("candidates", "scorer_evals", "scorer_newton_steps"),
 }
 KERNEL_PHASE = {"roots_kernel": "roots_ms", "correct_kernel": "correct_ms", "score_kernel": "score_ms"}
+# the reference bench's named scenarios (benches/propagate_universal.rs:61-160) -> the KAT of the same state
+# in tests/golden/reference_kats.json (extracted from kepler/propagation.rs by the committed script)
+KEPLER_SCENARIOS = {
+    "real_fink_fat_state": "test_propag", "quasi_circular": "test_quasi_circular_orbit",
+    "high_eccentricity_near_perihelion": "test_high_eccentricity_near_perihelion",
+    "near_parabolic_elliptic": "test_near_parabolic_elliptic", "near_parabolic_hyperbolic": "test_near_parabolic_hyperbolic",
+    "hyperbolic": "test_hyperbolic_orbit", "gap_35_days": "test_gap_35_days_ztf_lsst_cadence",
+    "gap_400_days_multi_revolution": "test_gap_400_days_multi_revolution"}
 
 
-# One `ncu` capture of a single-pass launch of THIS workload (100 k trajectories x 12 observations),
-# profiles/r03c_ncu_metrics_100k.csv: DRAM bytes per launch (read + write), FP64 pipe utilisation, issue
-# slot utilisation, active threads per warp instruction.  Static evidence, not re-measured by bench.py.
-NCU_R03C = {
-    "roots_kernel": {"dram_bytes": 1556703488 + 1037716480, "fp64_pipe_pct": 81.28, "issue_pct": 53.05, "threads_per_inst": 31.07},
-    "correct_kernel": {"dram_bytes": 2045758208 + 1946571520, "fp64_pipe_pct": 63.89, "issue_pct": 54.51, "threads_per_inst": 24.83},
-    # (score_kernel's pipe / issue figures: profiles/r04_ncu_phases.txt, taken after its trigonometry was rewritten)
-    "score_kernel": {"dram_bytes": 2200741888 + 652708608, "fp64_pipe_pct": 63.33, "issue_pct": 69.07, "threads_per_inst": 29.63},
-}
+def kernel_source_sha():
+    """sha256 over the kernel sources of the tree: the key an ncu capture is bound to (tools/ncu_latest.py)."""
+    d = os.path.join(ROOT, "outfit_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".inc")) or name == "Makefile":
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()
+
+
+def load_ncu_latest():
+    """profiles/ncu_latest.json, or a reason why it cannot be used for this binary."""
+    path = os.path.join(ROOT, "profiles", "ncu_latest.json")
+    if not os.path.exists(path):
+        return None, "profiles/ncu_latest.json is missing"
+    try:
+        d = json.load(open(path))
+    except Exception as e:  # noqa: BLE001
+        return None, f"profiles/ncu_latest.json unreadable: {e}"
+    if d.get("kernel_source_sha256") != kernel_source_sha():
+        return None, ("profiles/ncu_latest.json was captured from other kernel sources (sha "
+                      f"{str(d.get('kernel_source_sha256'))[:12]} != tree {kernel_source_sha()[:12]}): not used")
+    return d, None
 
 
 def algorithmic_flops(counters, keys=None):
@@ -125,24 +160,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_rate(batch, table, kw, target_s=15.0, n_threads=0):
-    """Oracle (C restatement of the reference's Rayon path) on a bounded sample: (traj/s, n, secs)."""
+def oracle_rate(batch, table, kw, target_s=12.0, n_threads=0, dedup_earth=False):
+    """Oracle (C restatement of the reference's Rayon path, -O3 build) on a bounded sample: (traj/s, n, secs)."""
     from oracle import binding as O
-    from outfit_b200 import shard, synth
+    from outfit_b200 import shard
     et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
     p = O.default_iod_params(**kw)
     T = len(batch["traj_offset"]) - 1
     n0 = min(T, 256)
     t0 = time.perf_counter()
-    O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, n0)), et, p, n_threads=n_threads)
+    O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, n0)), et, p, n_threads=n_threads, dedup_earth=dedup_earth)
     rate0 = n0 / max(time.perf_counter() - t0, 1e-9)
     n = int(min(T, max(n0, rate0 * target_s)))
     ob = O.from_soa_batch(shard.slice_batch(batch, 0, n))
-    O.lib().oo_counters_reset()
     t0 = time.perf_counter()
-    O.fit_full_iod(ob, et, p, n_threads=n_threads)
+    O.fit_full_iod(ob, et, p, n_threads=n_threads, dedup_earth=dedup_earth)
     dt = time.perf_counter() - t0
-    return n / dt, n, dt, O.counters()
+    return n / dt, n, dt
 
 
 def _claim_stdout():
@@ -154,6 +188,89 @@ def _claim_stdout():
     return real
 
 
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: the 1 M-trajectory batch, generated block-wise in worker processes (before CUDA starts)
+# ---------------------------------------------------------------------------------------------------------
+def _c4_block(b):
+    from outfit_b200 import synth
+    table = synth.make_ephemeris_table()
+    blk = synth.make_trajectories(C4_BLOCK_T, C4_NOBS, seed=C4_SEED + b, table=table, max_triplets=30, n_noise=10,
+                                  with_noise=False)
+    return {k: blk[k] for k in ("traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl")}
+
+
+def c4_lengths():
+    """Observation counts of all C4_BLOCKS x C4_BLOCK_T trajectories without generating them (the first draw of
+    synth.make_trajectories' generator)."""
+    return np.concatenate([np.random.default_rng(C4_SEED + b).integers(C4_NOBS[0], C4_NOBS[1] + 1, size=C4_BLOCK_T)
+                           for b in range(C4_BLOCKS)])
+
+
+def c4_generate(t_begin, t_end, workers):
+    """Host batch of the trajectories [t_begin, t_end) of the 1 M batch (offsets re-based)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from outfit_b200 import shard
+    if t_end <= t_begin:
+        return None
+    b0, b1 = t_begin // C4_BLOCK_T, (t_end - 1) // C4_BLOCK_T
+    with ProcessPoolExecutor(max_workers=max(1, min(workers, b1 - b0 + 1))) as ex:
+        blocks = list(ex.map(_c4_block, range(b0, b1 + 1)))
+    parts = []
+    for i, blk in enumerate(blocks):
+        lo = max(t_begin, (b0 + i) * C4_BLOCK_T) - (b0 + i) * C4_BLOCK_T
+        hi = min(t_end, (b0 + i + 1) * C4_BLOCK_T) - (b0 + i) * C4_BLOCK_T
+        parts.append(shard.slice_batch(blk, lo, hi))
+    out = {}
+    lens = np.concatenate([np.diff(p["traj_offset"].astype(np.int64)) for p in parts])
+    out["traj_offset"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec"):
+        out[k] = np.ascontiguousarray(np.concatenate([p[k] for p in parts]))
+    for k in ("helio_equ", "geo_ecl"):
+        out[k] = np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=1))
+    # per-trajectory seeds of the on-device deviates (SmallRng::seed_from_u64), a function of the GLOBAL index
+    out["traj_seed"] = (np.arange(t_begin, t_end, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(C4_SEED))
+    out["noise_z"] = None
+    out["max_obs_per_traj"] = int(lens.max())
+    return out
+
+
+def reference_arm(args, out_stream, table, T, n_obs, K, nn, kw, config, cores):
+    sample_T = 3000
+    from outfit_b200 import shard, synth
+    batch = synth.make_trajectories(sample_T, n_obs, seed=20261018, table=table, max_triplets=K, n_noise=nn)
+    from oracle import binding as O
+    et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    p = O.default_iod_params(**kw)
+    # size each step so that warmup + steps stay within a few minutes
+    t0 = time.perf_counter()
+    O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, 128)), et, p, n_threads=0)
+    rate0 = 128 / (time.perf_counter() - t0)
+    per_step = int(min(sample_T, max(128, rate0 * 100.0 / max(1, args.steps + args.warmup))))
+    ob = O.from_soa_batch(shard.slice_batch(batch, 0, per_step))
+    for _ in range(args.warmup):
+        O.fit_full_iod(ob, et, p, n_threads=0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.fit_full_iod(ob, et, p, n_threads=0)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = per_step / dt
+    t0 = time.perf_counter()
+    O.fit_full_iod(ob, et, p, n_threads=0, dedup_earth=True)
+    v_dedup = per_step / (time.perf_counter() - t0)
+    sample = (f"{per_step} trajectories of the same workload per step, all {cores} host threads (pthread pool, one task per "
+              "trajectory, dynamic scheduling like par_iter_traj_id)")
+    print(json.dumps({
+        "impl": "reference", "metric": "full_iod_trajectories_per_s", "value": v, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample,
+                         "build": "gcc -O3 -march=x86-64-v3 -ffp-contract=off (oracle/liboutfit_oracle_o3.so; bit-identical to the -O2 parity build)",
+                         "dedup_earth_variant": {"value": v_dedup, "note": "the same path with the per-candidate Earth re-evaluation (observation_ephemeris.rs:309) hoisted to once per observation -- NOT the reference's behaviour, reported beside it"},
+                         "note": "C restatement of the reference's Rayon path (oracle/); the Rust reference cannot be built in this image"},
+        "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out_stream, flush=True)
+
+
 def main():
     out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -162,7 +279,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_100k_x12", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-kepler", action="store_true", help="skip the 10M propagate_universal leg")
+    ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler / ephemeris / LSQ / fit_iod legs")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 1 M-trajectory strong-scaling leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -172,6 +290,7 @@ def main():
     T, n_obs, K, nn, nscale = WORKLOADS[args.workload]
     kw = dict(n_noise_realizations=nn, noise_scale=nscale, max_triplets=K, max_obs_for_triplets=100)
     cores = os.cpu_count() or 1
+    os.environ["OUTFIT_ORACLE_BUILD"] = "o3"  # the CPU arm / cpu_baseline time the -O3 build of the oracle
     config = {"workload": f"synthetic {T} trajectories x {n_obs} obs per GPU, full Gauss IOD with arc RMS "
                           f"(IODParams of examples/run_full_iod: max_triplets={K}, n_noise_realizations={nn}, "
                           f"noise_scale={nscale}); synthetic DE440-shaped ephemeris",
@@ -185,43 +304,29 @@ def main():
 
     # ------------------------------------------------------------------ reference arm (CPU only)
     if args.impl == "reference":
-        if rank != 0:
-            return
-        sample_T = 3000
-        batch = synth.make_trajectories(sample_T, n_obs, seed=20261018, table=table, max_triplets=K, n_noise=nn)
-        from oracle import binding as O
-        from outfit_b200 import shard
-        et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
-        p = O.default_iod_params(**kw)
-        ob = O.from_soa_batch(batch)
-        # size each step so that warmup + steps stay within a few minutes
-        t0 = time.perf_counter()
-        O.fit_full_iod(O.from_soa_batch(shard.slice_batch(batch, 0, 128)), et, p, n_threads=0)
-        rate0 = 128 / (time.perf_counter() - t0)
-        per_step = int(min(sample_T, max(128, rate0 * 120.0 / max(1, args.steps + args.warmup))))
-        ob = O.from_soa_batch(shard.slice_batch(batch, 0, per_step))
-        for _ in range(args.warmup):
-            O.fit_full_iod(ob, et, p, n_threads=0)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.fit_full_iod(ob, et, p, n_threads=0)
-        dt = (time.perf_counter() - t0) / max(1, args.steps)
-        v = per_step / dt
-        sample = f"{per_step} trajectories of the same workload per step, all {cores} host threads (pthread pool, one task per trajectory)"
-        print(file=out_stream, flush=True, *[json.dumps({
-            "impl": "reference", "metric": "full_iod_trajectories_per_s", "value": v, "unit": "trajectories/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config,
-            "cpu_baseline": {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample,
-                             "note": "C restatement of the reference's Rayon path (oracle/); the Rust reference cannot be built in this image"},
-            "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
+        if rank == 0:
+            reference_arm(args, out_stream, table, T, n_obs, K, nn, kw, config, cores)
         return
 
     # ------------------------------------------------------------------------------ our arm
+    # configs[3] data first: worker processes are forked BEFORE this process touches CUDA
+    c4 = None
+    if not args.no_c4:
+        from outfit_b200 import shard_ranges
+        lens = c4_lengths()
+        off_all = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        cuts = shard_ranges(off_all, world, K, nn)  # the library's cut (outfit_b200_shard_ranges)
+        t0 = time.perf_counter()
+        mine = c4_generate(cuts[rank][0], cuts[rank][1], workers=max(1, min(8, cores // max(1, world))))
+        whole = None
+        if rank == 0 and world > 1:  # rank 0 also drives the single-process group over the WHOLE batch
+            whole = c4_generate(0, C4_BLOCKS * C4_BLOCK_T, workers=max(1, min(8, cores // 2)))
+        c4 = {"cuts": cuts, "mine": mine, "whole": whole if world > 1 else mine, "gen_s": time.perf_counter() - t0,
+              "n_obs_total": int(lens.sum())}
+
     import torch
     import torch.distributed as dist
-    from outfit_b200 import IODParams, OutfitB200, RESULT_DTYPE, SolverType
+    from outfit_b200 import IODParams, OutfitB200, OutfitGroup, RESULT_DTYPE, SolverType
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: outfit_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -235,21 +340,24 @@ def main():
     params = IODParams.builder(**kw)
     fp64_peak = ctx.measure_fp64_peak()
 
+    def pin(a):
+        return torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).pin_memory()
+
+    def unpin(t, like):
+        return t.numpy().view(np.uint64) if like.dtype == np.uint64 else t.numpy()
+
     keys = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "noise_z"]
     # pinned host copies (the e2e leg copies from these) and device-resident copies (the `value` leg)
-    pinned, devb = {}, {}
-    for k in keys:
-        a = batch[k]
-        t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a)
-        pinned[k] = t.pin_memory()
-        devb[k] = pinned[k].to(dev, non_blocking=True)
-    host_batch = {k: (pinned[k].numpy().view(np.uint64) if k == "traj_offset" else pinned[k].numpy()) for k in keys}
+    pinned = {k: pin(batch[k]) for k in keys}
+    devb = {k: pinned[k].to(dev, non_blocking=True) for k in keys}
+    host_batch = {k: unpin(pinned[k], batch[k]) for k in keys}
     h2d_bytes = int(sum(pinned[k].numel() * pinned[k].element_size() for k in keys))
     d_out = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d2h_bytes = int(d_out.numel())
     gather_bufs = [torch.zeros_like(d_out) for _ in range(world)] if world > 1 else None
     devb["max_obs_per_traj"] = int(np.diff(batch["traj_offset"].astype(np.int64)).max())
     stream = torch.cuda.current_stream().cuda_stream
+    launches = 0
 
     def step_device():
         ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
@@ -277,16 +385,14 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / max(1, args.steps)
     per_step_launches = int(ctx.last_iod_phase_ms()["kernel_launches"])  # 8 passes x 5 kernels + observer
-    launches = (max(3, args.warmup) + args.steps) * per_step_launches
+    launches += (max(3, args.warmup) + args.steps) * per_step_launches
     # per-kernel durations: the timed steps keep 8 passes in flight on 8 streams, where kernels of
     # different passes overlap; the per-kernel figures come from extra steps run as ONE pass on the
     # launching stream, bracketed by CUDA events the library records between its kernels
     ctx.set_pass_streams(1)
-    single_ms = []
     for _ in range(3):
         ctx.fit_full_iod_device(devb, params, d_out, stream=stream)
         phases = ctx.last_iod_phase_ms()
-        single_ms.append(phases["total_ms"])
     launches += 3 * int(phases["kernel_launches"])
     kernel_ms = phases["total_ms"]  # all kernels of one single-pass step, no gather
     # one extra, untimed step with the counting instantiation: the event counts behind the flop figure
@@ -315,7 +421,7 @@ def main():
     # (OutfitObsBatch.traj_seed; parity with rand's stream unpinned): 8 B instead of 14.4 kB per trajectory
     seeded = {k: v for k, v in host_batch.items() if k != "noise_z"}
     seeded["noise_z"] = None
-    seeded["traj_seed"] = torch.from_numpy((np.arange(T, dtype=np.int64) * 2654435761 + 20261018 + rank)).pin_memory().numpy().view(np.uint64)
+    seeded["traj_seed"] = pin((np.arange(T, dtype=np.int64) * 2654435761 + 20261018 + rank)).numpy().view(np.uint64)
     ctx.fit_full_iod(seeded, params, out=out_pinned)
     barrier()
     t0 = time.perf_counter()
@@ -328,7 +434,118 @@ def main():
     seeded_h2d = h2d_bytes - int(pinned["noise_z"].numel() * 8) + T * 8
     clocks = sampler.stop()
 
-    # Kepler leg: 10 M propagate_universal (BASELINE configs[1]), device-resident
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def wall(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    # ------------------------------------------------------------------ configs[3]: 1 M trajectories, strong scaling
+    c4_out = None
+    if c4 is not None:
+        mine = c4["mine"]
+        n_mine = 0 if mine is None else len(mine["traj_offset"]) - 1
+        c4_ms = c4_e2e_ms = 0.0
+        c4_ok = 0
+        if n_mine:
+            ck = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "traj_seed"]
+            cp = {k: pin(mine[k]) for k in ck}
+            cdev = {k: cp[k].to(dev, non_blocking=True) for k in ck}
+            cdev["noise_z"] = None
+            cdev["max_obs_per_traj"] = mine["max_obs_per_traj"]
+            chost = {k: unpin(cp[k], mine[k]) for k in ck}
+            chost["noise_z"] = None
+            d_c4 = torch.zeros(n_mine * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            c4_pinned_out = torch.zeros(n_mine * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+        barrier()
+        if n_mine:
+            c4_ms = timed(lambda: ctx.fit_full_iod_device(cdev, params, d_c4, stream=stream), reps=2, warm=1)
+        barrier()
+        if n_mine:
+            c4_e2e_ms = wall(lambda: ctx.fit_full_iod(chost, params, out=c4_pinned_out), reps=2, warm=1) * 1e3
+            c4_ok = int((c4_pinned_out["status"] == 0).sum())
+            launches += 5 * (per_step_launches + 8)
+            del d_c4, cdev
+        barrier()
+        tm4 = torch.tensor([c4_ms, c4_e2e_ms], dtype=torch.float64, device=dev)
+        all4 = [torch.zeros_like(tm4) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all4, tm4)
+        else:
+            all4 = [tm4]
+        per_rank = [[float(x) for x in t.tolist()] for t in all4]
+        okt = torch.tensor([float(c4_ok)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.SUM)
+        n_all = C4_BLOCKS * C4_BLOCK_T
+        dev_ms = max(p[0] for p in per_rank)
+        e2e4_ms = max(p[1] for p in per_rank)
+        c4_out = {"workload": f"BASELINE configs[3]: ONE seeded batch of {n_all} trajectories x U[8,30] observations "
+                              f"({c4['n_obs_total']} observations), IODParams of examples/run_full_iod (K=30, 10 noisy copies, deviates "
+                              "generated on the device from per-trajectory seeds), cut over the ranks by outfit_b200_shard_ranges",
+                  "scaling": "strong", "n_trajectories": n_all, "n_gpus": world,
+                  "cuts": [list(c) for c in c4["cuts"]],
+                  "value": n_all / (dev_ms * 1e-3), "unit": "trajectories/s", "ms_per_step": dev_ms,
+                  "per_rank_ms": [p[0] for p in per_rank],
+                  "imbalance_max_over_mean": dev_ms / max(1e-9, float(np.mean([p[0] for p in per_rank]))),
+                  "e2e": {"value": n_all / (e2e4_ms * 1e-3), "ms_per_step": e2e4_ms, "per_rank_ms": [p[1] for p in per_rank],
+                          "api": "outfit_b200_fit_full_iod on each rank's shard (pinned host buffers, results D2H)",
+                          "h2d_bytes_per_step": int(88 * c4["n_obs_total"] + 16 * n_all), "d2h_bytes_per_step": int(128 * n_all)},
+                  "selected_ok_fraction": float(okt.item()) / n_all, "host_generation_s": c4["gen_s"]}
+        # the same batch through ONE call of the multi-GPU group inside the C-ABI (rank 0; the other ranks wait on
+        # the rendezvous store -- a host-side wait, so that no barrier kernel spins on their GPUs meanwhile)
+        barrier()
+        store = dist.distributed_c10d._get_default_store() if world > 1 else None
+        if rank != 0 and store is not None:
+            from datetime import timedelta
+            store.wait(["c4_group_done"], timedelta(seconds=900))
+        if rank == 0:
+            try:
+                whole = c4["whole"]
+                gk = ["traj_offset", "mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec", "helio_equ", "geo_ecl", "traj_seed"]
+                gp = {k: pin(whole[k]) for k in gk}
+                ghost = {k: unpin(gp[k], whole[k]) for k in gk}
+                ghost["noise_z"] = None
+                g_out = torch.zeros(n_all * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+                grp = OutfitGroup(list(range(world)))
+                grp.load_ephemeris(table)
+                grp.fit_full_iod(ghost, params, out=g_out)  # warm-up (arenas, streams)
+                t0 = time.perf_counter()
+                grp.fit_full_iod(ghost, params, out=g_out)
+                g_s = time.perf_counter() - t0
+                gcuts, gms = grp.last_shards()
+                c4_out["group_single_process"] = {
+                    "api": "outfit_b200_group_fit_full_iod: ONE process, ONE call, one host thread + context per GPU, results at their global index",
+                    "n_gpus": world, "value": n_all / g_s, "ms_per_step": g_s * 1e3, "shard_ms": [float(x) for x in gms],
+                    "cuts": [int(x) for x in gcuts], "selected_ok_fraction": float((g_out["status"] == 0).mean()),
+                    "equals_per_rank_results": bool(n_mine and world == 1 and g_out.tobytes() == c4_pinned_out.tobytes()) if world == 1 else None}
+                launches += 2 * (per_step_launches + 8) * world
+                grp.close()
+                del gp, ghost, g_out
+            except Exception as e:  # noqa: BLE001
+                c4_out["group_single_process"] = {"error": str(e)[:300]}
+            if store is not None:
+                store.set("c4_group_done", "1")
+        barrier()
+        c4 = None
+
+    # Kepler leg: 10 M propagate_universal (BASELINE configs[1]), device-resident + host entry
     kep = None
     if not args.no_kepler:
         n_prop = 10_000_000
@@ -337,23 +554,50 @@ def main():
         d_o = torch.empty(11 * n_prop, dtype=torch.float64, device=dev)
         d_s = torch.empty(n_prop, dtype=torch.int32, device=dev)
         st = SolverType(kind=2)
-        for _ in range(3):
-            ctx.propagate_universal_device(n_prop, d_rv, d_t0, d_t1, d_o, d_s, st, stream=stream)
-        torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(5):
-            ctx.propagate_universal_device(n_prop, d_rv, d_t0, d_t1, d_o, d_s, st, stream=stream)
-        p1.record()
-        torch.cuda.synchronize()
-        pms = p0.elapsed_time(p1) / 5
+        pms = timed(lambda: ctx.propagate_universal_device(n_prop, d_rv, d_t0, d_t1, d_o, d_s, st, stream=stream), reps=5, warm=3)
         launches += 8
         kep = {"propagate_universal_per_s": n_prop / (pms * 1e-3), "n": n_prop, "ms": pms,
-               "hbm_gbs": 156.0 * n_prop / (pms * 1e-3) / 1e9, "ok_fraction": float((d_s == 0).float().mean().item()),
+               "hbm_gbs": 156.0 * n_prop / (pms * 1e-3) / 1e9, "hbm_frac": 156.0 * n_prop / (pms * 1e-3) / 1e9 / 6536.7,
+               "ok_fraction": float((d_s == 0).float().mean().item()),
                "workload": "10M random elliptic/hyperbolic heliocentric states, SolverKind::Auto, convergency 100 eps"}
-        del d_rv, d_t0, d_t1, d_o, d_s
+        # host entry: pinned inputs -> chunked H2D / kernel / D2H ring -> pinned outputs
+        hp = [pin(x) for x in (rv, t0a, t1a)]
+        ho = torch.empty(11 * n_prop, dtype=torch.float64).pin_memory()
+        hs = torch.empty(n_prop, dtype=torch.int32).pin_memory()
+        L, h = ctx._L, ctx._h
+        import ctypes as C
 
-    # Ephemeris leg: BASELINE configs[4], 1 M orbits x 100 daily epochs, Combined output, device-resident
+        def prop_host():
+            rc = L.outfit_b200_propagate_universal(h, n_prop, hp[0].data_ptr(), hp[1].data_ptr(), hp[2].data_ptr(), None,
+                                                   C.byref(st), ho.data_ptr(), hs.data_ptr())
+            assert rc == 0, rc
+        e2e_p = wall(prop_host, reps=3, warm=1)
+        launches += 4 * 10
+        kep["e2e"] = {"value": n_prop / e2e_p, "ms": e2e_p * 1e3, "h2d_bytes": 80 * n_prop, "d2h_bytes": 92 * n_prop,
+                      "pcie_gbs": 172.0 * n_prop / e2e_p / 1e9,
+                      "api": "outfit_b200_propagate_universal (pinned host buffers; 1 M-state chunks through a 3-slot H2D/kernel/D2H ring)",
+                      "equals_device_result": bool(torch.equal(ho.view(11, n_prop)[:, :100000], d_o.view(11, n_prop)[:, :100000].cpu()))}
+        # the reference bench's named scenarios: 2 M replicas of each state, one launch per scenario
+        try:
+            kats = {c["name"]: c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")))["propagate_universal"]["cases"]}
+            n_s = 2_000_000
+            st_b = SolverType(kind=2, convergency=2.220446049250313e-14)  # the bench's default_solver_type()
+            scen = {}
+            for name, kat in KEPLER_SCENARIOS.items():
+                c = kats[kat]
+                s_rv = torch.tensor(list(c["r"]) + list(c["v"]), dtype=torch.float64, device=dev).repeat_interleave(n_s).contiguous()
+                s_t0 = torch.full((n_s,), float(c["t0"]), dtype=torch.float64, device=dev)
+                s_t1 = torch.full((n_s,), float(c["t1"]), dtype=torch.float64, device=dev)
+                sms = timed(lambda: ctx.propagate_universal_device(n_s, s_rv, s_t0, s_t1, d_o, d_s, st_b, stream=stream), reps=3, warm=1)
+                scen[name] = {"per_s": n_s / (sms * 1e-3), "ns_per_propagation": sms * 1e6 / n_s}
+                launches += 4
+            kep["scenarios"] = scen
+            kep["scenarios_note"] = "benches/propagate_universal.rs:61-160, 2 M replicas of each state per launch, SolverKind::Auto, convergency 2.2e-14"
+        except Exception as e:  # noqa: BLE001
+            kep["scenarios"] = {"error": str(e)[:200]}
+        del d_rv, d_t0, d_t1, d_o, d_s, hp, ho, hs
+
+    # Ephemeris leg: BASELINE configs[4], 1 M orbits x 100 daily epochs, Combined output
     eph = None
     if not args.no_kepler:
         n_orb, n_ep = 1_000_000, 100
@@ -362,22 +606,32 @@ def main():
         d_kind, d_ep, d_el, d_tt, d_ut = (torch.from_numpy(x).to(dev) for x in (kind, epoch0, elem, tt, ut1))
         d_eo = torch.empty(9 * n_ep * n_orb, dtype=torch.float64, device=dev)
         d_es = torch.empty(n_ep * n_orb, dtype=torch.int32, device=dev)
-        for _ in range(2):
-            ctx.ephemeris_twobody_device(n_orb, d_kind, d_ep, d_el, n_ep, d_tt, d_ut, bf, d_eo, d_es, stream=stream)
-        torch.cuda.synchronize()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(3):
-            ctx.ephemeris_twobody_device(n_orb, d_kind, d_ep, d_el, n_ep, d_tt, d_ut, bf, d_eo, d_es, stream=stream)
-        q1.record()
-        torch.cuda.synchronize()
-        ems = q0.elapsed_time(q1) / 3
+        ems = timed(lambda: ctx.ephemeris_twobody_device(n_orb, d_kind, d_ep, d_el, n_ep, d_tt, d_ut, bf, d_eo, d_es, stream=stream), reps=3, warm=2)
         launches += 5 * 2
         n_ent = n_orb * n_ep
         eph = {"entries_per_s": n_ent / (ems * 1e-3), "orbits": n_orb, "epochs": n_ep, "ms": ems,
                "hbm_gbs": (76.0 * n_ent + 60.0 * n_orb) / (ems * 1e-3) / 1e9, "hbm_frac": (76.0 * n_ent + 60.0 * n_orb) / (ems * 1e-3) / 1e9 / 6536.7,
                "ok_fraction": float((d_es == 0).float().mean().item()),
                "workload": "1M elliptic orbits x 100 daily epochs, one topocentric observer, two-body, first-order aberration, Combined output (9 f64 + status per entry)"}
+        del d_eo, d_es
+        # host entry on a bounded slice (the full output is 7.6 GB: the call is bound by the D2H copy)
+        n_h = 200_000
+        hk, he, hl = pin(kind[:n_h].copy()), pin(epoch0[:n_h].copy()), pin(np.ascontiguousarray(elem[:, :n_h]))
+        ho = torch.empty(9 * n_ep * n_h, dtype=torch.float64).pin_memory()
+        hs = torch.empty(n_ep * n_h, dtype=torch.int32).pin_memory()
+        import ctypes as C
+        bfc = (C.c_double * 3)(*[float(x) for x in bf])
+        L, h = ctx._L, ctx._h
+
+        def eph_host():
+            rc = L.outfit_b200_ephemeris_twobody(h, n_h, hk.data_ptr(), he.data_ptr(), hl.data_ptr(), n_ep, tt.ctypes.data,
+                                                 ut1.ctypes.data, bfc, ho.data_ptr(), hs.data_ptr())
+            assert rc == 0, rc
+        e2e_e = wall(eph_host, reps=2, warm=1)
+        launches += 3 * 8
+        eph["e2e"] = {"entries_per_s": n_h * n_ep / e2e_e, "ms": e2e_e * 1e3, "orbits": n_h, "d2h_bytes": 76 * n_h * n_ep,
+                      "pcie_gbs": 76.0 * n_h * n_ep / e2e_e / 1e9,
+                      "api": "outfit_b200_ephemeris_twobody (pinned host buffers; orbit chunks through a 3-slot ring; bound by the 76 B per entry that go back over PCIe)"}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import binding as O
             et_ = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
@@ -385,11 +639,10 @@ def main():
             t0 = time.perf_counter()
             O.ephemeris_twobody_batch(et_, kind[:ns].copy(), epoch0[:ns].copy(), np.ascontiguousarray(elem[:, :ns]), tt, ut1, bf)
             eph["cpu_entries_per_s"] = ns * n_ep / (time.perf_counter() - t0)
-            eph["cpu_sample"] = f"{ns} orbits x {n_ep} epochs, oracle on all {cores} host threads (observer state re-evaluated per entry like the reference)"
-        del d_eo, d_es
+            eph["cpu_sample"] = f"{ns} orbits x {n_ep} epochs, oracle (-O3 build) on all {cores} host threads (observer state re-evaluated per entry like the reference)"
+        del hk, he, hl, ho, hs
 
-
-    # FitLSQ leg: differential correction of the batch's IOD orbits, device-resident
+    # FitLSQ leg: differential correction of the batch's IOD orbits
     lsq = None
     if not args.no_kepler:
         from outfit_b200 import DifferentialCorrectionConfig, LSQ_RESULT_DTYPE, OBS_FIT_DTYPE
@@ -398,27 +651,27 @@ def main():
         d_lo = torch.zeros(T * LSQ_RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         d_lf = torch.zeros(n_all * OBS_FIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         ctx.fit_full_iod_device(devb, params, d_out, stream=stream)  # initial orbits = this batch's IOD results
-        for _ in range(3):
-            ctx.fit_lsq_device(devb, lcfg, d_out, d_lo, d_lf, stream=stream)
-        torch.cuda.synchronize()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record()
-        for _ in range(5):
-            ctx.fit_lsq_device(devb, lcfg, d_out, d_lo, d_lf, stream=stream)
-        l1.record()
-        torch.cuda.synchronize()
-        lms = l0.elapsed_time(l1) / 5
+        lms = timed(lambda: ctx.fit_lsq_device(devb, lcfg, d_out, d_lo, d_lf, stream=stream), reps=5, warm=3)
         launches += 8 * 2 + per_step_launches + 3 * 2  # 8 device calls + the IOD call + 3 host-entry calls
         lres = d_lo.cpu().numpy().view(LSQ_RESULT_DTYPE).reshape(-1)
-        io_host = d_out.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
-        lhost_s = float("inf")
-        for _ in range(3):  # first call: arena growth and first-touch of the result pages
-            t0 = time.perf_counter()
-            lhost, _ = ctx.fit_lsq(host_batch, params, lcfg, initial_orbits=io_host)
-            lhost_s = min(lhost_s, time.perf_counter() - t0)
+        io_pinned = torch.zeros(T * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        io_pinned.copy_(d_out.cpu())
+        io_host = io_pinned.numpy().view(RESULT_DTYPE).reshape(-1)
+        lo_p = torch.zeros(T * LSQ_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        lf_p = torch.zeros(n_all * OBS_FIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        bstruct = ctx._batch_struct(host_batch)
+        bstruct.noise_z = None
+        import ctypes as C
+
+        def lsq_host():
+            rc = ctx._L.outfit_b200_fit_lsq(ctx._h, C.byref(params), C.byref(lcfg), C.byref(bstruct), io_host.ctypes.data,
+                                            lo_p.data_ptr(), lf_p.data_ptr())
+            assert rc == 0, rc
+        lhost_s = wall(lsq_host, reps=3, warm=2)
         n_it = int(lres["total_newton_iterations"].sum())
         lsq = {"trajectories_per_s": T / (lms * 1e-3), "ms": lms, "host_entry_trajectories_per_s": T / lhost_s,
-               "host_entry_ms": lhost_s * 1e3, "host_equals_device": bool(lhost.tobytes() == lres.tobytes()),
+               "host_entry_ms": lhost_s * 1e3, "host_equals_device": bool(lo_p.numpy().tobytes() == lres.tobytes()),
+               "host_entry_bytes": {"h2d": int(n_all * 64 + T * (8 + 128)), "d2h": int(T * 776 + n_all * 32)},
                "corrected_fraction": float((lres["kind"] == 1).mean()), "iod_fallback_fraction": float((lres["kind"] == 2).mean()),
                "newton_iterations": n_it, "observation_equations_per_s": n_it * (n_all / T) / (lms * 1e-3),
                "workload": "differential correction (two-body, default DifferentialCorrectionConfig) of the same batch from its IOD orbits; one thread per trajectory"}
@@ -430,8 +683,37 @@ def main():
             t0 = time.perf_counter()
             O.fit_lsq(ob_, et_, O.default_lsq_config(), io_, n_threads=0)
             lsq["cpu_trajectories_per_s"] = T / (time.perf_counter() - t0)
-            lsq["cpu_sample"] = f"the whole batch ({T} trajectories), oracle on all {cores} host threads"
-        del d_lo, d_lf
+            lsq["cpu_sample"] = f"the whole batch ({T} trajectories), oracle (-O3 build) on all {cores} host threads"
+        del d_lo, d_lf, lo_p, lf_p
+
+    # configs[0]: latency of the single-trajectory entry (FitIOD::fit_iod) on the reference's quick start
+    fit_iod = None
+    if not args.no_kepler and rank == 0:
+        try:
+            from outfit_b200 import mpc80
+            d = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_2015AB.json")))
+            _, b1 = mpc80.to_batch({d["designation"]: d["records"]})
+            t1 = synth.make_ephemeris_table(mjd_start=54900.0, n_blocks=80)
+            c1 = OutfitB200(local_rank)
+            c1.load_ephemeris(t1)
+            p1 = IODParams.builder(n_noise_realizations=10, noise_scale=1.1, max_triplets=30)
+            b1 = dict(b1)
+            b1["noise_z"] = None
+            b1["traj_seed"] = np.array([42], dtype=np.uint64)
+            r = c1.fit_iod(b1, p1, 0, use_body_fixed=True)
+            lat = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                r = c1.fit_iod(b1, p1, 0, use_body_fixed=True)
+                lat.append(time.perf_counter() - t0)
+            launches += 31 * 8
+            fit_iod = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_min": float(np.min(lat) * 1e3),
+                       "status": int(r["status"]), "rms": float(r["rms"]), "n_obs": int(len(b1["ra"])),
+                       "api": "outfit_b200_fit_iod (host buffers, on-device observer geometry from body-fixed + UT1, K=30, 10 noisy copies from a device seed)",
+                       "workload": "BASELINE configs[0]: the 37 observations of the reference's quick start (tests/data/2015AB.obs), one trajectory: a LATENCY figure"}
+            c1.close()
+        except Exception as e:  # noqa: BLE001
+            fit_iod = {"error": str(e)[:300]}
 
     # max over ranks
     tm = torch.tensor([ms, e2e_s * 1e3, kernel_ms, e2e_seeded_s * 1e3], dtype=torch.float64, device=dev)
@@ -447,6 +729,7 @@ def main():
     ms, e2e_ms, kernel_ms_max, e2e_seeded_ms = (float(x) for x in tm.tolist())
 
     if rank == 0:
+        ncu, ncu_why = load_ncu_latest()
         flops = algorithmic_flops(counters)
         achieved = flops / (kernel_ms * 1e-3)
         kernels = {}
@@ -455,8 +738,8 @@ def main():
             kfl = algorithmic_flops(counters, ev)
             kernels[kname] = {"ms": kms, "share_of_step": kms / kernel_ms, "algorithmic_flop": kfl,
                               "tflops": kfl / (kms * 1e-3) / 1e12, "frac_fp64_peak": kfl / (kms * 1e-3) / fp64_peak}
-            if args.workload == "c3_100k_x12":
-                kernels[kname]["ncu_r03c"] = NCU_R03C[kname]
+            if ncu and kname in ncu.get("kernels", {}):
+                kernels[kname]["ncu"] = ncu["kernels"][kname]
         for kname, key in (("scorer_observer_kernel", "observer_ms"), ("triplets_kernel", "triplets_ms"),
                            ("select_kernel", "select_ms")):
             kernels[kname] = {"ms": phases[key], "share_of_step": phases[key] / kernel_ms}
@@ -464,6 +747,9 @@ def main():
         n_total_obs = int(batch["mjd_tt"].shape[0])
         alg_bytes = 88.0 * n_total_obs + 96.0 * T + 48.0 * T * K * nn
         kepler_in_iod = counters["scorer_evals"] + counters["kepler_universal_solves"]
+        traffic = None
+        if ncu and dom in ncu.get("kernels", {}) and args.workload == ncu.get("workload"):
+            traffic = ncu["kernels"][dom].get("dram_bytes")
         out = {
             "metric": "full_iod_trajectories_per_s", "value": T * world / (ms * 1e-3), "unit": "trajectories/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
@@ -479,8 +765,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": kernels[dom]["tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": kernels[dom]["frac_fp64_peak"],
-                         "traffic": NCU_R03C[dom]["dram_bytes"] if args.workload == "c3_100k_x12" else None, "kernel": dom,
+                         "frac": kernels[dom]["frac_fp64_peak"], "traffic": traffic, "kernel": dom,
+                         "ncu_capture": ({"git": ncu.get("git"), "kernel_source_sha256": ncu.get("kernel_source_sha256"), "captured": ncu.get("captured"),
+                                          "file": "profiles/ncu_latest.json"} if ncu else {"unavailable": ncu_why}),
                          "kernel_ms": kernels[dom]["ms"], "algorithmic_flop_per_launch": kernels[dom]["algorithmic_flop"],
                          "step": {"achieved": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / fp64_peak, "ms": ms,
                                   "single_pass_ms": kernel_ms, "single_pass_frac": achieved / fp64_peak,
@@ -492,18 +779,24 @@ def main():
                          "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": 6536.7,
                                  "algorithmic_bytes_per_launch": alg_bytes,
                                  "note": "observation + noise stream; the kernel is FP64-latency/issue bound, not HBM bound"}},
+            "c4_strong": c4_out,
             "kepler": {"iod_kepler_props_per_s": kepler_in_iod * world / (ms * 1e-3),
                        "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
             "ephemeris": eph,
             "lsq": lsq,
+            "fit_iod": fit_iod,
             "counters": counters,
             "selected_ok_fraction": float((res_host["status"] == 0).mean()),
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, n, dt, oc = oracle_rate(batch, table, kw)
+            v, n, dt = oracle_rate(batch, table, kw)
+            v2, n2, dt2 = oracle_rate(batch, table, kw, target_s=6.0, dedup_earth=True)
             out["cpu_baseline"] = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                                   "build": "gcc -O3 -march=x86-64-v3 -ffp-contract=off (oracle/liboutfit_oracle_o3.so; bit-identical to the -O2 parity build)",
                                    "sample": f"first {n} trajectories of the same batch, {dt:.1f} s wall on all {cores} host threads "
-                                             "(C restatement of the reference's Rayon path; per-candidate Earth re-evaluation kept)"}
+                                             "(C restatement of the reference's Rayon path; per-candidate Earth re-evaluation kept)",
+                                   "dedup_earth_variant": {"value": v2, "sample": f"first {n2} trajectories, {dt2:.1f} s",
+                                                           "note": "Earth evaluated once per observation instead of once per (candidate, observation): NOT the reference's behaviour"}}
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.barrier()

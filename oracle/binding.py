@@ -19,9 +19,12 @@ def build():
 
 
 def lib():
+    """The parity build, or -- OUTFIT_ORACLE_BUILD=o3, set by bench.py's CPU arm only -- the -O3 baseline build of
+    the same sources (bit-identical results, see oracle/Makefile)."""
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "liboutfit_oracle.so")
+        name = "liboutfit_oracle_o3.so" if os.environ.get("OUTFIT_ORACLE_BUILD") == "o3" else "liboutfit_oracle.so"
+        path = os.path.join(_HERE, name)
         if not os.path.exists(path):
             build()
         _LIB = C.CDLL(path)
@@ -166,6 +169,10 @@ def _declare(L):
                                      C.POINTER(WeightedTriplet)]
     L.oo_best_k_triplets.restype = C.c_size_t
     L.oo_earth_ephemeris.argtypes = [C.POINTER(EphemTable), C.c_double, C.c_int, D3, D3]
+    L.oo_cheb_record.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint32, C.c_double, C.c_int, D3, D3]
+    L.oo_cheb_record.restype = None
+    for n in ("oo_solve_kepuni_newton", "oo_solve_kepuni_brent"):
+        getattr(L, n).argtypes = [C.POINTER(KeplerParams), C.POINTER(KeplerSolution)]
     L.oo_obleq.argtypes = [C.c_double]
     L.oo_obleq.restype = C.c_double
     L.oo_nutn80.argtypes = [C.c_double, c_double_p, c_double_p]

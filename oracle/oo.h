@@ -215,6 +215,9 @@ typedef struct {
 /* jpl_ephem/mod.rs:145 + horizon_data.rs:711-849 + horizon_records.rs:204 ; AU, AU/day equatorial */
 int oo_earth_ephemeris(const oo_ephem_table *tab, double mjd_tt, int with_vel, double pos[3],
                        double vel[3]);
+/* HorizonRecord::interpolate on one record (horizon_records.rs:204-298); n_coeff <= 32, n_sub <= 8 */
+void oo_cheb_record(const double *coeffs, uint32_t n_coeff, double tau, uint32_t n_sub, double span_days,
+                    int with_vel, double pos[3], double vel[3]);
 double oo_obleq(double tjm);                          /* earth_orientation.rs:119 */
 void oo_nutn80(double tjm, double *dpsi, double *deps); /* :170 */
 void oo_rnut80(double tjm, double m[9]);              /* :459 */

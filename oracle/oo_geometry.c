@@ -416,6 +416,20 @@ static void cheb_body(const double *blk, const uint32_t ipt[3], double tau, doub
   }
 }
 
+/* HorizonRecord::interpolate (horizon_records.rs:204-298) on ONE record: coeffs[3][n_coeff] (x | y | z), tau in
+ * [0, 1] over the record, n_sub as the reference passes it; pos / vel in the coefficients' units (per day over
+ * `span_days`).  Exposed for the restatement of the reference's record tests (horizon_records.rs:356-520). */
+void oo_cheb_record(const double *coeffs, uint32_t n_coeff, double tau, uint32_t n_sub, double span_days,
+                    int with_vel, double pos[3], double vel[3]) {
+  /* cheb_body picks the sub-interval's coefficient set itself (horizon_data.rs:774); a single record is the
+   * same set for every sub-interval */
+  double blk[8 * 3 * 32];
+  const uint32_t ns = n_sub ? n_sub : 1;
+  for (uint32_t sb = 0; sb < ns && sb < 8; sb++) memcpy(blk + (size_t)sb * n_coeff * 3, coeffs, sizeof(double) * 3 * n_coeff);
+  const uint32_t ipt[3] = {0, n_coeff, ns};
+  cheb_body(blk, ipt, tau, span_days, with_vel, pos, vel);
+}
+
 /* jpl_ephem/mod.rs:145-174 ; horizon_data.rs:711-735, 810-849 ; interpolation_result.rs:82 */
 int oo_earth_ephemeris(const oo_ephem_table *tab, double et, int with_vel, double pos[3],
                        double vel[3]) {

@@ -90,7 +90,7 @@ class IodResult(C.Structure):
                 ("attempts", C.c_uint64), ("span", C.c_double), ("corrected", C.c_int32),
                 ("element_kind", C.c_int32), ("epoch", C.c_double), ("elem", C.c_double * 6),
                 ("rms", C.c_double), ("triplet_idx", C.c_uint32 * 3), ("triplet_rank", C.c_uint32),
-                ("realization", C.c_uint32)]
+                ("realization", C.c_uint32), ("_pad0", C.c_uint32)]
 
 
 class IodCounters(C.Structure):
@@ -108,7 +108,7 @@ class IodPhaseMs(C.Structure):
 RESULT_DTYPE = np.dtype([
     ("status", "<i4"), ("cause", "<i4"), ("cause_value", "<f8"), ("attempts", "<u8"), ("span", "<f8"),
     ("corrected", "<i4"), ("element_kind", "<i4"), ("epoch", "<f8"), ("elem", "<f8", (6,)),
-    ("rms", "<f8"), ("triplet_idx", "<u4", (3,)), ("triplet_rank", "<u4"), ("realization", "<u4")],
+    ("rms", "<f8"), ("triplet_idx", "<u4", (3,)), ("triplet_rank", "<u4"), ("realization", "<u4"), ("_pad0", "<u4")],
     align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(IodResult)
 

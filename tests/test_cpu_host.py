@@ -167,6 +167,30 @@ def test_shard_ranges_cover_and_balance():
     assert shard.shard_ranges(np.zeros(1, dtype=np.uint64), 2) == [(0, 0), (0, 0)]
 
 
+def test_o3_baseline_build_of_the_oracle_is_bit_identical_to_the_parity_build(oracle):
+    """bench.py's CPU arm times oracle/liboutfit_oracle_o3.so (-O3 -march=x86-64-v3, no FMA contraction): same
+    sources, same bits as the -O2 parity build, with and without the de-duplicated Earth evaluation."""
+    code = (
+        "import sys, hashlib\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from oracle import binding as O\n"
+        "from outfit_b200 import synth\n"
+        "t = synth.make_ephemeris_table()\n"
+        "et = O.make_ephem_table(t['cheb'], t['jd_start'], t['block_days'], t['ipt'], t['emrat'])\n"
+        "b = synth.make_trajectories(60, (8, 20), seed=3, table=t, max_triplets=10, n_noise=2)\n"
+        "p = O.default_iod_params(n_noise_realizations=2, max_triplets=10, noise_scale=1.1)\n"
+        "for dd in (False, True):\n"
+        "    r = O.fit_full_iod(O.from_soa_batch(b), et, p, n_threads=2, dedup_earth=dd)\n"
+        "    print(hashlib.md5(r.tobytes()).hexdigest())\n")
+    outs = []
+    for build in ("", "o3"):
+        env = dict(os.environ, OUTFIT_ORACLE_BUILD=build)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(r.stdout.split())
+    assert len(outs[0]) == 2 and len(set(outs[0] + outs[1])) == 1, outs
+
+
 def test_library_cut_equals_the_python_cut(lib):
     """outfit_b200_shard_ranges (the cut OutfitGroup uses inside the C-ABI; pure host arithmetic, no device
     needed) == outfit_b200/shard.py on ragged, uniform, tiny and empty batches."""
