@@ -77,11 +77,12 @@ KEPLER_SCENARIOS = {
 
 
 def kernel_source_sha():
-    """sha256 over the kernel sources of the tree: the key an ncu capture is bound to (tools/ncu_latest.py)."""
+    """sha256 over the KERNEL sources of the tree (every .cuh / .inc of outfit_b200/csrc + the Makefile with its
+    compiler flags; outfit_b200.cu holds host code only): the key an ncu capture is bound to (tools/ncu_latest.py)."""
     d = os.path.join(ROOT, "outfit_b200", "csrc")
     h = hashlib.sha256()
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".inc")) or name == "Makefile":
+        if name.endswith((".cuh", ".inc")) or name == "Makefile":
             h.update(name.encode())
             h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()

@@ -218,6 +218,8 @@ def _declare(L):
                                              C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, D3,
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.oo_ephemeris_twobody_batch.restype = None
+    L.oo_set_aberration_order.argtypes = [C.c_int]
+    L.oo_set_aberration_order.restype = None
     L.oo_ephemeris_observer_pv.argtypes = [C.POINTER(EphemTable), C.c_double, C.c_double, D3, D3, D3, D3]
     L.oo_counters_get.argtypes = [C.POINTER(Counters)]
     L.oo_counters_get.restype = None
@@ -304,14 +306,19 @@ def propagate_universal_batch(rv, t0, t1, kind=2, convergency=100 * 2.2204460492
 
 
 def ephemeris_twobody_batch(table, kind, epoch, elem, mjd_tt, mjd_ut1, body_fixed, n_threads=0,
-                            dedup_observer=False):
-    """kind (n,) int32, epoch (n,), elem (6, n), mjd_tt/mjd_ut1 (E,) -> out (9, E, n), status (E, n)."""
+                            dedup_observer=False, aberration_order=1):
+    """kind (n,) int32, epoch (n,), elem (6, n), mjd_tt/mjd_ut1 (E,) -> out (9, E, n), status (E, n).
+    aberration_order: 1 = AberrationOrder::First, 2 = Second (ephemeris/aberration.rs:60-75)."""
     n, E = kind.shape[0], mjd_tt.shape[0]
     out = np.empty((9, E, n), dtype=np.float64)
     status = np.empty((E, n), dtype=np.int32)
-    lib().oo_ephemeris_twobody_batch(C.byref(table), n, ptr(kind), ptr(epoch), ptr(elem), E, ptr(mjd_tt),
-                                     ptr(mjd_ut1), d3(body_fixed), ptr(out), ptr(status), n_threads,
-                                     1 if dedup_observer else 0)
+    lib().oo_set_aberration_order(int(aberration_order))
+    try:
+        lib().oo_ephemeris_twobody_batch(C.byref(table), n, ptr(kind), ptr(epoch), ptr(elem), E, ptr(mjd_tt),
+                                         ptr(mjd_ut1), d3(body_fixed), ptr(out), ptr(status), n_threads,
+                                         1 if dedup_observer else 0)
+    finally:
+        lib().oo_set_aberration_order(1)
     return out, status
 
 

@@ -300,6 +300,7 @@ void oo_draw_noise(uint64_t seed, size_t n, double *out);       /* n deviates in
 /* ---- two-body `Combined` ephemeris (ephemeris/mod.rs:189-292; oo_ephemeris.c) -------------- */
 /* apparent_position.rs:264-296 : observer position / velocity (= Earth velocity) / Earth position,
    equatorial mean J2000, AU and AU/day */
+void oo_set_aberration_order(int order); /* 1 First (default) | 2 Second (aberration.rs:60-75,195-234) */
 int oo_ephemeris_observer_pv(const oo_ephem_table *tab, double mjd_tt, double mjd_ut1,
                              const double r_bf[3], double obs_pos_equ[3], double obs_vel_equ[3],
                              double earth_pos_equ[3]);

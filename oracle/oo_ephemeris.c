@@ -10,6 +10,7 @@
  *   compute_geometry + helpers          ephemeris/geometry.rs:204-345
  *   PropagatorKind::TwoBody             propagator/mod.rs:84-91, 128-135
  *   correct_aberration_first_order      ephemeris/aberration.rs:139-145
+ *   correct_aberration_second_order     ephemeris/aberration.rs:195-234 (AberrationOrder::Second, :60-75)
  *   check_elliptical_orbit              ephemeris/observation_ephemeris.rs:288-296
  *
  * Parity unpinned (the reference's KATs for this path need DE440 + UT1): hifitime's ns epoch
@@ -41,6 +42,23 @@ int oo_ephemeris_observer_pv(const oo_ephem_table *tab, double mjd_tt, double mj
   return OO_OK;
 }
 
+/* EphemerisConfig::aberration (ephemeris/mod.rs:129-142): 1 = AberrationOrder::First (default), 2 = Second.
+ * A process-wide switch of the oracle (test infrastructure), set before a batch call. */
+static int g_aberration_order = 1;
+void oo_set_aberration_order(int order) { g_aberration_order = order == 2 ? 2 : 1; }
+
+/* retropropagate (aberration.rs:223-234): heliocentric position, equatorial J2000, at t_obs - separation / c */
+static int retropropagate(const oo_elements *equi, double obs_time_mjd, double separation, double r[3]) {
+  double dt_light = separation / VLIGHT_AU;
+  double t_retarded = obs_time_mjd - dt_light;
+  double dt_orbit = t_retarded - equi->epoch;
+  double pe[3], ve[3];
+  int rc = oo_propagate_twobody(equi, 0.0, dt_orbit, pe, ve);
+  if (rc != OO_OK) return rc;
+  oo_matvec(ROT_ECL2EQU, pe, r);
+  return OO_OK;
+}
+
 /* One (orbit, epoch) entry given the observer state: out[9] = ra, dec, geocentric_dist,
  * heliocentric_dist, phase_angle, solar_elongation, radial_velocity, d_ra_dt, d_dec_dt. */
 int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const double obs_pos[3],
@@ -57,9 +75,20 @@ int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const doubl
   double dgeo[3], topo_raw[3];
   for (int i = 0; i < 3; i++) { dgeo[i] = ap[i] - earth_pos[i]; topo_raw[i] = ap[i] - obs_pos[i]; }
   double geo = oo_norm3(dgeo);
-  double ltt = oo_norm3(topo_raw) / VLIGHT_AU;
   double topo[3];
-  for (int i = 0; i < 3; i++) topo[i] = topo_raw[i] - ltt * av[i];
+  if (g_aberration_order == 2) {
+    /* correct_aberration_second_order (aberration.rs:195-209): two back-propagations by the light time */
+    double r1[3], d1[3], r2[3];
+    rc = retropropagate(equi, obs_time_mjd, oo_norm3(topo_raw), r1);
+    if (rc != OO_OK) return rc;
+    for (int i = 0; i < 3; i++) d1[i] = r1[i] - obs_pos[i];
+    rc = retropropagate(equi, obs_time_mjd, oo_norm3(d1), r2);
+    if (rc != OO_OK) return rc;
+    for (int i = 0; i < 3; i++) topo[i] = r2[i] - obs_pos[i];
+  } else {
+    double ltt = oo_norm3(topo_raw) / VLIGHT_AU;
+    for (int i = 0; i < 3; i++) topo[i] = topo_raw[i] - ltt * av[i];
+  }
   out[0] = oo_rem_euclid(atan2(topo[1], topo[0]), OO_DPI);
   out[1] = atan2(topo[2], sqrt(topo[0] * topo[0] + topo[1] * topo[1]));
   out[2] = geo;

@@ -112,6 +112,15 @@ RESULT_DTYPE = np.dtype([
     align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(IodResult)
 
+class EphemerisConfig(C.Structure):
+    """EphemerisConfig (ephemeris/mod.rs:124-142): propagator 0 TwoBody | 1 NBody (unsupported on the device);
+    aberration 1 First (default) | 2 Second."""
+    _fields_ = [("propagator", C.c_int32), ("aberration", C.c_int32)]
+
+    def __init__(self, propagator=0, aberration=1):
+        super().__init__(propagator, aberration)
+
+
 class DifferentialCorrectionConfig(C.Structure):
     """DifferentialCorrectionConfig (diff_cor.rs:100-192) + OutlierRejectionConfig + EquinoctialLimits."""
     _fields_ = [("max_newton_iterations", C.c_uint64), ("max_outlier_rejection_passes", C.c_uint64),
@@ -161,6 +170,7 @@ ABI_SYMBOLS = [
     "outfit_b200_group_fit_full_iod", "outfit_b200_group_fit_lsq", "outfit_b200_group_propagate_universal",
     "outfit_b200_group_ephemeris_request", "outfit_b200_group_last_shards", "outfit_b200_shard_ranges",
     "outfit_b200_host_alloc", "outfit_b200_host_free",
+    "outfit_b200_ephemeris_config_default", "outfit_b200_set_ephemeris_config", "outfit_b200_group_set_ephemeris_config",
 ]
 
 
@@ -235,6 +245,10 @@ def load_library():
     L.outfit_b200_host_alloc.restype = vp
     L.outfit_b200_host_free.argtypes = [vp]
     L.outfit_b200_host_free.restype = None
+    L.outfit_b200_ephemeris_config_default.argtypes = [C.POINTER(EphemerisConfig)]
+    L.outfit_b200_ephemeris_config_default.restype = None
+    L.outfit_b200_set_ephemeris_config.argtypes = [vp, C.POINTER(EphemerisConfig)]
+    L.outfit_b200_group_set_ephemeris_config.argtypes = [vp, C.POINTER(EphemerisConfig)]
     _LIB = L
     return L
 
@@ -448,6 +462,10 @@ class OutfitB200:
                                                           _p(off), _p(tt), _p(ut), out.ctypes.data, status.ctypes.data))
         return out, status
 
+    def set_ephemeris_config(self, config):
+        """EphemerisConfig of the ephemeris entries of this context (aberration order; two-body propagator only)."""
+        self._check(self._L.outfit_b200_set_ephemeris_config(self._h, C.byref(config)))
+
     def selftest_arith(self, n, seed=1, exp_range=60):
         """Mismatch counts (rcp, div, sqrt, sincos) of the library's own arithmetic against CUDA's."""
         out = (C.c_uint64 * 4)()
@@ -538,6 +556,9 @@ class OutfitGroup:
 
     def set_pass_streams(self, n):
         self._check(self._L.outfit_b200_group_set_pass_streams(self._h, int(n)))
+
+    def set_ephemeris_config(self, config):
+        self._check(self._L.outfit_b200_group_set_ephemeris_config(self._h, C.byref(config)))
 
     def fit_full_iod(self, batch, params, use_body_fixed=False, out=None):
         b = OutfitB200._batch_struct(batch, use_body_fixed)

@@ -133,6 +133,44 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       : "memory");
 }
 
+// retropropagate (ephemeris/aberration.rs:223-234) with the hoisted per-orbit constants: heliocentric position,
+// equatorial J2000, at the epoch `t` (= t_obs - separation / c).  Same statement of propagate_twobody as the
+// main evaluation of the kernel below (equinoctial_element.rs:326-348, 639-759).  false <=> Kepler solve failed.
+struct EphOrbitC {
+  double a, h, k, lambda, t_ref, n_mot, lon_peri, ch, ck, bhk, sx0, cx0;
+  V3 fv, gv;
+};
+__device__ __forceinline__ bool eph_retarded_position(const EphOrbitC &o, double t, V3 &pos_equ) {
+  const double dt = t - o.t_ref;
+  double lam1 = rem_euclid(o.lambda + o.n_mot * (dt - 0.0), kTwoPi);
+  if (lam1 < o.lon_peri) lam1 += kTwoPi;
+  const double eps = kEps * 1e2;
+  double x = kPi + o.lon_peri, sF = o.sx0, cF = o.cx0;
+  int iter = 0;
+  bool last = false, have = true;
+  for (;;) {
+    if (!have) sincos_angle(x, &sF, &cF);
+    have = false;
+    if (last) break;
+    const double f = x - o.k * sF + o.h * cF - lam1;
+    const double d = 1.0 - o.k * cF - o.h * sF;
+    if (fabs(f) < eps) break;
+    if (fabs(d) < eps) {
+      if (iter == 0) { x = x + 1.0; iter = 1; continue; }
+      return false;
+    }
+    const double x1 = x - bf_div(f, d);
+    const bool conv = fabs(x - x1) < eps;
+    x = x1;
+    if (conv) { last = true; continue; }
+    if (++iter >= 25) return false;
+  }
+  const double xe = o.a * (o.ch * cF + o.bhk * sF - o.k);
+  const double ye = o.a * (o.ck * sF + o.bhk * cF - o.h);
+  pos_equ = ecl_to_equ(xe * o.fv + ye * o.gv);
+  return true;
+}
+
 constexpr int kEphThreads = 128;
 constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 8 B = 9 KB
 
@@ -142,6 +180,9 @@ constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 
 #ifndef OUTFIT_EPH_BPS
 #define OUTFIT_EPH_BPS 5  // 96 registers, 20 warps per SM: 10.0 ms per 1e8 entries against 10.6 at 4 (r02b)
 #endif
+// SECOND = AberrationOrder::Second (aberration.rs:195-209): the line of sight comes from two back-propagations by the
+// light time instead of the linear shift; a separate instantiation, the first-order kernel is untouched by it.
+template <bool SECOND>
 __global__ void __launch_bounds__(kEphThreads, OUTFIT_EPH_BPS)
 ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const double *__restrict__ epoch,
                          const double *__restrict__ elem, size_t n_epochs, size_t e_stride,
@@ -258,8 +299,22 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
             const V3 dgeo = ap - ep;
             const double geo = bf_sqrt(dot(dgeo, dgeo));
             const V3 raw = ap - op;
-            const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
-            const V3 topo = raw - ltt * av;
+            V3 topo;
+            bool ab_ok = true;
+            if (SECOND) {
+              const EphOrbitC oc{a, h, k, lambda, t_ref, n_mot, lon_peri, ch, ck, bhk, sx0, cx0, fv, gv};
+              V3 r1, r2;
+              ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu), r1);
+              if (ab_ok) {
+                const V3 d1 = r1 - op;
+                ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(d1, d1)), kVlightAu, 1.0 / kVlightAu), r2);
+              }
+              topo = r2 - op;
+            } else {
+              const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
+              topo = raw - ltt * av;
+            }
+            if (!ab_ok) st = 11;  // the back-propagation's Kepler solve failed: RootFindingError
             o[0] = rem_euclid(atan2_finite(topo.y, topo.x), kTwoPi);
             o[1] = atan2_finite(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
             o[2] = geo;

@@ -1,12 +1,13 @@
-// outfit_b200.cu -- kernels + C-ABI (include/outfit_b200.h) of the B200-native batched IOD path.
+// outfit_b200.cu -- host side of the C-ABI (include/outfit_b200.h) of the B200-native batched IOD path: contexts,
+// arenas, streams, launch configuration, the host-buffer entries and the multi-GPU group.
 //
-// Kernels (all scalar FP64, sm_100a):
-//   triplets / roots / correct / score / select kernels: the full-IOD pipeline (one warp per
-//                              trajectory for selection + fold, one lane per (triplet, realization))
-//   scorer_observer_kernel     per observation: DE-style Chebyshev Earth position + frame rotations
-//   propagate_universal_kernel one thread per two-body propagation
-//   fp64_peak_kernel           DFMA issue-rate probe (roofline denominator)
-// There is no CPU fallback anywhere in this file.
+// Kernels (all scalar FP64, sm_100a) live in the headers included below:
+//   k_iod.cuh         triplets / roots / correct / score / select: the full-IOD pipeline (one warp per trajectory
+//                     for selection + fold, one lane per (triplet, realization))
+//   dev_geometry.cuh  scorer_observer_kernel, observer_cache_kernel: Chebyshev Earth position + frame rotations
+//   dev_ephemeris.cuh two-body Combined ephemeris (first / second-order aberration)
+//   k_bulk.cuh        propagate_universal_kernel, lsq_kernel, arithmetic self-test, fp64_peak_kernel
+// There is no CPU fallback anywhere in this library.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -29,900 +30,8 @@
 
 using namespace ofb;
 
-// =================================================================================================
-// full-IOD pipeline.  Mapping: one warp per trajectory for the two trajectory-level steps (triplet
-// selection, best-orbit fold with warp-shuffle argmin) and one lane per candidate = (triplet,
-// noise realization) for the three numeric phases.  The phases are separate launches over flat
-// candidate arrays because the fused single kernel was instruction-cache bound (ncu r01a/r01b:
-// 57-73 % stall_no_inst with ~100 KB of hot SASS); per phase the hot loop is a few KB, every warp
-// of an SM runs the same loop, and register use / occupancy is set per phase.
-//   P0 triplets_kernel   warp / trajectory   best-K triplets            -> trip[T][K], ktraj[T]
-//   P1 roots_kernel      lane / candidate    geometry, degree-8 poly, Aberth -> roots, code
-//   P2 correct_kernel    lane / candidate    accept root, f-g correction -> state (r, v, epoch)
-//   P3 score_kernel      lane / candidate    elements, equinoctial, arc RMS sum -> kind, sum, n_arc
-//   P4 select_kernel     warp / trajectory   order-preserving fold + result record
-// Candidate id = (t * K + r) * M + m  (K = max_triplets, M = 1 + n_noise_realizations).
-// =================================================================================================
-struct IodBatchDev {
-  unsigned long long n_traj;
-  unsigned long long n_obs;
-  const unsigned long long *traj_offset;
-  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
-  const double *helio;   // [3][n_obs]
-  const double *scorer;  // [3][n_obs]
-  const double *noise_z; // [n_traj][max_triplets][n_noise][6] or null
-  const int *obs_status; // [n_obs] 0 | OUTFIT_ST_EPHEM_OUT_OF_RANGE (observer kernels)
-};
-
-struct IodScratch {
-  unsigned *trip;        // [T][K] packed (i<<20 | j<<10 | k), ascending weight
-  unsigned *ktraj;       // [T] number of triplets found
-  int *code;             // [C] P1: 0 ok | OUTFIT_ST_* ; P3 overwrites with the score kind
-  unsigned char *nroots; // [C]
-  double *roots;         // [8][C] admissible roots in solver order
-  int *state_kind;       // [C] 0 none, 1 PrelimOrbit, 2 CorrectedOrbit
-  double *state;         // [7][C] r(t2) xyz, v(t2) xyz, epoch
-  int *score_kind;       // [C] 0 gauss error (code in score_code), 1 abort, 2 break, 3 sum
-  int *score_code;       // [C]
-  double *score_sum;     // [C]
-  unsigned *score_narc;  // [C]
-  unsigned long long n_cand;
-};
-
-constexpr int kWarpsPerBlock = 4;
-constexpr int kCandThreads = 128;
-
-__device__ __forceinline__ void flush_work(const Work &w, unsigned long long *__restrict__ work_counters) {
-  const unsigned *wp = reinterpret_cast<const unsigned *>(&w);
-  const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-  for (int q = 0; q < (int)(sizeof(Work) / sizeof(unsigned)); ++q) {
-    unsigned long long v = wp[q];
-    if (__any_sync(0xffffffffu, v != 0)) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0 && work_counters) atomicAdd(&work_counters[q], v);
-    }
-  }
-}
-
-// ---- P0: best-K triplets, one warp per trajectory --------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-triplets_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned n_obs_cap) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const size_t per_warp = ((size_t)n_obs_cap * sizeof(double) + (size_t)P.max_triplets * (8 + 4) + 15) & ~(size_t)15;
-  TrajSmem sm;
-  sm.t = reinterpret_cast<double *>(smem_raw + warp * per_warp);
-  sm.heap_w = sm.t + n_obs_cap;
-  sm.heap_x = reinterpret_cast<unsigned *>(sm.heap_w + P.max_triplets);
-  const unsigned long long tr = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp;
-  if (tr >= B.n_traj) return;
-  const unsigned long long o0 = B.traj_offset[tr];
-  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-  for (unsigned i = lane; i < n_obs; i += 32) sm.t[i] = B.mjd_tt[o0 + i];
-  __syncwarp();
-  const unsigned K = select_triplets(sm, n_obs, P, lane);
-  for (unsigned a = lane; a < K; a += 32) S.trip[tr * P.max_triplets + a] = sm.heap_x[a];
-  if (lane == 0) S.ktraj[tr] = K;
-}
-
-// P0, one thread per trajectory (dev_iod.cuh: select_triplets_thread); dynamic shared memory =
-// blockDim.x * max_triplets * 12 bytes
-__global__ void __launch_bounds__(128)
-triplets_thread_kernel(IodBatchDev B, IodDevParams P, IodScratch S) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *hw = reinterpret_cast<double *>(smem_raw);
-  unsigned *hx = reinterpret_cast<unsigned *>(hw + (size_t)P.max_triplets * blockDim.x);
-  const unsigned long long tr = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tr >= B.n_traj) return;
-  const unsigned long long o0 = B.traj_offset[tr];
-  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-  const HeapCol h{hw + threadIdx.x, hx + threadIdx.x, blockDim.x};
-  const unsigned K = select_triplets_thread(h, B.mjd_tt + o0, n_obs, P);
-  for (unsigned a = 0; a < K; ++a) S.trip[tr * P.max_triplets + a] = h.X(a);
-  S.ktraj[tr] = K;
-}
-
-// candidate id -> (trajectory, triplet rank, realization); false when the slot is unused
-__device__ __forceinline__ bool decode_candidate(unsigned long long cid, const IodDevParams &P, const IodScratch &S,
-                                                 unsigned long long &tr, unsigned &r, unsigned &m) {
-  const unsigned M = P.n_noise + 1;
-  const unsigned long long tk = cid / M;
-  m = (unsigned)(cid - tk * M);
-  tr = tk / P.max_triplets;
-  r = (unsigned)(tk - tr * P.max_triplets);
-  return r < S.ktraj[tr];
-}
-
-// observations of the triplet (+ the host-drawn noise of this realization, gauss.rs:323-387)
-__device__ __forceinline__ void load_triplet(const IodBatchDev &B, const IodDevParams &P, const IodScratch &S,
-                                             unsigned long long tr, unsigned r, unsigned m, Triplet &g, unsigned (&idx)[3]) {
-  const unsigned packed = S.trip[tr * P.max_triplets + r];
-  idx[0] = packed >> 20; idx[1] = (packed >> 10) & 1023u; idx[2] = packed & 1023u;
-  const unsigned long long o0 = B.traj_offset[tr];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const unsigned long long gI = o0 + idx[c];
-    g.t[c] = __ldg(B.mjd_tt + gI);
-    g.ra[c] = __ldg(B.ra + gI);
-    g.dec[c] = __ldg(B.dec + gI);
-    g.R[c] = V3{__ldg(B.helio + gI), __ldg(B.helio + B.n_obs + gI), __ldg(B.helio + 2 * B.n_obs + gI)};
-  }
-  if (m > 0) {
-    const double *z = B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6;
-    const double2 z01 = __ldg(reinterpret_cast<const double2 *>(z));
-    const double2 z23 = __ldg(reinterpret_cast<const double2 *>(z) + 1);
-    const double2 z45 = __ldg(reinterpret_cast<const double2 *>(z) + 2);
-    const unsigned long long g0 = o0 + idx[0], g1 = o0 + idx[1], g2 = o0 + idx[2];
-    g.ra[0] = g.ra[0] + z01.x * (__ldg(B.sigma_ra + g0) * P.noise_scale);
-    g.ra[1] = g.ra[1] + z01.y * (__ldg(B.sigma_ra + g1) * P.noise_scale);
-    g.ra[2] = g.ra[2] + z23.x * (__ldg(B.sigma_ra + g2) * P.noise_scale);
-    g.dec[0] = g.dec[0] + z23.y * (__ldg(B.sigma_dec + g0) * P.noise_scale);
-    g.dec[1] = g.dec[1] + z45.x * (__ldg(B.sigma_dec + g1) * P.noise_scale);
-    g.dec[2] = g.dec[2] + z45.y * (__ldg(B.sigma_dec + g2) * P.noise_scale);
-  }
-}
-
-// ---- P1: geometry + polynomial + Aberth ---------------------------------------------------------
-#ifndef OUTFIT_ROOTS_BPS
-#define OUTFIT_ROOTS_BPS 4
-#endif
-__global__ void __launch_bounds__(kCandThreads, OUTFIT_ROOTS_BPS)
-roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  extern __shared__ __align__(16) double roots_sm[];  // [32][kCandThreads]: iterates + Aberth sums
-  volatile double *zsm = roots_sm + threadIdx.x;
-  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
-  Work w;
-  memset(&w, 0, sizeof w);
-  unsigned long long tr;
-  unsigned r, m;
-  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
-    ++w.candidates;
-    ++w.gauss_solves;
-    Triplet g;
-    unsigned idx[3];
-    load_triplet(B, P, S, tr, r, m, g, idx);
-    GaussGeom gm;
-    int code = 0;
-    unsigned n = 0;
-    double c0, c3, c6;
-    if (!gauss_geometry(g, gm)) code = OUTFIT_ST_SINGULAR_DIRECTION_MATRIX;
-    else if (!gauss_polynomial(g, gm, c0, c3, c6)) code = OUTFIT_ST_GAUSS_NO_ROOTS;
-    else if (aberth8(c0, c3, c6, P.aberth_max_iter, P.aberth_eps, zsm, kCandThreads, w) == 2) code = OUTFIT_ST_POLY_ROOT_FAILED;
-    else {
-      // visit_real_positive_roots + plausibility window (gauss.rs:975-981, 1148), solver order kept
-#pragma unroll 1
-      for (int k = 0; k < 8; ++k) {
-        const double re = zsm[k * kCandThreads];
-        if (re > 0.0 && fabs(zsm[(8 + k) * kCandThreads]) < P.root_imag_eps && re >= P.r2_min_au && re <= P.r2_max_au) {
-          S.roots[(size_t)n * S.n_cand + cid] = re;
-          ++n;
-        }
-      }
-      if (n == 0) code = OUTFIT_ST_GAUSS_NO_ROOTS;
-    }
-    S.code[cid] = code;
-    S.nroots[cid] = (unsigned char)n;
-  }
-  flush_work(w, work_counters);
-}
-
-// ---- P2: roots -> accepted state, f-g correction ---------------------------------------------------
-// One lane per candidate, register-resident f-g loop (dev_correct.cuh).  The triplet geometry is
-// rebuilt here (6 sincos + the cofactor inverse: ~3 % of this phase) instead of being carried from P1
-// through HBM (144 B per candidate).
-#ifndef OUTFIT_CORRECT_BPS
-#define OUTFIT_CORRECT_BPS 5  // 96 registers, 20 warps per SM: 42.3 ms against 44.5 at 4 blocks / 126 registers (round 2, r2a)
-#endif
-template <bool COUNT>
-__global__ void __launch_bounds__(kCorrectThreads, OUTFIT_CORRECT_BPS)
-correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  extern __shared__ __align__(16) double geo_sm[];
-  double *my = geo_sm + threadIdx.x;
-  const unsigned long long cid = (unsigned long long)blockIdx.x * kCorrectThreads + threadIdx.x;
-  WorkC w;
-  w.roots_accepted = 0; w.fg_iterations = 0; w.kepler_solves = 0; w.newton_steps = 0; w.sfunct_terms = 0; w.fg_skipped = 0;
-#ifdef OUTFIT_DEBUG_STRAGGLERS
-  const long long dbg_t0 = clock64();
-#endif
-  unsigned long long tr;
-  unsigned r, m;
-  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
-    int kind = 0;
-    const unsigned n = S.code[cid] == 0 ? S.nroots[cid] : 0u;
-    if (n > 0) {
-      // ---- triplet + noise -> unit vectors, heliocentric observer positions (shared memory) ----
-      const unsigned packed = S.trip[tr * P.max_triplets + r];
-      const unsigned long long o0 = B.traj_offset[tr];
-      const double *z = m > 0 ? B.noise_z + (((size_t)tr * P.max_triplets + r) * P.n_noise + (m - 1)) * 6 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        const unsigned long long gI = o0 + ((packed >> (20 - 10 * c)) & 1023u);
-        double ra = __ldg(B.ra + gI), dec = __ldg(B.dec + gI);
-        if (m > 0) {
-          ra = ra + __ldg(z + c) * (__ldg(B.sigma_ra + gI) * P.noise_scale);
-          dec = dec + __ldg(z + 3 + c) * (__ldg(B.sigma_dec + gI) * P.noise_scale);
-        }
-        double sr, cr, sd, cd;
-        sincos(ra, &sr, &cr);
-        sincos(dec, &sd, &cd);
-        my[(SL_S0 + 3 * c + 0) * kCorrectThreads] = cr * cd;
-        my[(SL_S0 + 3 * c + 1) * kCorrectThreads] = sr * cd;
-        my[(SL_S0 + 3 * c + 2) * kCorrectThreads] = sd;
-        my[(SL_R0 + 3 * c + 0) * kCorrectThreads] = __ldg(B.helio + gI);
-        my[(SL_R0 + 3 * c + 1) * kCorrectThreads] = __ldg(B.helio + B.n_obs + gI);
-        my[(SL_R0 + 3 * c + 2) * kCorrectThreads] = __ldg(B.helio + 2 * B.n_obs + gI);
-        my[(SL_T0 + c) * kCorrectThreads] = __ldg(B.mjd_tt + gI);
-      }
-      const GeoSm G{my};
-      {
-        // gauss_prelim (gauss.rs:464-549): tau, a, b, cofactor inverse (rows of S^-1)
-        const V3 S0 = G.v3(SL_S0), S1 = G.v3(SL_S1), S2 = G.v3(SL_S2);
-        const double m11 = S0.x, m12 = S1.x, m13 = S2.x, m21 = S0.y, m22 = S1.y, m23 = S2.y, m31 = S0.z, m32 = S1.z, m33 = S2.z;
-        const double mi1 = m22 * m33 - m32 * m23, mi2 = m21 * m33 - m31 * m23, mi3 = m21 * m32 - m31 * m22;
-        const double det = m11 * mi1 - m12 * mi2 + m13 * mi3;  // != 0: P1 accepted this candidate
-        const double num[9] = {mi1, m13 * m32 - m33 * m12, m12 * m23 - m22 * m13, -mi2, m11 * m33 - m31 * m13,
-                               m13 * m21 - m23 * m11, mi3, m12 * m31 - m32 * m11, m11 * m22 - m21 * m12};
-        // det != 0 and P1 found admissible roots with this very matrix: a |det| small enough to break the
-        // reciprocal form (< 1e-290) would have sent the roots out of the plausibility window
-        const double yd = 1.0 / det;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) my[(SL_I0 + q) * kCorrectThreads] = div_mk(num[q], det, yd);
-      }
-      unsigned n_solutions = 0;
-#pragma unroll 1
-      for (unsigned k = 0; k < n; ++k) {
-        V3 p1, vel;
-        double ep;
-        MidC mid;
-        if (!accept_root_fast<COUNT>(G, P, S.roots[(size_t)k * S.n_cand + cid], p1, vel, ep, mid, w)) continue;
-        ++n_solutions;
-        // prelim_orbit (gauss.rs:1238-1247): first CorrectedOrbit in discovery order, else first pushed
-        const bool first = kind == 0;
-        if (first) {
-          kind = 1;
-          S.state[0 * S.n_cand + cid] = p1.x; S.state[1 * S.n_cand + cid] = p1.y; S.state[2 * S.n_cand + cid] = p1.z;
-          S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
-          S.state[6 * S.n_cand + cid] = ep;
-        }
-        if (fg_correction_fast<COUNT>(G, P, p1, vel, mid, ep, w)) {
-          kind = 2;
-          S.state[0 * S.n_cand + cid] = p1.x; S.state[1 * S.n_cand + cid] = p1.y; S.state[2 * S.n_cand + cid] = p1.z;
-          S.state[3 * S.n_cand + cid] = vel.x; S.state[4 * S.n_cand + cid] = vel.y; S.state[5 * S.n_cand + cid] = vel.z;
-          S.state[6 * S.n_cand + cid] = ep;
-          break;
-        }
-        if (n_solutions >= P.max_tested_solutions) break;
-      }
-    }
-    S.state_kind[cid] = kind;
-#ifdef OUTFIT_DEBUG_STRAGGLERS
-    // slowest thread of the launch ((cycles >> 8) << 26 | cid) and the total thread time (cycles >> 8)
-    const unsigned long long dc = (unsigned long long)(clock64() - dbg_t0);
-    atomicMax(work_counters + 20, ((dc >> 8) << 26) | (cid & 0x3ffffffull));
-    atomicAdd(work_counters + 24, dc >> 8);
-#endif
-  }
-  if (COUNT) {
-    Work wk;
-    memset(&wk, 0, sizeof wk);
-    wk.roots_accepted = w.roots_accepted; wk.fg_iterations = w.fg_iterations; wk.kepler_solves = w.kepler_solves;
-    wk.newton_steps = w.newton_steps; wk.sfunct_terms = w.sfunct_terms; wk.fg_skipped = w.fg_skipped;
-    flush_work(wk, work_counters);
-  }
-}
-
-__device__ __forceinline__ void state_to_orbit(const IodScratch &S, unsigned long long cid, int state_kind, Orbit &orb) {
-  const V3 rr = V3{S.state[0 * S.n_cand + cid], S.state[1 * S.n_cand + cid], S.state[2 * S.n_cand + cid]};
-  const V3 vv = V3{S.state[3 * S.n_cand + cid], S.state[4 * S.n_cand + cid], S.state[5 * S.n_cand + cid]};
-  // build_result (gauss.rs:1063): rotate to ecliptic J2000, state -> elements
-  ccek1(equ_to_ecl(rr), equ_to_ecl(vv), S.state[6 * S.n_cand + cid], orb);
-  orb.corrected = state_kind == 2 ? 1 : 0;
-}
-
-// ---- P3: elements -> equinoctial -> arc RMS sum --------------------------------------------------
-#ifndef OUTFIT_SCORE_BPS
-#define OUTFIT_SCORE_BPS 6  // 80 registers: 19.4 ms against 20.2 at 5 blocks per SM (r02d)
-#endif
-template <bool COUNT>
-__global__ void __launch_bounds__(kCandThreads, OUTFIT_SCORE_BPS)
-score_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
-  const unsigned long long cid = (unsigned long long)blockIdx.x * kCandThreads + threadIdx.x;
-  Work w;
-  memset(&w, 0, sizeof w);
-  unsigned long long tr;
-  unsigned r, m;
-  if (cid < S.n_cand && decode_candidate(cid, P, S, tr, r, m)) {
-    int kind, code = 0;
-    double sum = 0.0;
-    unsigned n_arc = 0;
-    const int gcode = S.code[cid];
-    const int sk = S.state_kind[cid];
-    if (gcode != 0) { kind = 0; code = gcode; }
-    else if (sk == 0) { kind = 0; code = OUTFIT_ST_GAUSS_NO_ROOTS; }
-    else {
-      Orbit orb;
-      state_to_orbit(S, cid, sk, orb);
-      Equinoctial eq;
-      const int rq = to_equinoctial(orb, eq);
-      if (rq != 0) { kind = 1; code = rq; }
-      else {
-        // select_rms_interval (trajectory.rs:294-350)
-        const unsigned packed = S.trip[tr * P.max_triplets + r];
-        const unsigned i0 = packed >> 20, i2 = packed & 1023u;
-        const unsigned long long o0 = B.traj_offset[tr];
-        const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-        const double *T = B.mjd_tt + o0;
-        const double t1 = __ldg(T + i0), t3 = __ldg(T + i2);
-        double dtw = P.extf >= 0.0 ? (t3 - t1) * P.extf : 10.0 * (__ldg(T + n_obs - 1) - __ldg(T));
-        if (P.dtmax >= 0.0) dtw = fmax(dtw, P.dtmax);
-        unsigned is = 0, ie = n_obs - 1;
-        for (int ii = (int)i0; ii >= 0; --ii) {
-          if (t1 - __ldg(T + ii) > dtw) break;
-          is = (unsigned)ii;
-        }
-        for (unsigned ii = i2; ii < n_obs; ++ii) {
-          if (__ldg(T + ii) - t3 > dtw) break;
-          ie = ii;
-        }
-        n_arc = ie - is + 1;
-        const ScoreOrbit so = make_score_orbit(eq);
-        kind = 3;
-        if (!so.elliptic) {
-          kind = 2;
-        } else {
-#pragma unroll 1
-          for (unsigned ii = is; ii <= ie; ++ii) {
-            const unsigned long long gI = o0 + ii;
-            const double dec_o = __ldg(B.dec + gI);
-            double v;
-            if (!ephemeris_error<COUNT>(so, __ldg(T + ii), __ldg(B.ra + gI), dec_o, cos_angle(dec_o), __ldg(B.sigma_ra + gI),
-                                 __ldg(B.sigma_dec + gI),
-                                 V3{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)},
-                                 v, w)) {
-              kind = 2;
-              break;
-            }
-            const double ns = sum + v;
-            if (ns >= INFINITY) { kind = 2; break; }
-            sum = ns;
-          }
-        }
-      }
-    }
-    S.score_kind[cid] = kind;
-    S.score_code[cid] = code;
-    S.score_sum[cid] = sum;
-    S.score_narc[cid] = n_arc;
-  }
-  if (COUNT) flush_work(w, work_counters);
-}
-
-// ---- P4: per-trajectory fold, one warp per trajectory (trajectory.rs:429-545) ----------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-select_kernel(IodBatchDev B, IodDevParams P, IodScratch S, OutfitIodResult *__restrict__ out) {
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const unsigned long long tr = (unsigned long long)blockIdx.x * kWarpsPerBlock + warp;
-  if (tr >= B.n_traj) return;
-  const unsigned M = P.n_noise + 1;
-  const unsigned K = S.ktraj[tr];
-  const unsigned long long o0 = B.traj_offset[tr];
-  const unsigned n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-  OutfitIodResult res;
-  memset(&res, 0, sizeof res);
-  res.rms = NAN;
-  {
-    // An observation epoch outside the loaded ephemeris: the reference panics ("Time outside ephemeris
-    // range", horizon_data.rs:722); here the trajectory carries the error as a value and the others go on.
-    int bad = 0;
-    for (unsigned i = lane; i < n_obs; i += 32) bad |= B.obs_status[o0 + i];
-    if (__any_sync(0xffffffffu, bad != 0)) {
-      if (lane == 0) {
-        res.status = OUTFIT_ST_EPHEM_OUT_OF_RANGE;
-        out[tr] = res;
-      }
-      return;
-    }
-  }
-  if (K == 0) {
-    if (lane == 0) {
-      res.status = OUTFIT_ST_NO_FEASIBLE_TRIPLETS;
-      res.span = n_obs == 0 ? 0.0 : B.mjd_tt[o0 + n_obs - 1] - B.mjd_tt[o0];
-      out[tr] = res;
-    }
-    return;
-  }
-  const unsigned n_cand = K * M;
-  const unsigned long long cbase0 = tr * (unsigned long long)P.max_triplets * M;
-  double best_rms = INFINITY;
-  unsigned best_c = 0xffffffffu;
-  int abort_code = 0;
-  unsigned abort_c = 0xffffffffu;
-  int last_code = 0;
-  double last_val = 0.0;
-  for (unsigned cbase = 0; cbase < n_cand; cbase += 32) {
-    const unsigned c = cbase + lane;
-    int kind = -1, code = 0;
-    double sum = 0.0;
-    unsigned n_arc = 0;
-    if (c < n_cand) {
-      kind = S.score_kind[cbase0 + c];
-      code = S.score_code[cbase0 + c];
-      sum = S.score_sum[cbase0 + c];
-      n_arc = S.score_narc[cbase0 + c];
-    }
-    // (a) the first candidate whose conversion to equinoctial fails aborts the trajectory (`?`)
-    {
-      const unsigned ab = __ballot_sync(0xffffffffu, kind == 1);
-      if (ab != 0 && abort_c == 0xffffffffu) {
-        const int src = __ffs(ab) - 1;
-        abort_c = cbase + src;
-        abort_code = __shfl_sync(0xffffffffu, code, src);
-      }
-    }
-    // (b) running best with the reference's pruning rule: a candidate replaces the best iff its
-    //     full sum stays below best^2 * 2N (never pruned) and sqrt(sum / 2N) < best (strict)
-    {
-      const double denom = 2.0 * (double)n_arc;
-      const double rms_c = sqrt(sum / denom);
-      unsigned from = 0;
-      for (;;) {
-        const double cutoff = isfinite(best_rms) ? best_rms * best_rms * denom : INFINITY;
-        const bool acc = kind == 3 && lane >= from && !(sum >= cutoff) && isfinite(rms_c) && rms_c < best_rms;
-        const unsigned bal = __ballot_sync(0xffffffffu, acc);
-        if (bal == 0) break;
-        const int src = __ffs(bal) - 1;
-        best_rms = __shfl_sync(0xffffffffu, rms_c, src);
-        best_c = cbase + src;
-        from = src + 1;
-        if (from >= 32) break;
-      }
-    }
-    // (c) error of the LAST candidate in evaluation order (used only when nothing succeeded, in
-    //     which case the running best stayed +inf for every candidate)
-    if (c == n_cand - 1) {
-      if (kind == 0) { last_code = code; last_val = 0.0; }
-      else if (kind == 2) { last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = INFINITY; }
-      else if (kind == 3) { last_code = OUTFIT_ST_NON_FINITE_SCORE; last_val = sqrt(sum / (2.0 * (double)n_arc)); }
-    }
-  }
-  const unsigned last_lane = (n_cand - 1) & 31u;
-  const int l_code = __shfl_sync(0xffffffffu, last_code, last_lane);
-  const double l_val = __shfl_sync(0xffffffffu, last_val, last_lane);
-  if (lane != 0) return;
-  if (abort_c != 0xffffffffu) {
-    res.status = abort_code;
-    res.attempts = abort_c + 1;
-  } else if (best_c != 0xffffffffu) {
-    const unsigned r = best_c / M;
-    const unsigned long long cid = cbase0 + best_c;
-    Orbit orb;
-    state_to_orbit(S, cid, S.state_kind[cid], orb);
-    res.status = OUTFIT_ST_OK;
-    res.attempts = n_cand;
-    res.corrected = orb.corrected;
-    res.element_kind = orb.kind;
-    res.epoch = orb.epoch;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) res.elem[q] = orb.e[q];
-    res.rms = best_rms;
-    const unsigned packed = S.trip[tr * P.max_triplets + r];
-    res.triplet_idx[0] = packed >> 20;
-    res.triplet_idx[1] = (packed >> 10) & 1023u;
-    res.triplet_idx[2] = packed & 1023u;
-    res.triplet_rank = r;
-    res.realization = best_c - r * M;
-  } else {
-    res.status = OUTFIT_ST_NO_VIABLE_ORBIT;
-    res.cause = l_code;
-    res.cause_value = l_val;
-    res.attempts = n_cand;
-  }
-  out[tr] = res;
-}
-
-// =================================================================================================
-// bulk propagate_universal (kepler/propagation.rs:114-207)
-// =================================================================================================
-__global__ void __launch_bounds__(128)
-propagate_universal_kernel(size_t n, const double *__restrict__ rv, const double *__restrict__ t0,
-                           const double *__restrict__ t1, const double *__restrict__ psi_guess,
-                           OutfitSolverType st, double *__restrict__ out, int *__restrict__ status) {
-  // The initial guess is the one type-dependent step (elliptic: acos + a sincos Newton; hyperbolic: log,
-  // sinh and an expm1 Newton; parabolic: a cubic) and random batches mix the types inside every warp, which
-  // then pays for all of them.  The five scalars the guess needs are therefore exchanged through shared
-  // memory in TYPE ORDER within the block: thread j evaluates the guess of the j-th state of that order, so
-  // three of the four warps of a block run a single type, and every thread reads its own guess back.  The
-  // arithmetic per state is untouched (same bits).
-  __shared__ double g_in[5][128];
-  __shared__ double g_psi[128];
-  __shared__ unsigned g_cnt[4][4];
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const size_t ic = live ? i : 0;
-  const V3 r = V3{rv[ic], rv[n + ic], rv[2 * n + ic]};
-  const V3 v = V3{rv[3 * n + ic], rv[4 * n + ic], rv[5 * n + ic]};
-  double o[11];
-#pragma unroll
-  for (int q = 0; q < 11; ++q) o[q] = NAN;
-  int stt = OUTFIT_ST_OK;
-  const double r0 = bf_sqrt(dot(r, r));
-  const bool degenerate = r0 < kEps;
-  const double v2 = dot(v, v);
-  const double sig0 = bf_div(dot(r, v), kGaussK);
-  const double alpha = bf_div(v2 - bf_div(2.0 * kMu, r0), kMu);
-  const V3 h = cross(r, v);
-  double e0 = bf_sqrt(1.0 + bf_div(alpha * dot(h, h), kMu));
-  e0 = (e0 != e0) ? 0.0 : fmax(e0, 0.0);
-  const double dt = t1[ic] - t0[ic];
-  double psi_own = 0.0;
-  if (psi_guess) {
-    psi_own = psi_guess[ic];
-  } else {
-    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const unsigned key = (!live || degenerate) ? 3u : (alpha < 0.0 ? 0u : (alpha > 0.0 ? 1u : 2u));
-    unsigned rank_in_warp = 0;
-#pragma unroll
-    for (unsigned k = 0; k < 4; ++k) {
-      const unsigned b = __ballot_sync(0xffffffffu, key == k);
-      if (lane == 0) g_cnt[wib][k] = (unsigned)__popc(b);
-      if (key == k) rank_in_warp = (unsigned)__popc(b & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    unsigned pos = rank_in_warp, n_work = 0;
-    for (unsigned k = 0; k < 4; ++k)
-      for (unsigned w = 0; w < 4; ++w) {
-        const unsigned c = g_cnt[w][k];
-        if (k < key || (k == key && w < wib)) pos += c;
-        if (k < 3) n_work += c;
-      }
-    g_in[0][pos] = dt; g_in[1][pos] = r0; g_in[2][pos] = sig0; g_in[3][pos] = alpha; g_in[4][pos] = e0;
-    __syncthreads();
-    if (threadIdx.x < n_work)
-      g_psi[threadIdx.x] = prelim_kepuni_v(g_in[0][threadIdx.x], g_in[1][threadIdx.x], g_in[2][threadIdx.x],
-                                           g_in[3][threadIdx.x], g_in[4][threadIdx.x], st.convergency,
-                                           (unsigned)st.max_iter_prelim_kepuni, st.parabolic_method);
-    __syncthreads();
-    psi_own = g_psi[pos < 128 ? pos : 127];
-  }
-  if (!live) return;
-  if (degenerate) {
-    stt = OUTFIT_ST_DEGENERATE_STATE;
-  } else {
-    // initial guess (prelim_kepler/*.rs) out of line (above), Newton (newton_solver.rs:240-352) inlined with the
-    // register-resident Stumpff series of dev_correct.cuh: same operations, same bits as dev_kepler.cuh
-    double psi = psi_own;
-    const double psi0 = psi;
-    double s01[2] = {0.0, 0.0}, s2 = 0.0, s3 = 0.0;
-    WorkC wc;
-    wc.roots_accepted = 0; wc.fg_iterations = 0; wc.kepler_solves = 0; wc.newton_steps = 0; wc.sfunct_terms = 0; wc.fg_skipped = 0;
-    bool ok = false;
-    if (st.kind == OUTFIT_SOLVER_NEWTON || st.kind == OUTFIT_SOLVER_AUTO)
-      ok = kepuni_newton_fast<false>(dt, r0, sig0, alpha, st.convergency, psi, s2, s3, wc, s01);
-    if (!ok && st.kind != OUTFIT_SOLVER_NEWTON) {  // Brent-Dekker (rare): the out-of-line reference statement
-      KepIn kp;
-      kp.dt = dt; kp.r0 = r0; kp.sig0 = sig0; kp.alpha = alpha; kp.e0 = e0;
-      kp.convergency = st.convergency;
-      kp.max_iter_prelim = (unsigned)st.max_iter_prelim_kepuni;
-      kp.parabolic_newton = st.parabolic_method;
-      Work w;
-      memset(&w, 0, sizeof w);
-      const KepSol sol = solve_kepuni_brent(kp, psi0, w);
-      ok = sol.ok;
-      psi = sol.psi; s01[0] = sol.s.s0; s01[1] = sol.s.s1; s2 = sol.s.s2; s3 = sol.s.s3;
-    }
-    if (!ok) {
-      stt = st.kind == OUTFIT_SOLVER_NEWTON ? OUTFIT_ST_NEWTON_KEPLER : OUTFIT_ST_BRENT_KEPLER;
-    } else {
-      const double r1 = r0 * s01[0] + sig0 * s01[1] + s2;
-      if (r1 < kEps) {
-        stt = OUTFIT_ST_DEGENERATE_STATE;
-      } else {
-        const double fl = 1.0 - bf_div(s2, r0);
-        const double gl = bf_div(r0 * s01[1] + sig0 * s2, kGaussK);
-        const double fd = -bf_div(kGaussK, r0 * r1) * s01[1];
-        const double gd = 1.0 - bf_div(s2, r1);
-        o[0] = fl * r.x + gl * v.x; o[1] = fl * r.y + gl * v.y; o[2] = fl * r.z + gl * v.z;
-        o[3] = fd * r.x + gd * v.x; o[4] = fd * r.y + gd * v.y; o[5] = fd * r.z + gd * v.z;
-        o[6] = fl; o[7] = gl; o[8] = fd; o[9] = gd; o[10] = psi;
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 11; ++q) out[(size_t)q * n + i] = o[q];
-  status[i] = stt;
-}
-
-// =================================================================================================
-// differential orbit correction (FitLSQ), one thread per trajectory at a time: dev_lsq.cuh
-// =================================================================================================
-struct LsqBatchDev {
-  unsigned long long n_traj, n_obs;
-  const unsigned long long *traj_offset;
-  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
-  const double *scorer;  // [3][n_obs] observer position, equatorial J2000 (scorer_observer_kernel)
-  const int *obs_status; // [n_obs] 0 | OUTFIT_ST_EPHEM_OUT_OF_RANGE
-};
-
-// Scheduling: a persistent grid whose lanes fetch trajectories from a work counter and advance them ONE
-// Newton step per loop trip, so a lane whose trajectory is done (2 steps for a diverging start, 3-8 for a
-// converging one) takes the next one instead of idling until the slowest trajectory of its warp finishes
-// (3.4 ms against 4.0 ms for a fixed thread <-> trajectory mapping, identical bytes; profiles/r04_lsq_*).
-#ifndef OUTFIT_LSQ_BPS
-#define OUTFIT_LSQ_BPS 4
-#endif
-__global__ void __launch_bounds__(64, OUTFIT_LSQ_BPS)
-lsq_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ iod, OutfitLsqResult *__restrict__ out,
-                  OutfitObsFit *__restrict__ fit, double *__restrict__ tmp, unsigned long long *__restrict__ next) {
-  const double kMax = 1.7976931348623157e308;
-  unsigned num_free = 0;
-  for (int j = 0; j < 6; ++j) num_free += C.free_el[j] ? 1u : 0u;
-  // per-lane trajectory state
-  unsigned long long tr = 0, o0 = 0;
-  unsigned n_obs = 0;
-  OutfitLsqResult *res = nullptr;
-  OutfitObsFit *F = nullptr;
-  double *t_rra = nullptr, *t_rdec = nullptr, *t_chi = nullptr;
-  double el[7], el_lin[7];
-  double nm[36], cov[36], work[36], last_nm[36], last_cov[36];
-  double last_rms = kMax, prev_rms = kMax;
-  unsigned long long last_nmeas = 0, total_it = 0, outer = 0, inner = 0, stagnation = 0;
-  bool have_lin = false, converged = false, busy = false, exhausted = false, post = false;
-  int fail_code = 0;
-  for (;;) {
-    if (!busy && !exhausted) {  // fetch and set up the next trajectory
-      tr = atomicAdd(next, 1ull);
-      if (tr >= B.n_traj) {
-        exhausted = true;
-      } else {
-        o0 = B.traj_offset[tr];
-        n_obs = (unsigned)(B.traj_offset[tr + 1] - o0);
-        res = out + tr;
-        F = fit + o0;
-        t_rra = tmp + o0; t_rdec = tmp + B.n_obs + o0; t_chi = tmp + 2 * B.n_obs + o0;
-        for (unsigned i = 0; i < n_obs; ++i) {  // ObsFitData::new (obs_fit_data.rs:105-116)
-          F[i].residual_ra = 0.0; F[i].residual_dec = 0.0; F[i].chi = 0.0; F[i].selection = 0; F[i]._pad0 = 0;
-        }
-        {
-          double *z = reinterpret_cast<double *>(res);
-          for (unsigned i = 0; i < sizeof(OutfitLsqResult) / 8; ++i) z[i] = 0.0;
-        }
-        int ist = iod[tr].status;
-        for (unsigned i = 0; i < n_obs; ++i)
-          if (B.obs_status[o0 + i] != 0) ist = OUTFIT_ST_EPHEM_OUT_OF_RANGE;  // the reference panics (horizon_data.rs:722)
-        if (ist != OUTFIT_ST_OK) {
-          res->status = ist; res->kind = OUTFIT_LSQ_NONE;
-        } else {
-          Orbit orb;
-          orb.kind = iod[tr].element_kind; orb.corrected = iod[tr].corrected; orb.epoch = iod[tr].epoch;
-          for (int j = 0; j < 6; ++j) orb.e[j] = iod[tr].elem[j];
-          Equinoctial q;
-          const int rq = to_equinoctial(orb, q);
-          if (rq != 0) {
-            res->status = rq; res->kind = OUTFIT_LSQ_NONE;
-          } else {
-            el[0] = q.epoch; el[1] = q.a; el[2] = q.h; el[3] = q.k; el[4] = q.p; el[5] = q.q; el[6] = q.lambda;
-            for (int i = 0; i < 36; ++i) { last_nm[i] = 0.0; last_cov[i] = 0.0; }
-            last_rms = kMax; last_nmeas = 0; total_it = 0; fail_code = 0;
-            outer = 0; inner = 0; prev_rms = kMax; stagnation = 0; converged = false; have_lin = false;
-            busy = true; post = false;
-          }
-        }
-      }
-    }
-    if (__all_sync(0xffffffffu, exhausted && !busy)) break;
-    if (busy && !post) {
-      if (inner >= C.max_newton_iterations) {
-        post = true;
-      } else {
-        ++inner;
-        ++total_it;
-        // single_iteration (single_iteration.rs:140-317) + solve_weighted_least_squares (least_square.rs:225-327)
-        for (int i = 0; i < 36; ++i) nm[i] = 0.0;
-        double rhs[6] = {0, 0, 0, 0, 0, 0};
-        double qsum = 0.0;
-        unsigned long long active = 0;
-        for (unsigned i = 0; i < n_obs; ++i) {
-          const unsigned long long gI = o0 + i;
-          t_rra[i] = F[i].residual_ra; t_rdec[i] = F[i].residual_dec; t_chi[i] = F[i].chi;
-          if (F[i].selection != 0) continue;
-          double ra, dec, pr[6], pd[6];
-          const V3 obs{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)};
-          if (!lsq_obs_and_partials(el, __ldg(B.mjd_tt + gI), obs, ra, dec, pr, pd)) continue;
-          const double sra = __ldg(B.sigma_ra + gI), sdec = __ldg(B.sigma_dec + gI);
-          const double xr = lsq_angular_diff(__ldg(B.ra + gI) - 0.0, ra);
-          const double xd = (__ldg(B.dec + gI) - 0.0) - dec;
-          const double ca = xr / sra, cd = xd / sdec;
-          t_rra[i] = xr; t_rdec[i] = xd; t_chi[i] = sqrt(ca * ca + cd * cd);
-          const double wr = 1.0 / (sra * sra), wd = 1.0 / (sdec * sdec), wc = 0.0;
-          ++active;
-          for (int j = 0; j < 6; ++j) {
-            for (int k = 0; k < 6; ++k)
-              OFB_M6(nm, j, k) += pr[j] * wr * pr[k] + pd[j] * wd * pd[k] + wc * (pd[j] * pr[k] + pr[j] * pd[k]);
-            rhs[j] += (pr[j] * wr + pd[j] * wc) * xr + (pr[j] * wc + pd[j] * wd) * xd;
-          }
-          qsum += wr * xr * xr + wd * xd * xd + 2.0 * wc * xr * xd;
-        }
-        const unsigned long long nmeas = 2 * active;
-        for (int j = 0; j < 6; ++j)
-          if (!C.free_el[j]) {
-            for (int k = 0; k < 6; ++k) { OFB_M6(nm, j, k) = 0.0; OFB_M6(nm, k, j) = 0.0; }
-            OFB_M6(nm, j, j) = 1.0;
-            rhs[j] = 0.0;
-          }
-        const bool inv_ok = lsq_invert_normal_matrix(nm, cov, work);
-        double dx[6] = {0, 0, 0, 0, 0, 0};
-        if (inv_ok) lsq_gemv6(cov, rhs, dx);
-        for (int j = 0; j < 6; ++j)
-          if (!C.free_el[j]) dx[j] = 0.0;
-        const double new_rms = nmeas > 0 ? sqrt(qsum / (double)nmeas) : 0.0;
-        double cdx[6];
-        lsq_gemv6(nm, dx, cdx);
-        const double cnorm = sqrt(lsq_dot6(dx, cdx));
-        double corrected[6];
-        for (int j = 0; j < 6; ++j) corrected[j] = C.free_el[j] ? el[1 + j] + dx[j] : el[1 + j];
-        if (!inv_ok) { fail_code = OUTFIT_ST_LSQ_INVERSION; post = true; }
-        else if (lsq_is_bizarre(corrected, C)) { fail_code = OUTFIT_ST_LSQ_BIZARRE; post = true; }
-        else if (prev_rms < kMax && new_rms / prev_rms >= C.rms_divergence_ratio) { fail_code = OUTFIT_ST_LSQ_DIVERGED; post = true; }
-        else {
-          const bool stagnated = prev_rms < kMax && new_rms / prev_rms >= C.rms_stagnation_ratio;
-          bool stop = false;
-          if (stagnated) {
-            if (++stagnation >= C.max_stagnation_iterations) stop = true;
-          } else {
-            stagnation = 0;
-          }
-          if (stop) {
-            post = true;
-          } else {  // advance the state
-            for (int j = 0; j < 7; ++j) el_lin[j] = el[j];
-            have_lin = true;
-            for (int i = 0; i < 36; ++i) { last_nm[i] = nm[i]; last_cov[i] = cov[i]; }
-            last_rms = new_rms;
-            last_nmeas = nmeas;
-            for (int j = 0; j < 6; ++j) el[1 + j] = corrected[j];
-            for (unsigned i = 0; i < n_obs; ++i) { F[i].residual_ra = t_rra[i]; F[i].residual_dec = t_rdec[i]; F[i].chi = t_chi[i]; }
-            prev_rms = new_rms;
-            if (cnorm < C.convergence_threshold) { converged = true; post = true; }
-          }
-        }
-      }
-    }
-    if (busy && post) {  // the inner loop has ended (diff_cor.rs:400-428)
-      bool finish = fail_code != 0 || !C.enable_outlier_rejection ||
-                    (outer == 0 && last_rms < C.convergence_before_rejection_threshold) || !converged || !have_lin;
-      if (!finish) {
-        // update_observation_selection (outlier_rejection.rs:118-235) at el_lin
-        unsigned long long changes = 0;
-        for (unsigned i = 0; i < n_obs; ++i) {
-          const unsigned long long gI = o0 + i;
-          const int sel = F[i].selection;
-          if (sel == 2) continue;
-          double pr[6] = {0, 0, 0, 0, 0, 0}, pd[6] = {0, 0, 0, 0, 0, 0};
-          double wr = 1.0, wd = 1.0;
-          const double sra = __ldg(B.sigma_ra + gI), sdec = __ldg(B.sigma_dec + gI);
-          if (sel == 0) {
-            double ra, dec;
-            const V3 obs{__ldg(B.scorer + gI), __ldg(B.scorer + B.n_obs + gI), __ldg(B.scorer + 2 * B.n_obs + gI)};
-            if (lsq_obs_and_partials(el_lin, __ldg(B.mjd_tt + gI), obs, ra, dec, pr, pd)) {
-              wr = 1.0 / (sra * sra); wd = 1.0 / (sdec * sdec);
-            } else {
-              for (int j = 0; j < 6; ++j) { pr[j] = 0.0; pd[j] = 0.0; }
-            }
-          }
-          const double var_ra = sra * sra, var_dec = sdec * sdec;
-          const double cov_cross = -sra * sdec * 0.0 / (wr * wd);
-          double gga[6], ggd[6];
-          lsq_gemv6(last_cov, pr, gga);
-          lsq_gemv6(last_cov, pd, ggd);
-          const double paa = lsq_dot6(pr, gga), pdd = lsq_dot6(pd, ggd), pad = lsq_dot6(pr, ggd);
-          const double v00 = var_ra - paa, v01 = cov_cross - pad, v11 = var_dec - pdd;
-          const double det = v00 * v11 - v01 * v01;
-          const double scale = fmax(fabs(v00), fabs(v11));
-          if (fabs(det) < kEps * scale * scale || scale == 0.0) continue;
-          const double i00 = v11 / det, i01 = -v01 / det, i10 = -v01 / det, i11 = v00 / det;
-          const double rr = F[i].residual_ra, rd = F[i].residual_dec;
-          double y0 = i00 * rr, y1 = i10 * rr;
-          y0 = i01 * rd + y0;
-          y1 = i11 * rd + y1;
-          const double chi2 = rr * y0 + rd * y1;
-          if (sel == 0 && chi2 > C.chi2_reject) { F[i].selection = 1; ++changes; }
-          else if (sel == 1 && chi2 <= C.chi2_recover) { F[i].selection = 0; ++changes; }
-        }
-        if (changes == 0) finish = true;
-        else if (++outer > C.max_outlier_rejection_passes) finish = true;
-        else { inner = 0; prev_rms = kMax; stagnation = 0; converged = false; have_lin = false; post = false; }
-      }
-      if (finish) {
-        res->status = OUTFIT_ST_OK;
-        res->total_newton_iterations = total_it;
-        if (fail_code) {  // Err(_) => Ok(initial_orbit) (mod.rs:113)
-          res->kind = OUTFIT_LSQ_IOD_FALLBACK;
-          res->fallback_cause = fail_code;
-          res->epoch = iod[tr].epoch;
-          for (int j = 0; j < 6; ++j) res->elem[j] = iod[tr].elem[j];
-          res->normalised_rms = iod[tr].rms;
-          for (unsigned i = 0; i < n_obs; ++i) { F[i].residual_ra = 0.0; F[i].residual_dec = 0.0; F[i].chi = 0.0; F[i].selection = 0; }
-        } else {  // rescale_covariance (least_square.rs:371-394)
-          double mu = 1.0;
-          if (num_free < last_nmeas) {
-            const double factor = sqrt((double)last_nmeas / (double)(last_nmeas - num_free));
-            mu = last_rms > 1.0 ? last_rms * factor : factor;
-          }
-          const double mu2 = mu * mu;
-          res->kind = OUTFIT_LSQ_CORRECTED;
-          res->epoch = el[0];
-          for (int j = 0; j < 6; ++j) res->elem[j] = el[1 + j];
-          for (int i = 0; i < 36; ++i) {
-            res->covariance[i] = last_cov[i] * mu2;
-            res->normal_matrix[i] = last_nm[i] / mu2;
-          }
-          for (int j = 0; j < 6; ++j) res->sigma[j] = sqrt(last_cov[7 * j] * mu2);
-          res->normalised_rms = last_rms;
-          res->num_measurements = last_nmeas;
-        }
-        busy = false;
-      }
-    }
-  }
-}
-
-// =================================================================================================
-// self-test of the branch-free arithmetic (dev_kepler.cuh: bf_rcp / bf_div / bf_sqrt) against the intrinsics
-// =================================================================================================
-__global__ void __launch_bounds__(256) selftest_arith_kernel(unsigned long long n, unsigned long long seed, int exp_range,
-                                                            unsigned long long *__restrict__ mismatches) {
-  unsigned long long bad_r = 0, bad_d = 0, bad_s = 0, bad_t = 0;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    unsigned long long st = seed + 0x9e3779b97f4a7c15ull * i;
-    const unsigned long long u = splitmix64_next(st), v = splitmix64_next(st), e = splitmix64_next(st);
-    const long long ea = 1023 - exp_range + (long long)(e % (unsigned long long)(2 * exp_range));
-    const long long eb = 1023 - exp_range + (long long)((e >> 32) % (unsigned long long)(2 * exp_range));
-    const double a = __longlong_as_double((long long)((u & 0x800fffffffffffffull) | ((unsigned long long)ea << 52)));
-    const double b = __longlong_as_double((long long)((v & 0x800fffffffffffffull) | ((unsigned long long)eb << 52)));
-    if (__double_as_longlong(bf_rcp(b)) != __double_as_longlong(__drcp_rn(b))) ++bad_r;
-    if (__double_as_longlong(bf_div(a, b)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_d;
-    const double p = fabs(a);
-    if (__double_as_longlong(bf_sqrt(p)) != __double_as_longlong(__dsqrt_rn(p))) ++bad_s;
-    // angles: uniform in (-64, 64) from one draw, magnitudes down to 2^-40 from the other
-    const double ang = ((double)(long long)(u >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 128.0;
-    const double small = __longlong_as_double((long long)((v & 0x800fffffffffffffull) | ((unsigned long long)(1023 - (e % 40)) << 52)));
-    double s0, c0, s1, c1;
-    sincos(ang, &s0, &c0); sincos_angle(ang, &s1, &c1);
-    if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
-    if (__double_as_longlong(cos(ang)) != __double_as_longlong(c1)) ++bad_t;  // cos() alone == the cosine of sincos()
-    sincos(small, &s0, &c0); sincos_angle(small, &s1, &c1);
-    if (__double_as_longlong(s0) != __double_as_longlong(s1) || __double_as_longlong(c0) != __double_as_longlong(c1)) ++bad_t;
-    // atan2: the operand pair (a, b) of the division test (ratios over +-2 exp_range binades, all
-    // quadrants) and a pair of comparable magnitudes
-    if (__double_as_longlong(atan2(a, b)) != __double_as_longlong(atan2_finite(a, b))) ++bad_t;
-    if (__double_as_longlong(atan2(ang, small)) != __double_as_longlong(atan2_finite(ang, small))) ++bad_t;
-    if (__double_as_longlong(atan2(small, ang)) != __double_as_longlong(atan2_finite(small, ang))) ++bad_t;
-    const double c2 = ang * 0.37 + small;
-    if (__double_as_longlong(atan2(ang, c2)) != __double_as_longlong(atan2_finite(ang, c2))) ++bad_t;
-  }
-  if (bad_t) atomicAdd(mismatches + 3, bad_t);
-  if (bad_r) atomicAdd(mismatches + 0, bad_r);
-  if (bad_d) atomicAdd(mismatches + 1, bad_d);
-  if (bad_s) atomicAdd(mismatches + 2, bad_s);
-}
-
-// =================================================================================================
-// FP64 pipe probe
-// =================================================================================================
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters) {
-  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
-  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
-  const double m = 1.0000001, c = 1e-9;
-  for (int i = 0; i < iters; ++i) {
-    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-  }
-  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  if (s == 12345.678) sink[0] = s;
-}
+#include "k_iod.cuh"
+#include "k_bulk.cuh"
 
 // =================================================================================================
 // context + C-ABI
@@ -960,6 +69,7 @@ struct OutfitCtx {
   unsigned phase_observer_kernels = 0;
   bool phase_valid = false;
   bool count_work = true;  // work counters on (outfit_b200_set_work_counters)
+  int aberration_order = 1;  // EphemerisConfig::aberration (outfit_b200_set_ephemeris_config)
 };
 
 static int fail(OutfitCtx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -1954,11 +1064,32 @@ static int ephemeris_device_impl(OutfitCtx *ctx, size_t n_orbits, const int32_t 
   int *d_ost;
   int rc = ephemeris_observer_table(ctx, n_epochs, mjd_tt, mjd_ut1, d_bf, bf, stream, &e_stride, &d_table, &d_ost);
   if (rc) return rc;
-  ephemeris_twobody_kernel<<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
-      n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
+  if (ctx->aberration_order == 2)
+    ephemeris_twobody_kernel<true><<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
+        n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
+  else
+    ephemeris_twobody_kernel<false><<<(unsigned)((n_orbits + kEphThreads - 1) / kEphThreads), kEphThreads, 0, stream>>>(
+        n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table, d_ost, out, status);
   CK(cudaGetLastError());
   return OUTFIT_OK;
 }
+
+extern "C" void outfit_b200_ephemeris_config_default(OutfitEphemerisConfig *c) {  // EphemerisConfig::default()
+  if (!c) return;
+  c->propagator = OUTFIT_PROPAGATOR_TWOBODY;
+  c->aberration = OUTFIT_ABERRATION_FIRST;
+}
+extern "C" int outfit_b200_set_ephemeris_config(OutfitCtx *ctx, const OutfitEphemerisConfig *c) {
+  if (!ctx || !c) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (c->propagator != OUTFIT_PROPAGATOR_TWOBODY)
+    return fail(ctx, OUTFIT_E_UNSUPPORTED, "PropagatorKind::NBody (DOP853 with planetary perturbations) is not implemented on the device");
+  if (c->aberration != OUTFIT_ABERRATION_FIRST && c->aberration != OUTFIT_ABERRATION_SECOND)
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "aberration must be OUTFIT_ABERRATION_FIRST or _SECOND");
+  ctx->aberration_order = c->aberration == OUTFIT_ABERRATION_SECOND ? 2 : 1;
+  return OUTFIT_OK;
+}
+extern "C" int outfit_b200_group_set_ephemeris_config(OutfitGroup *g, const OutfitEphemerisConfig *c);
 
 extern "C" int outfit_b200_ephemeris_twobody_device(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind,
                                                     const double *epoch, const double *elem, size_t n_epochs,
@@ -2033,8 +1164,12 @@ static int ephemeris_range(OutfitCtx *ctx, size_t n_all, size_t i0, size_t i1, c
     if (e == cudaSuccess) e = cudaEventRecord(ev_up, up);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(run, ev_up, 0);
     if (e != cudaSuccess) break;
-    ephemeris_twobody_kernel<<<(unsigned)((c + kEphThreads - 1) / kEphThreads), kEphThreads, 0, run>>>(
-        c, d_kind, d_epoch, d_elem, n_epochs, e_stride, d_tt, d_table, d_ost, d_out, d_st);
+    if (ctx->aberration_order == 2)
+      ephemeris_twobody_kernel<true><<<(unsigned)((c + kEphThreads - 1) / kEphThreads), kEphThreads, 0, run>>>(
+          c, d_kind, d_epoch, d_elem, n_epochs, e_stride, d_tt, d_table, d_ost, d_out, d_st);
+    else
+      ephemeris_twobody_kernel<false><<<(unsigned)((c + kEphThreads - 1) / kEphThreads), kEphThreads, 0, run>>>(
+          c, d_kind, d_epoch, d_elem, n_epochs, e_stride, d_tt, d_table, d_ost, d_out, d_st);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaEventRecord(ev_run, run);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(down, ev_run, 0);
@@ -2190,6 +1325,14 @@ extern "C" int outfit_b200_group_load_ephemeris(OutfitGroup *g, const double *ch
   for (OutfitCtx *c : g->ctx) {  // replicated: 0.5 - 46 MB, read-only
     const int rc = outfit_b200_load_ephemeris(c, cheb, n_blocks, block_stride, jd_start, block_days, ipt, emrat);
     if (rc) { g->last_error = c->last_error; return rc; }
+  }
+  return OUTFIT_OK;
+}
+extern "C" int outfit_b200_group_set_ephemeris_config(OutfitGroup *g, const OutfitEphemerisConfig *c) {
+  if (!g) return OUTFIT_E_INVALID_ARGUMENT;
+  for (OutfitCtx *x : g->ctx) {
+    const int rc = outfit_b200_set_ephemeris_config(x, c);
+    if (rc) { g->last_error = x->last_error; return rc; }
   }
   return OUTFIT_OK;
 }

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <sstream>
 #include <string>
@@ -182,6 +183,29 @@ class Ut1Table {
 
 // Records of one trajectory -> Observation rows (TT epochs, constant sigma, UT1 = UTC + dut1 or the table's)
 struct Site { double lon_deg, rho_cos, rho_sin; };
+
+// MPC observatory list (ObsCodes.html / obscodes.txt) -> parallax constants by code.  Fixed columns: code 1-3,
+// east longitude 5-13, rho cos phi' 14-21, rho sin phi' 22-30; space-based / roving entries (blank constants)
+// are skipped.  Same rule as outfit_b200/mpc80.py: parse_obscodes.
+inline std::map<std::string, Site> parse_obscodes(const std::string &text) {
+  std::map<std::string, Site> out;
+  std::istringstream in(text);
+  std::string ln;
+  auto number = [](std::string f, double &v) {
+    f.erase(std::remove(f.begin(), f.end(), ' '), f.end());
+    if (f.empty()) return false;
+    char *end = nullptr;
+    v = std::strtod(f.c_str(), &end);
+    return end && *end == '\0';
+  };
+  while (std::getline(in, ln)) {
+    if (ln.size() < 30 || ln[0] == '<' || ln.compare(0, 4, "Code") == 0) continue;
+    Site s;
+    if (!number(ln.substr(4, 9), s.lon_deg) || !number(ln.substr(13, 8), s.rho_cos) || !number(ln.substr(21, 9), s.rho_sin)) continue;
+    out[ln.substr(0, 3)] = s;
+  }
+  return out;
+}
 inline std::vector<Observation> to_observations(const std::vector<Mpc80Record> &recs,
                                                 const std::map<std::string, Site> &sites, double sigma_arcsec = 0.5,
                                                 double dut1_s = 0.0, const Ut1Table *ut1 = nullptr) {

@@ -97,18 +97,46 @@ def parse(text, single_trajectory=False):
     return out
 
 
-def body_fixed_position(obscode):
-    """Earth-fixed observer position in AU (observer_extension.rs:159-171: lon, rho cos, rho sin)."""
-    lon, rc, rs = OBSERVATORIES[obscode]
+def parse_obscodes(text):
+    """MPC observatory list (ObsCodes.html / obscodes.txt) -> {code: (east longitude deg, rho cos phi', rho sin phi')}.
+    Fixed columns: code 1-3, longitude 5-13, cos 14-21, sin 22-30, name from 31.  Space-based / roving entries
+    (blank constants) are skipped."""
+    out = {}
+    for ln in text.splitlines():
+        if len(ln) < 30 or ln.startswith(("<", "Code")):
+            continue
+        code = ln[0:3]
+        try:
+            lon, rc, rs = float(ln[4:13]), float(ln[13:21]), float(ln[21:30].replace(" ", ""))
+        except ValueError:
+            continue
+        out[code] = (lon, rc, rs)
+    return out
+
+
+def load_obscodes(path):
+    with open(path, errors="replace") as f:
+        return parse_obscodes(f.read())
+
+
+def body_fixed_position(obscode, observatories=None):
+    """Earth-fixed observer position in AU (observer_extension.rs:159-171: lon, rho cos, rho sin).
+    `observatories`: extra / overriding {code: (lon deg, rho cos, rho sin)} entries, e.g. parse_obscodes()."""
+    table = OBSERVATORIES if not observatories else {**OBSERVATORIES, **observatories}
+    if obscode not in table:
+        raise KeyError(f"observatory code {obscode!r} is not in the built-in table ({', '.join(sorted(OBSERVATORIES))}): pass "
+                       "observatories={code: (east_lon_deg, rho_cos_phi, rho_sin_phi)} or the parsed MPC ObsCodes list "
+                       "(mpc80.load_obscodes)")
+    lon, rc, rs = table[obscode]
     lon = math.radians(lon)
     return np.array([ERAU * rc * math.cos(lon), ERAU * rc * math.sin(lon), ERAU * rs])
 
 
-def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0, ut1_table=None):
+def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0, ut1_table=None, observatories=None):
     """{id: [record, ...]} -> (ids, batch): the body-fixed flavour of OutfitObsBatch.  Each trajectory is
     sorted by TT epoch (obs_dataset_api.rs:222-223); UT1 = UTC + dut1_s, or -- with a `ut1.Ut1Table`
     read from JPL's latest_eop2.long -- what `epoch.to_ut1(provider).to_mjd_tai_days()` gives
-    (observer_extension.rs:191-192)."""
+    (observer_extension.rs:191-192).  `observatories`: see body_fixed_position."""
     ids = list(trajectories)
     rows = []
     offs = [0]
@@ -124,7 +152,7 @@ def to_batch(trajectories, sigma_arcsec=0.5, dut1_s=0.0, ut1_table=None):
         "mjd_ut1": mjd_utc + dut1_s / 86400.0,
         "ra": np.array([r["ra"] for r in rows]), "dec": np.array([r["dec"] for r in rows]),
         "sigma_ra": np.full(n, sigma_arcsec * ARCSEC), "sigma_dec": np.full(n, sigma_arcsec * ARCSEC),
-        "body_fixed": np.ascontiguousarray(np.stack([body_fixed_position(r["obscode"]) for r in rows], axis=1)) if n
+        "body_fixed": np.ascontiguousarray(np.stack([body_fixed_position(r["obscode"], observatories) for r in rows], axis=1)) if n
         else np.zeros((3, 0)),
         "noise_z": None,
     }

@@ -14,8 +14,14 @@ int main(int argc, char **argv) {
   std::ifstream g(argv[2]);
   const std::string eop((std::istreambuf_iterator<char>(g)), std::istreambuf_iterator<char>());
   Ut1Table ut1 = Ut1Table::from_eop2_text(eop);
-  std::map<std::string, Site> sites = {{"500", {0.0, 0.0, 0.0}}, {"G96", {249.21128, 0.845111, 0.533614}},
-                                       {"F51", {203.74409, 0.936241, 0.351543}}};
+  // the site table from the MPC observatory list's fixed columns (same rule as mpc80.parse_obscodes)
+  std::map<std::string, Site> sites = parse_obscodes(
+      "Code  Long.   cos      sin    Name\n"
+      "500   0.0000 0.00000  0.00000  Geocentric\n"
+      "G96 249.211280.845111+0.533614Mt. Lemmon Survey\n"
+      "C51                           WISE\n"
+      "F51 203.744090.936241+0.351543Pan-STARRS 1, Haleakala\n");
+  std::printf("sites %zu\n", sites.size());
   auto obs = to_observations(traj[0].second, sites, 0.5, 0.0, &ut1);
   for (const Observation &o : obs)
     std::printf("obs %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", o.mjd_tt, o.ra, o.dec, o.sigma_ra, o.body_fixed[0],

@@ -160,3 +160,25 @@ def test_quick_start_example_host_side(tmp_path):
                    "<ra>180.5</ra><dec>12.25</dec><rmsRA>0.2</rmsRA><rmsDec>0.2</rmsDec></optical></ades>")
     out = subprocess.run(exe + [str(xml)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "1 trajectory(ies), 1 observations" in out.stdout, out.stderr[-800:]
+
+
+def test_observatory_table_argument_and_obscodes_parser():
+    """An observatory the built-in table does not hold: a clear error naming the code, or parallax constants from
+    the caller / the MPC ObsCodes list (fixed columns: code 1-3, longitude 5-13, cos 14-21, sin 22-30)."""
+    from outfit_b200 import mpc80
+    txt = ("Code  Long.   cos      sin    Name\n"
+           "000   0.0000 0.62411 +0.77873 Greenwich\n"
+           "G96 249.211280.845111+0.533614Mt. Lemmon Survey\n"
+           "C51                           WISE\n"
+           "T05 203.7429 0.936235+0.351547ATLAS-HKO, Haleakala\n")
+    t = mpc80.parse_obscodes(txt)
+    assert t == {"000": (0.0, 0.62411, 0.77873), "G96": (249.21128, 0.845111, 0.533614), "T05": (203.7429, 0.936235, 0.351547)}
+    with pytest.raises(KeyError, match="T05"):
+        mpc80.body_fixed_position("T05")
+    bf = mpc80.body_fixed_position("T05", t)
+    assert abs(np.linalg.norm(bf) / mpc80.ERAU - np.hypot(0.936235, 0.351547)) < 1e-12
+    rec = dict(mjd_utc=59000.0, ra=1.0, dec=0.1, obscode="T05")
+    ids, b = mpc80.to_batch({"x": [rec]}, observatories=t)
+    assert np.array_equal(b["body_fixed"][:, 0], bf)
+    with pytest.raises(KeyError):
+        mpc80.to_batch({"x": [rec]})

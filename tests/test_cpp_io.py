@@ -33,6 +33,7 @@ def test_cpp_host_io_matches_python(tmp_path):
     assert out.returncode == 0, out.stderr
     rows = [ln.split() for ln in out.stdout.splitlines()]
     assert rows[0] == ["ntraj", "1", "id", "K09R05F", "n", "3"]
+    assert ["sites", "3"] in rows  # parse_obscodes: 500, G96, F51 (the space-based entry is skipped)
     got = np.array([[float(x) for x in r[1:]] for r in rows if r[0] == "obs"])
     # the Python chain on the same files
     tr = mpc80.parse(obs.read_text(), single_trajectory=True)

@@ -40,7 +40,9 @@ def report(oracle):
     return rep
 
 
-@pytest.mark.parametrize("key,min_plain", [("c3", 0.90), ("c4", 0.90), ("c3_strict_no_noise", 0.90)])
+# measured (profiles/parity_r02.json, full scale): 0.9628 / 0.9662 / 0.9689 inside the plain north-star tolerance
+# (the oracle against itself with RA moved by one ulp: 0.912 / 0.927 / 0.920)
+@pytest.mark.parametrize("key,min_plain", [("c3", 0.955), ("c4", 0.955), ("c3_strict_no_noise", 0.96)])
 def test_iod_sweep(report, key, min_plain):
     r = report[key]
     n = r["n_trajectories"]
@@ -52,7 +54,7 @@ def test_iod_sweep(report, key, min_plain):
     # the GPU sits inside the algorithm's own one-ulp sensitivity: at least as many trajectories inside the plain
     # tolerance as the oracle keeps against itself when RA moves by one ulp (minus sampling noise)
     assert r["plain_both_fraction"] >= r["oracle_vs_itself_ra_plus_1ulp"]["plain_both_fraction"] - 0.02
-    assert r["outside_plain"]["unexplained"] <= max(1, int(2e-4 * n)), r["outside_plain"]
+    assert r["outside_plain"]["unexplained"] == 0, r["outside_plain"]
     assert r["epoch_abs_err_days_max"] <= 1e-8 or r["outside_plain"]["oracle_discontinuous_under_1ulp"] > 0
 
 
@@ -60,12 +62,15 @@ def test_lsq_sweep(report):
     r = report["lsq"]
     assert r["n_outcome_flips"] <= max(3, int(2e-3 * r["n_trajectories"])), r
     assert r["fallback_orbits_bitwise_equal"]
-    assert r["plain_fraction"] >= 0.97, r
+    assert r["plain_fraction"] >= 0.985, r  # measured 0.9911
 
 
 def test_c2_sweep(report):
     r = report["c2"]
-    assert r["n_status_mismatch"] == 0 and r["ok_fraction"] > 0.999
+    # a status may differ only where the ORACLE's own status flips under random 1-ulp moves of the state (a Brent /
+    # Newton budget on the edge): measured 1 in 10^7 (profiles/parity_r02.json)
+    assert r["n_status_mismatch"] == r["status_mismatches_proven_oracle_unstable"] and r["n_status_mismatch"] <= max(1, int(1e-6 * r["n"]))
+    assert r["ok_fraction"] > 0.999
     assert r["within_tolerance_fraction"] == 1.0, r
     assert r["r_rel_err"]["p50"] < 1e-13
 
@@ -73,4 +78,4 @@ def test_c2_sweep(report):
 def test_c5_sweep(report):
     r = report["c5"]
     assert r["status_exact_fraction"] == 1.0 and r["failed_entries_are_nan"]
-    assert r["within_tolerance_fraction"] >= 0.9999, r
+    assert r["within_tolerance_fraction"] >= 0.999999, r

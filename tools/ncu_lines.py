@@ -19,7 +19,8 @@ for r in rows[hi + 1:]:
     if len(r) < len(hdr) or r[0] == "Address":
         continue
     try:
-        prof.append((r[idx["Source"]].strip(), int(r[idx["# Samples"]] or 0), int(r[idx["Instructions Executed"]] or 0)))
+        prof.append((r[idx["Source"]].strip(), int(r[idx["# Samples"]] or 0), int(r[idx["Instructions Executed"]] or 0),
+                     int(r[idx["Thread Instructions Executed"]] or 0)))
     except ValueError:
         pass
 tmp = tempfile.mkdtemp()
@@ -48,9 +49,9 @@ print(f"opcode mismatches in the first {n}: {bad}")
 if bad or len(prof) != len(ins):
     print("the in-tree build is not the profiled build: no line attribution")
     sys.exit(0)
-by = Counter(); ex = Counter(); tot = sum(p[1] for p in prof); tex = sum(p[2] for p in prof)
+by = Counter(); ex = Counter(); th = Counter(); tot = sum(p[1] for p in prof); tex = sum(p[2] for p in prof)
 for i in range(n):
-    by[ins[i][1]] += prof[i][1]; ex[ins[i][1]] += prof[i][2]
+    by[ins[i][1]] += prof[i][1]; ex[ins[i][1]] += prof[i][2]; th[ins[i][1]] += prof[i][3]
 src_cache = {}
 def src(f, l):
     for d in ("outfit_b200/csrc", "include"):
@@ -64,4 +65,8 @@ byfile = Counter()
 for (f, l), v in by.items(): byfile[f] += v
 print("samples by file:", ", ".join(f"{f} {100*v/tot:.1f}%" for f, v in byfile.most_common(8)))
 for (f, l), v in by.most_common(topn):
-    print(f"{100*v/tot:5.2f}% smp {100*ex[(f,l)]/tex:5.2f}% exe  {f}:{l}: {src(f, l)}")
+    print(f"{100*v/tot:5.2f}% smp {100*ex[(f,l)]/tex:5.2f}% exe {th[(f,l)]/max(1,ex[(f,l)]):5.1f} lanes  {f}:{l}: {src(f, l)}")
+# lanes per executed instruction by source file (where the divergence is)
+fx = Counter(); ft = Counter()
+for (f, l), v in ex.items(): fx[f] += v; ft[f] += th[(f, l)]
+print("lanes per instruction by file:", ", ".join(f"{f} {ft[f]/max(1,fx[f]):.1f} ({100*fx[f]/tex:.0f}% exe)" for f, _ in fx.most_common(8)))

@@ -156,9 +156,32 @@ def iod_config_report(ctx, O, synth, table, et, name, T, n_obs, seed, K=30, nn=1
         e_o, r_o = ee[~plain], er[~plain]
         within = (e_o <= np.maximum(ELEM_TOL, FLOOR_FACTOR * ef)) & (r_o <= np.maximum(RMS_TOL, FLOOR_FACTOR * rf))
         near_parab = (want["elem"][out_idx][:, 1] > 0.99) | (got["elem"][out_idx][:, 1] > 0.99)
+        # second stage: the four uniform probes move every observation the same way; trajectories they leave
+        # unexplained get 64 random per-observation +-1 ulp moves (each RA / Dec up, down or untouched)
+        second = np.flatnonzero(~within & ~unstable & ~near_parab)
+        if len(second):
+            sub2 = take_trajectories(batch, out_idx[second])
+            base2 = want[out_idx[second]]
+            rng = np.random.default_rng(12345)
+            for _ in range(64):
+                ob = O.from_soa_batch(sub2)
+                for key in ("ra", "dec"):
+                    sg = rng.integers(-1, 2, size=len(ob[key]))
+                    ob[key] = np.where(sg > 0, np.nextafter(ob[key], np.inf), np.where(sg < 0, np.nextafter(ob[key], -np.inf), ob[key]))
+                pert = O.fit_full_iod(ob, et, op, n_threads=0)
+                flip = int_mismatch(pert, base2)
+                jump = ~flip & (np.abs(pert["epoch"] - base2["epoch"]) > 1e-8)
+                unstable[second] |= flip | jump
+                good = ~flip & ~jump
+                e2 = np.where(good, elem_err(pert["elem"], base2["elem"]), 0.0)
+                r2 = np.where(good, np.abs(pert["rms"] - base2["rms"]) / np.maximum(np.abs(base2["rms"]), 1e-300), 0.0)
+                ef[second] = np.maximum(ef[second], e2)
+                rf[second] = np.maximum(rf[second], r2)
+            within = (e_o <= np.maximum(ELEM_TOL, FLOOR_FACTOR * ef)) & (r_o <= np.maximum(RMS_TOL, FLOOR_FACTOR * rf))
         ratio = np.maximum(e_o / np.maximum(ef, 1e-300), r_o / np.maximum(rf, 1e-300))
         unexplained = ~within & ~unstable & ~near_parab
-        rep["outside_plain"] = {"oracle_discontinuous_under_1ulp": int(unstable.sum()),
+        rep["outside_plain"] = {"second_stage_probed": int(len(second)),
+                                "oracle_discontinuous_under_1ulp": int(unstable.sum()),
                                 "within_256x_oracle_1ulp_sensitivity": int((within & ~unstable).sum()),
                                 "near_parabolic_e_gt_0_99": int((near_parab & ~within & ~unstable).sum()),
                                 "unexplained": int(unexplained.sum()),
@@ -220,6 +243,22 @@ def c2_report(ctx, O, synth, n, log=print):
     t1 = time.perf_counter()
     want, wst = O.propagate_universal_batch(rv, ta, tb, 2, st.convergency, 0)
     log(f"[c2] {n} propagations: gpu+synth {t1 - t0:.1f} s, oracle {time.perf_counter() - t1:.1f} s")
+    # every status mismatch: is the ORACLE's own status stable under random 1-ulp moves of the state?
+    mism = np.flatnonzero(gst != wst)
+    mrows = []
+    rng = np.random.default_rng(777)
+    for i in mism[:50]:
+        same = 0
+        for _ in range(64):
+            p = rv[:, i:i + 1].copy()
+            sg = rng.integers(-1, 2, size=6)
+            for q in range(6):
+                if sg[q]:
+                    p[q, 0] = np.nextafter(p[q, 0], np.inf if sg[q] > 0 else -np.inf)
+            _, s1 = O.propagate_universal_batch(np.ascontiguousarray(p), ta[i:i + 1].copy(), tb[i:i + 1].copy(), 2, st.convergency, 1)
+            same += int(s1[0] == wst[i])
+        mrows.append({"index": int(i), "oracle_status": int(wst[i]), "gpu_status": int(gst[i]),
+                      "oracle_keeps_its_status_in_64_random_1ulp_probes": same, "oracle_unstable_under_1ulp": bool(same < 64)})
     ok = (wst == 0) & (gst == 0)
     sr = np.linalg.norm(want[0:3, ok], axis=0)
     sv = np.linalg.norm(want[3:6, ok], axis=0)
@@ -228,6 +267,7 @@ def c2_report(ctx, O, synth, n, log=print):
     efg = np.abs(got[6:10, ok] - want[6:10, ok]).max(axis=0)
     return {"config": "C2 propagate_universal, SolverKind::Auto, convergency 100 eps", "n": int(n),
             "status_exact_fraction": float((gst == wst).mean()), "n_status_mismatch": int((gst != wst).sum()),
+            "status_mismatches": mrows, "status_mismatches_proven_oracle_unstable": int(sum(m["oracle_unstable_under_1ulp"] for m in mrows)),
             "status_histogram": {str(int(k)): int(v) for k, v in zip(*np.unique(wst, return_counts=True))},
             "ok_fraction": float(ok.mean()), "bitwise_equal_fraction": float((got[:, ok] == want[:, ok]).all(axis=0).mean()),
             "tolerance": "1e-9 relative to |r1|, |v1| (the reference's own: 1e-9 / 1e-8 absolute, propagation.rs:245-262)",
@@ -256,15 +296,17 @@ def c5_report(ctx, O, synth, et, n_orb, n_ep, log=print):
             d = np.abs((g - w + np.pi) % (2 * np.pi) - np.pi)
         elif nm in ("geocentric_dist", "heliocentric_dist"):
             d = np.abs(g - w) / np.abs(w)
+        elif nm in ("radial_velocity", "d_ra_dt", "d_dec_dt"):
+            d = np.abs(g - w) / np.maximum(1.0, np.abs(w) / 1e-2)  # absolute below 1e-2 per day, relative above (near the pole)
         else:
             d = np.abs(g - w)
-        errs[nm] = {"p50": pct(d, .5), "max": float(d.max()), "tolerance": tol[nm]}
+        errs[nm] = {"p50": pct(d, .5), "max": float(d.max()), "tolerance": tol[nm], "n_outside": int((d > tol[nm]).sum())}
         within &= d <= tol[nm]
     return {"config": "C5 two-body Combined ephemeris, mixed element kinds, one topocentric observer", "orbits": int(n_orb), "epochs": int(n_ep),
             "entries": int(n_orb * n_ep), "status_exact_fraction": float((gst == wst).mean()), "ok_fraction": float(ok.mean()),
             "failed_entries_are_nan": bool(np.isnan(got[:, gst != 0]).all()),
             "within_tolerance_fraction": float(within.mean()), "errors": errs,
-            "tolerance_note": "angles absolute (rad), distances relative, rates absolute (AU/day, rad/day)"}
+            "tolerance_note": "angles absolute (rad), distances relative, rates absolute (AU/day, rad/day) below 1e-2 per day and relative to |rate| / 1e-2 above"}
 
 
 def run(scale=1.0, out_path=None, log=print):
