@@ -140,35 +140,43 @@ struct EphOrbitC {
   double a, h, k, lambda, t_ref, n_mot, lon_peri, ch, ck, bhk, sx0, cx0;
   V3 fv, gv;
 };
-__device__ __forceinline__ bool eph_retarded_position(const EphOrbitC &o, double t, V3 &pos_equ) {
+__device__ __forceinline__ bool eph_retarded_position(const EphOrbitC &o, double t, bool active, V3 &pos_equ) {
+  // called by EVERY lane of the warp (inactive ones with active = false): the Newton trip count is warp-uniform
   const double dt = t - o.t_ref;
   double lam1 = rem_euclid(o.lambda + o.n_mot * (dt - 0.0), kTwoPi);
   if (lam1 < o.lon_peri) lam1 += kTwoPi;
   const double eps = kEps * 1e2;
   double x = kPi + o.lon_peri, sF = o.sx0, cF = o.cx0;
   int iter = 0;
-  bool last = false, have = true;
-  for (;;) {
-    if (!have) sincos_angle(x, &sF, &cF);
-    have = false;
-    if (last) break;
-    const double f = x - o.k * sF + o.h * cF - lam1;
-    const double d = 1.0 - o.k * cF - o.h * sF;
-    if (fabs(f) < eps) break;
-    if (fabs(d) < eps) {
-      if (iter == 0) { x = x + 1.0; iter = 1; continue; }
-      return false;
+  bool run = active, last = false, ok = true, have = true;
+  while (__any_sync(0xffffffffu, run)) {
+    if (run) {
+      if (!have) sincos_angle(x, &sF, &cF);
+      have = false;
+      if (last) {
+        run = false;
+      } else {
+        const double f = x - o.k * sF + o.h * cF - lam1;
+        const double d = 1.0 - o.k * cF - o.h * sF;
+        if (fabs(f) < eps) {
+          run = false;
+        } else if (fabs(d) < eps) {
+          if (iter == 0) { x = x + 1.0; iter = 1; }
+          else { ok = false; run = false; }
+        } else {
+          const double x1 = x - bf_div(f, d);
+          const bool conv = fabs(x - x1) < eps;
+          x = x1;
+          if (conv) last = true;
+          else if (++iter >= 25) { ok = false; run = false; }
+        }
+      }
     }
-    const double x1 = x - bf_div(f, d);
-    const bool conv = fabs(x - x1) < eps;
-    x = x1;
-    if (conv) { last = true; continue; }
-    if (++iter >= 25) return false;
   }
   const double xe = o.a * (o.ch * cF + o.bhk * sF - o.k);
   const double ye = o.a * (o.ck * sF + o.bhk * cF - o.h);
   pos_equ = ecl_to_equ(xe * o.fv + ye * o.gv);
-  return true;
+  return ok;
 }
 
 constexpr int kEphThreads = 128;
@@ -201,7 +209,7 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
   }
   // ---- per-orbit constants (OrbitalElements::compute preamble + the epoch-independent part of
   //      propagate_twobody) ----
-  int orbit_status = 0;
+  int orbit_status = i < n_orbits ? 0 : -1;  // -1: a thread beyond the batch (walks the epochs, stores nothing)
   double a = 0, h = 0, k = 0, lambda = 0, t_ref = 0, n_mot = 0, lon_peri = 0, ch = 0, ck = 0, bhk = 0;
   V3 fv = V3{0, 0, 0}, gv = V3{0, 0, 0};
   double sx0 = 0, cx0 = 0;  // sincos of the Newton start pi + lon_peri: the same for every epoch of the orbit
@@ -245,100 +253,100 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
     const unsigned te = (unsigned)(n_epochs - e0 < (size_t)kEphTile ? n_epochs - e0 : kEphTile);
     mbar_wait(&bar, parity);
     parity ^= 1u;
-    if (i < n_orbits) {
+    // Every lane of the warp walks the epochs (threads beyond n_orbits carry orbit_status = -1 and store nothing), and
+    // the Newton loop below runs a WARP-UNIFORM number of trips (vote): with per-lane `break`s the lanes that converged
+    // first ran ahead into the ~700-instruction tail on their own, and the tail was issued twice per epoch at 16 of 32
+    // lanes (ncu r2b: 2.01 executions of the tail per warp and epoch).  Same arithmetic per lane, same bits.
 #pragma unroll 1
-      for (unsigned j = 0; j < te; ++j) {
-        const size_t e = e0 + j;
-        double o[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) o[q] = NAN;
-        int st = orbit_status;
-        if (st == 0) st = __ldg(obs_status + e);
-        if (st == 0) {
-          const double t_obs = __ldg(mjd_tt + e);
-          const double dt = t_obs - t_ref;
-          double lam1 = rem_euclid(lambda + n_mot * (dt - 0.0), kTwoPi);
-          if (lam1 < lon_peri) lam1 += kTwoPi;
-          // generalised Kepler equation, roots 0.0.8 Newton (equinoctial_element.rs:326-348)
-          const double eps = kEps * 1e2;
-          double x = kPi + lon_peri, sF = sx0, cF = cx0;
-          int iter = 0;
-          bool last = false, ok = true, have = true;  // the first evaluation point is per orbit (hoisted above)
-          for (;;) {
-            if (!have) sincos_angle(x, &sF, &cF);
-            have = false;
-            if (last) break;
+    for (unsigned j = 0; j < te; ++j) {
+      const size_t e = e0 + j;
+      double o[9];
+      int st = orbit_status;
+      if (st == 0) st = __ldg(obs_status + e);
+      const double t_obs = __ldg(mjd_tt + e);
+      const double dt = t_obs - t_ref;
+      double lam1 = rem_euclid(lambda + n_mot * (dt - 0.0), kTwoPi);
+      if (lam1 < lon_peri) lam1 += kTwoPi;
+      // generalised Kepler equation, roots 0.0.8 Newton (equinoctial_element.rs:326-348)
+      const double eps = kEps * 1e2;
+      double x = kPi + lon_peri, sF = sx0, cF = cx0;
+      int iter = 0;
+      bool run = st == 0, last = false, ok = true, have = true;  // the first evaluation point is per orbit (hoisted above)
+      while (__any_sync(0xffffffffu, run)) {
+        if (run) {
+          if (!have) sincos_angle(x, &sF, &cF);
+          have = false;
+          if (last) {
+            run = false;
+          } else {
             const double f = x - k * sF + h * cF - lam1;
             const double d = 1.0 - k * cF - h * sF;
-            if (fabs(f) < eps) break;
-            if (fabs(d) < eps) {
-              if (iter == 0) { x = x + 1.0; iter = 1; continue; }
-              ok = false;
-              break;
-            }
-            const double x1 = x - bf_div(f, d);
-            const bool conv = fabs(x - x1) < eps;
-            x = x1;
-            if (conv) { last = true; continue; }
-            if (++iter >= 25) { ok = false; break; }
-          }
-          if (!ok) {
-            st = 11;  // RootFindingError
-          } else {
-            const double xe = a * (ch * cF + bhk * sF - k);
-            const double ye = a * (ck * sF + bhk * cF - h);
-            const double vc = bf_div(n_mot * (a * a), bf_sqrt(xe * xe + ye * ye));
-            const double vxe = vc * (bhk * cF - ch * sF);
-            const double vye = vc * (ck * cF - bhk * sF);
-            const V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
-            const V3 av = ecl_to_equ(vxe * fv + vye * gv);
-            const V3 op = V3{tile[j], tile[kEphTile + j], tile[2 * kEphTile + j]};
-            const V3 ov = V3{tile[3 * kEphTile + j], tile[4 * kEphTile + j], tile[5 * kEphTile + j]};
-            const V3 ep = V3{tile[6 * kEphTile + j], tile[7 * kEphTile + j], tile[8 * kEphTile + j]};
-            const double helio = bf_sqrt(dot(ap, ap));
-            const V3 dgeo = ap - ep;
-            const double geo = bf_sqrt(dot(dgeo, dgeo));
-            const V3 raw = ap - op;
-            V3 topo;
-            bool ab_ok = true;
-            if (SECOND) {
-              const EphOrbitC oc{a, h, k, lambda, t_ref, n_mot, lon_peri, ch, ck, bhk, sx0, cx0, fv, gv};
-              V3 r1, r2;
-              ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu), r1);
-              if (ab_ok) {
-                const V3 d1 = r1 - op;
-                ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(d1, d1)), kVlightAu, 1.0 / kVlightAu), r2);
-              }
-              topo = r2 - op;
+            if (fabs(f) < eps) {
+              run = false;
+            } else if (fabs(d) < eps) {
+              if (iter == 0) { x = x + 1.0; iter = 1; }
+              else { ok = false; run = false; }
             } else {
-              const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
-              topo = raw - ltt * av;
-            }
-            if (!ab_ok) st = 11;  // the back-propagation's Kepler solve failed: RootFindingError
-            o[0] = rem_euclid(atan2_finite(topo.y, topo.x), kTwoPi);
-            o[1] = atan2_finite(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
-            o[2] = geo;
-            o[3] = helio;
-            const double rho = bf_sqrt(dot(topo, topo));
-            const double r_obs = bf_sqrt(dot(op, op));
-            o[4] = acos(clampd(bf_div(dot(ap, topo), helio * rho), -1.0, 1.0));
-            o[5] = acos(clampd(bf_div(-dot(op, topo), r_obs * rho), -1.0, 1.0));
-            const V3 vt = av - ov;
-            o[6] = bf_div(dot(topo, vt), rho);
-            const double dxy2 = topo.x * topo.x + topo.y * topo.y;
-            const double dxy = bf_sqrt(dxy2);
-            if (dxy < kEps * rho) {
-              o[7] = 0.0; o[8] = 0.0;
-            } else {
-              o[7] = bf_div(-topo.y * vt.x + topo.x * vt.y, dxy2);
-              o[8] = bf_div(-topo.z * topo.x * vt.x - topo.z * topo.y * vt.y + dxy2 * vt.z, rho * rho * dxy);
+              const double x1 = x - bf_div(f, d);
+              const bool conv = fabs(x - x1) < eps;
+              x = x1;
+              if (conv) last = true;
+              else if (++iter >= 25) { ok = false; run = false; }
             }
           }
         }
-        if (st != 0) {
+      }
+      if (st == 0 && !ok) st = 11;  // RootFindingError
+      const double xe = a * (ch * cF + bhk * sF - k);
+      const double ye = a * (ck * sF + bhk * cF - h);
+      const double vc = bf_div(n_mot * (a * a), bf_sqrt(xe * xe + ye * ye));
+      const double vxe = vc * (bhk * cF - ch * sF);
+      const double vye = vc * (ck * cF - bhk * sF);
+      const V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
+      const V3 av = ecl_to_equ(vxe * fv + vye * gv);
+      const V3 op = V3{tile[j], tile[kEphTile + j], tile[2 * kEphTile + j]};
+      const V3 ov = V3{tile[3 * kEphTile + j], tile[4 * kEphTile + j], tile[5 * kEphTile + j]};
+      const V3 ep = V3{tile[6 * kEphTile + j], tile[7 * kEphTile + j], tile[8 * kEphTile + j]};
+      const double helio = bf_sqrt(dot(ap, ap));
+      const V3 dgeo = ap - ep;
+      const double geo = bf_sqrt(dot(dgeo, dgeo));
+      const V3 raw = ap - op;
+      V3 topo;
+      if (SECOND) {
+        const EphOrbitC oc{a, h, k, lambda, t_ref, n_mot, lon_peri, ch, ck, bhk, sx0, cx0, fv, gv};
+        V3 r1, r2;
+        bool ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu), st == 0, r1);
+        const V3 d1 = r1 - op;
+        ab_ok = eph_retarded_position(oc, t_obs - div_by_const(bf_sqrt(dot(d1, d1)), kVlightAu, 1.0 / kVlightAu), st == 0 && ab_ok, r2) && ab_ok;
+        topo = r2 - op;
+        if (st == 0 && !ab_ok) st = 11;  // the back-propagation's Kepler solve failed: RootFindingError
+      } else {
+        const double ltt = div_by_const(bf_sqrt(dot(raw, raw)), kVlightAu, 1.0 / kVlightAu);  // RN(x / c), Markstein
+        topo = raw - ltt * av;
+      }
+      o[0] = rem_euclid(atan2_finite(topo.y, topo.x), kTwoPi);
+      o[1] = atan2_finite(topo.z, bf_sqrt(topo.x * topo.x + topo.y * topo.y));
+      o[2] = geo;
+      o[3] = helio;
+      const double rho = bf_sqrt(dot(topo, topo));
+      const double r_obs = bf_sqrt(dot(op, op));
+      o[4] = acos(clampd(bf_div(dot(ap, topo), helio * rho), -1.0, 1.0));
+      o[5] = acos(clampd(bf_div(-dot(op, topo), r_obs * rho), -1.0, 1.0));
+      const V3 vt = av - ov;
+      o[6] = bf_div(dot(topo, vt), rho);
+      const double dxy2 = topo.x * topo.x + topo.y * topo.y;
+      const double dxy = bf_sqrt(dxy2);
+      if (dxy < kEps * rho) {
+        o[7] = 0.0; o[8] = 0.0;
+      } else {
+        o[7] = bf_div(-topo.y * vt.x + topo.x * vt.y, dxy2);
+        o[8] = bf_div(-topo.z * topo.x * vt.x - topo.z * topo.y * vt.y + dxy2 * vt.z, rho * rho * dxy);
+      }
+      if (st != 0) {
 #pragma unroll
-          for (int q = 0; q < 9; ++q) o[q] = NAN;
-        }
+        for (int q = 0; q < 9; ++q) o[q] = NAN;
+      }
+      if (i < n_orbits) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) out[((size_t)q * n_epochs + e) * n_orbits + i] = o[q];
         status[e * n_orbits + i] = st;

@@ -955,8 +955,7 @@ extern "C" int outfit_b200_propagate_universal_device(OutfitCtx *ctx, size_t n, 
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   if (n == 0) return OUTFIT_OK;
-  const int tpb = 128;
-  propagate_universal_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+  propagate_universal_kernel<<<(unsigned)((n + kPropTile - 1) / kPropTile), kPropThreads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
       n, rv, t0, t1, psi_guess, *solver, out, status);
   CK(cudaGetLastError());
   return OUTFIT_OK;

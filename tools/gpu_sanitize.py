@@ -17,4 +17,12 @@ o, st = ctx.propagate_universal(rv, t0, t1, SolverType(kind=2))
 kind, epoch, elem = synth.make_ephemeris_orbits(700, mixed_kinds=True)
 tt, ut1, bf = synth.make_ephemeris_epochs(133)
 eo, es = ctx.ephemeris_twobody(kind, epoch, elem, tt, ut1, bf)
+from outfit_b200 import DifferentialCorrectionConfig, EphemerisConfig, OutfitGroup
+ctx.set_ephemeris_config(EphemerisConfig(aberration=2))
+eo2, es2 = ctx.ephemeris_twobody(kind, epoch, elem, tt, ut1, bf)
+ctx.set_ephemeris_config(EphemerisConfig())
+lres, lfit = ctx.fit_lsq(batch, p, DifferentialCorrectionConfig.default(), initial_orbits=r1)
+g = OutfitGroup([0, 0]); g.load_ephemeris(table)
+assert g.fit_full_iod(batch, p).tobytes() == r1.tobytes()
+one = ctx.fit_iod(batch, p, 7)
 print("ok", (r1["status"] == 0).mean(), (r2["status"] == 0).mean(), (r3["status"] == 0).mean(), (st == 0).mean(), (es == 0).mean())
