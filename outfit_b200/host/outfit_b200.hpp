@@ -170,6 +170,17 @@ class Context {
   std::vector<FitOrbitResult> fit_full_iod(const OutfitObsBatch &batch, const OutfitIodParams &params) {
     std::vector<OutfitIodResult> raw(batch.n_traj);
     check(outfit_b200_fit_full_iod(h_, &params, &batch, raw.data()));
+    return from_raw(raw);
+  }
+  // FitIOD::fit_iod (obs_dataset_api.rs:118-143): one trajectory of the batch
+  FitOrbitResult fit_iod(const OutfitObsBatch &batch, const OutfitIodParams &params, uint64_t traj_index) {
+    std::vector<OutfitIodResult> raw(1);
+    check(outfit_b200_fit_iod(h_, &params, &batch, traj_index, raw.data()));
+    return from_raw(raw)[0];
+  }
+  // EphemerisConfig (ephemeris/mod.rs:124-142): aberration OUTFIT_ABERRATION_FIRST | _SECOND, two-body propagator
+  void set_ephemeris_config(const OutfitEphemerisConfig &c) { check(outfit_b200_set_ephemeris_config(h_, &c)); }
+  static std::vector<FitOrbitResult> from_raw(const std::vector<OutfitIodResult> &raw) {
     std::vector<FitOrbitResult> out(raw.size());
     for (size_t t = 0; t < raw.size(); ++t) {
       const OutfitIodResult &r = raw[t];
@@ -250,6 +261,50 @@ class Context {
     }
   }
   OutfitCtx *h_ = nullptr;
+};
+
+// Every GPU of the box behind one call: the host side of FitIOD::fit_full_iod_parallel (obs_dataset_api.rs:175-207).
+// The library cuts the batch into contiguous trajectory ranges of near-equal estimated work, runs one host thread and
+// one context per GPU and writes every record at its global trajectory index; results do not depend on the GPU count.
+class Group {
+ public:
+  // n_gpus <= 0: all visible devices; device_ids may repeat an id (several contexts on one GPU)
+  explicit Group(int n_gpus = 0, const int *device_ids = nullptr) {
+    const int rc = outfit_b200_init_multi(n_gpus, device_ids, &g_);
+    if (rc != OUTFIT_OK) throw Error(rc, outfit_b200_strerror(rc));
+  }
+  ~Group() { outfit_b200_group_destroy(g_); }
+  Group(const Group &) = delete;
+  Group &operator=(const Group &) = delete;
+  int size() const { return outfit_b200_group_size(g_); }
+  void load_ephemeris(const double *cheb, size_t n_blocks, size_t block_stride, double jd_start, double block_days,
+                      const uint32_t ipt[3][3], double emrat) {
+    check(outfit_b200_group_load_ephemeris(g_, cheb, n_blocks, block_stride, jd_start, block_days, ipt, emrat));
+  }
+  std::vector<FitOrbitResult> fit_full_iod(const OutfitObsBatch &batch, const OutfitIodParams &params) {
+    std::vector<OutfitIodResult> raw(batch.n_traj);
+    check(outfit_b200_group_fit_full_iod(g_, &params, &batch, raw.data()));
+    return Context::from_raw(raw);
+  }
+  void propagate_universal(size_t n, const double *rv, const double *t0, const double *t1, const OutfitSolverType &solver,
+                           double *out, int32_t *status, const double *psi_guess = nullptr) {
+    check(outfit_b200_group_propagate_universal(g_, n, rv, t0, t1, psi_guess, &solver, out, status));
+  }
+  // the cut of the last call and every shard's wall time (load imbalance)
+  void last_shards(std::vector<uint64_t> &cuts, std::vector<float> &ms) {
+    cuts.assign((size_t)size() + 1, 0);
+    ms.assign((size_t)size(), 0.f);
+    check(outfit_b200_group_last_shards(g_, cuts.data(), ms.data()));
+  }
+
+ private:
+  void check(int rc) {
+    if (rc != OUTFIT_OK) {
+      const char *m = outfit_b200_group_last_error(g_);
+      throw Error(rc, (m && *m) ? m : outfit_b200_strerror(rc));
+    }
+  }
+  OutfitGroup *g_ = nullptr;
 };
 
 }  // namespace outfit

@@ -2,9 +2,10 @@
 tests/data/*.obs, read there by the un-vendored `photom` crate) -> the SoA batch of the C-ABI.
 
 This is the "wire format" row of SURVEY 8f: it lets BASELINE configs[0] (one trajectory from an MPC
-80-column file) run without Rust.  What photom additionally does and this reader does NOT: the
-FCCT14 astrometric error model (a constant sigma per observatory is applied instead) and the batch
-RMS correction; both are documented as unpinned in DESIGN.md.
+80-column file) run without Rust.  What photom additionally does -- the FCCT14 astrometric error
+model and the batch RMS correction -- lives in outfit_b200/error_model.py (restated from the published definitions,
+parity with photom unpinned); `to_batch` honours the per-record sigmas it produces and otherwise applies a constant
+sigma.
 
 Columns (1-based, MPC "Format for optical astrometric observations"): 1-5 packed number, 6-12
 packed provisional designation, 13 discovery asterisk, 14 note 1, 15 note 2, 16-32 date of
@@ -77,6 +78,7 @@ def parse_line(line):
         "ra": (ra_h + ra_m / 60.0 + ra_s / 3600.0) * 15.0 * math.pi / 180.0,
         "dec": sign * (de_d + de_m / 60.0 + de_s / 3600.0) * math.pi / 180.0,
         "mag": float(mag) if mag else float("nan"), "band": line[70].strip(), "obscode": line[77:80],
+        "note2": line[14], "catalog": line[71].strip(),  # observation type and reduction catalog: the error model's keys
     }
 
 

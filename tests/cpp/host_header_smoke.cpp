@@ -16,6 +16,18 @@ int main() {
                      lc.chi2_rejection_threshold == 25.0 && sizeof(OutfitLsqResult) == 8 * 90 && sizeof(OutfitObsFit) == 32;
   bool nodev = false;
   try { Context c(0); } catch (const Error &e) { nodev = e.code == OUTFIT_E_NO_DEVICE; }
-  std::printf("params=%u threw=%d sorted=%d nodev_or_ok=%d\n", p.max_triplets, (int)threw, (int)sorted, (int)nodev);
-  return (threw && sorted && lsq_default) ? 0 : 1;
+  // the multi-GPU group: without a device it fails loudly like a single context; the cut is pure host arithmetic
+  bool group_nodev = false;
+  try { Group g; group_nodev = g.size() > 0; } catch (const Error &e) { group_nodev = e.code == OUTFIT_E_NO_DEVICE; }
+  const uint64_t off[6] = {0, 12, 24, 36, 48, 60};
+  uint64_t cuts[3] = {9, 9, 9};
+  const bool cut_ok = outfit_b200_shard_ranges(5, off, 30, 10, 2, cuts) == OUTFIT_OK && cuts[0] == 0 && cuts[2] == 5 &&
+                      (cuts[1] == 2 || cuts[1] == 3);
+  OutfitEphemerisConfig ec;
+  outfit_b200_ephemeris_config_default(&ec);
+  const bool eph_default = ec.propagator == OUTFIT_PROPAGATOR_TWOBODY && ec.aberration == OUTFIT_ABERRATION_FIRST &&
+                           sizeof(OutfitIodResult) == 128;
+  std::printf("params=%u threw=%d sorted=%d nodev_or_ok=%d group=%d cut=%d\n", p.max_triplets, (int)threw, (int)sorted, (int)nodev,
+              (int)group_nodev, (int)cut_ok);
+  return (threw && sorted && lsq_default && group_nodev && cut_ok && eph_default) ? 0 : 1;
 }
