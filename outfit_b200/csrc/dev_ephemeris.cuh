@@ -186,7 +186,7 @@ constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 
 // out [9][n_epochs][n_orbits] = ra, dec, geocentric_dist, heliocentric_dist, phase_angle,
 // solar_elongation, radial_velocity, d_ra_dt, d_dec_dt; status [n_epochs][n_orbits].
 #ifndef OUTFIT_EPH_BPS
-#define OUTFIT_EPH_BPS 5  // 96 registers, 20 warps per SM: 10.0 ms per 1e8 entries against 10.6 at 4 (r02b)
+#define OUTFIT_EPH_BPS 6  // 80 registers, 24 warps per SM: 5.67 ms per 1e8 entries against 5.86 at 5 blocks and 6.16 at 4 (r2d)
 #endif
 // SECOND = AberrationOrder::Second (aberration.rs:195-209): the line of sight comes from two back-propagations by the
 // light time instead of the linear shift; a separate instantiation, the first-order kernel is untouched by it.

@@ -301,7 +301,7 @@ __device__ __forceinline__ void state_to_orbit(const IodScratch &S, unsigned lon
 
 // ---- P3: elements -> equinoctial -> arc RMS sum --------------------------------------------------
 #ifndef OUTFIT_SCORE_BPS
-#define OUTFIT_SCORE_BPS 6  // 80 registers: 19.4 ms against 20.2 at 5 blocks per SM (r02d)
+#define OUTFIT_SCORE_BPS 7  // 72 registers: 16.75 ms per 100 k trajectories against 17.04 at 6 blocks and 16.94 at 8 (r2e)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kCandThreads, OUTFIT_SCORE_BPS)
