@@ -76,15 +76,19 @@ KEPLER_SCENARIOS = {
     "gap_400_days_multi_revolution": "test_gap_400_days_multi_revolution"}
 
 
+# the sources the IOD kernels are compiled from (k_iod.cuh and everything it includes, the observer kernels, the
+# compiler flags): the key an ncu capture of those kernels is bound to
+IOD_KERNEL_SOURCES = ("Makefile", "k_iod.cuh", "dev_iod.cuh", "dev_correct.cuh", "dev_gauss.cuh", "dev_kepler.cuh",
+                      "dev_elements.cuh", "dev_geometry.cuh", "dev_rng.cuh", "nutation_rows.inc")
+
+
 def kernel_source_sha():
-    """sha256 over the KERNEL sources of the tree (every .cuh / .inc of outfit_b200/csrc + the Makefile with its
-    compiler flags; outfit_b200.cu holds host code only): the key an ncu capture is bound to (tools/ncu_latest.py)."""
+    """sha256 over the sources of the full-IOD kernels in the tree (tools/ncu_latest.py records it with a capture)."""
     d = os.path.join(ROOT, "outfit_b200", "csrc")
     h = hashlib.sha256()
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cuh", ".inc")) or name == "Makefile":
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+    for name in IOD_KERNEL_SOURCES:
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()
 
 
