@@ -40,7 +40,7 @@ def main():
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         name = d.get("Kernel Name", "")
-        short = name.split("<")[0].split("(")[0].split("::")[-1]
+        short = name.split("<")[0].split("(")[0].split("::")[-1].replace("void ", "").strip()
         k = {}
         for key, metric in M.items():
             if metric in d and d[metric] not in ("", "n/a"):
