@@ -322,6 +322,70 @@ def ephemeris_twobody_batch(table, kind, epoch, elem, mjd_tt, mjd_ut1, body_fixe
     return out, status
 
 
+class Perturber(C.Structure):
+    _fields_ = [("gm", C.c_double), ("pos", C.c_double * 3)]
+
+
+def planet_gm(body):
+    """planet_gm.rs: 0 Sun, 1 Mercury, 2 Venus, 3 Earth-Moon, 4 Mars, 5 Jupiter, 6 Saturn, 7 Uranus, 8 Neptune, 9 Pluto, 10 Moon."""
+    L = lib()
+    L.oo_planet_gm.restype = C.c_double
+    L.oo_planet_gm.argtypes = [C.c_int]
+    return L.oo_planet_gm(int(body))
+
+
+def _perturbers(gm, pos):
+    arr = (Perturber * len(gm))()
+    for i, (g, p) in enumerate(zip(gm, pos)):
+        arr[i].gm = float(g)
+        arr[i].pos[0], arr[i].pos[1], arr[i].pos[2] = (float(x) for x in p)
+    return arr
+
+
+def nbody_rhs(y42, gm, pos):
+    L = lib()
+    L.oo_nbody_rhs.argtypes = [C.c_void_p, C.POINTER(Perturber), C.c_size_t, C.c_void_p]
+    L.oo_nbody_rhs.restype = None
+    y = np.ascontiguousarray(y42, dtype=np.float64)
+    dy = np.empty(42)
+    L.oo_nbody_rhs(y.ctypes.data, _perturbers(gm, pos), len(gm), dy.ctypes.data)
+    return dy
+
+
+def propagate_nbody(kind, epoch, elem, t1, gm, pert_pos, atol=1e-12, rtol=1e-12):
+    """EquinoctialElements::propagate_nbody for n orbits: kind (n,), epoch (n,), elem (6, n), t1 (n,), gm (P,),
+    pert_pos (P, 3, n) heliocentric ecliptic J2000 at each orbit's epoch -> state (6, n) ecliptic, stm (36, n)
+    column-major, status (n,), steps (n,)."""
+    L = lib()
+    L.oo_propagate_nbody.argtypes = [C.POINTER(Elements), C.c_double, C.POINTER(Perturber), C.c_size_t, C.c_double,
+                                     C.c_double, D3, D3, C.c_double * 36, C.POINTER(C.c_uint32)]
+    n = len(kind)
+    state, stm = np.full((6, n), np.nan), np.full((36, n), np.nan)
+    status, steps = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint32)
+    for i in range(n):
+        el = Elements()
+        el.kind, el.epoch = int(kind[i]), float(epoch[i])
+        for q in range(6):
+            el.e[q] = float(elem[q, i])
+        eq = Elements()
+        rc = L.oo_to_equinoctial(C.byref(el), C.byref(eq)) if el.kind != 1 else 0
+        if el.kind == 1:
+            eq = el
+        if rc != 0:
+            status[i] = rc
+            continue
+        if not (np.hypot(eq.e[1], eq.e[2]) < 1.0):  # the two-body start of propagate_nbody needs e < 1
+            status[i] = 10
+            continue
+        p, v, m, ns = D3(), D3(), (C.c_double * 36)(), C.c_uint32()
+        rc = L.oo_propagate_nbody(C.byref(eq), float(t1[i]), _perturbers(gm, pert_pos[:, :, i]), len(gm), atol, rtol, p, v, m,
+                                  C.byref(ns))
+        status[i], steps[i] = rc, ns.value
+        if rc == 0:
+            state[0:3, i], state[3:6, i], stm[:, i] = list(p), list(v), list(m)
+    return state, stm, status, steps
+
+
 def draw_noise(seeds, per_traj):
     """Deviates of SmallRng::seed_from_u64(seed) + StandardNormal for every seed: (len(seeds), per_traj)."""
     out = np.empty((len(seeds), per_traj), dtype=np.float64)

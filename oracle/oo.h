@@ -297,6 +297,16 @@ void oo_ziggurat_tables(double x[257], double f[257]);
 double oo_standard_normal(uint64_t s[4]);                       /* rand_distr::StandardNormal */
 void oo_draw_noise(uint64_t seed, size_t n, double *out);       /* n deviates in draw order */
 
+/* ---- N-body propagator (propagator/nbody.rs; oo_nbody.c) --------------------------------------- */
+enum { OO_ERR_NBODY = 21 };     /* NBodyPropagationFailed (nbody.rs:516-522) */
+typedef struct { double gm; double pos[3]; } oo_perturber; /* PerturberSnapshot (nbody.rs:17-32): heliocentric, ecliptic J2000, AU */
+void oo_nbody_rhs(const double *y42, const oo_perturber *pert, size_t n_pert, double *dy42);  /* nbody.rs:339-356 */
+int oo_dop853_nbody(double *y42, double span, const oo_perturber *pert, size_t n_pert, double atol, double rtol,
+                    uint32_t max_steps, uint32_t *n_steps, uint32_t *n_rejected);
+int oo_propagate_nbody(const oo_elements *equi, double t1_mjd_tt, const oo_perturber *pert, size_t n_pert, double atol,
+                       double rtol, double pos[3], double vel[3], double stm[36], uint32_t *n_steps);
+double oo_planet_gm(int body);  /* planet_gm.rs */
+
 /* ---- two-body `Combined` ephemeris (ephemeris/mod.rs:189-292; oo_ephemeris.c) -------------- */
 /* apparent_position.rs:264-296 : observer position / velocity (= Earth velocity) / Earth position,
    equatorial mean J2000, AU and AU/day */

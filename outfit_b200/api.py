@@ -22,7 +22,7 @@ STATUS_NAMES = {
     7: "BrentDekkerKeplerConvergence", 8: "DegenerateState", 9: "InvalidConversion", 10: "InvalidOrbit",
     11: "RootFindingError", 12: "NonFiniteScore", 13: "NoFeasibleTriplets", 14: "NoViableOrbit",
     15: "ObservationNotFound", 17: "EphemerisOutOfRange", 18: "DifferentialCorrectionFailed", 19: "BizarreOrbit",
-    20: "DifferentialCorrectionDiverged",
+    20: "DifferentialCorrectionDiverged", 21: "NBodyPropagationFailed",
 }
 
 
@@ -121,6 +121,19 @@ class EphemerisConfig(C.Structure):
         super().__init__(propagator, aberration)
 
 
+class NBodyConfig(C.Structure):
+    """NBodyConfig (propagator/mod.rs:107-150): tolerances of the DOP853 integration and the number of perturbers."""
+    _fields_ = [("abs_tol", C.c_double), ("rel_tol", C.c_double), ("n_perturbers", C.c_uint32), ("max_steps", C.c_uint32)]
+
+    def __init__(self, n_perturbers=1, abs_tol=1e-12, rel_tol=1e-12, max_steps=0):
+        super().__init__(abs_tol, rel_tol, n_perturbers, max_steps)
+
+
+def planet_gm(body):
+    """GM in AU^3/day^2 (propagator/planet_gm.rs): 0 Sun, 1 Mercury, ... 9 Pluto, 10 Moon."""
+    return float(load_library().outfit_b200_planet_gm(int(body)))
+
+
 class DifferentialCorrectionConfig(C.Structure):
     """DifferentialCorrectionConfig (diff_cor.rs:100-192) + OutlierRejectionConfig + EquinoctialLimits."""
     _fields_ = [("max_newton_iterations", C.c_uint64), ("max_outlier_rejection_passes", C.c_uint64),
@@ -171,6 +184,7 @@ ABI_SYMBOLS = [
     "outfit_b200_group_ephemeris_request", "outfit_b200_group_last_shards", "outfit_b200_shard_ranges",
     "outfit_b200_host_alloc", "outfit_b200_host_free",
     "outfit_b200_ephemeris_config_default", "outfit_b200_set_ephemeris_config", "outfit_b200_group_set_ephemeris_config",
+    "outfit_b200_nbody_config_default", "outfit_b200_planet_gm", "outfit_b200_propagate_nbody", "outfit_b200_propagate_nbody_device",
 ]
 
 
@@ -249,6 +263,13 @@ def load_library():
     L.outfit_b200_ephemeris_config_default.restype = None
     L.outfit_b200_set_ephemeris_config.argtypes = [vp, C.POINTER(EphemerisConfig)]
     L.outfit_b200_group_set_ephemeris_config.argtypes = [vp, C.POINTER(EphemerisConfig)]
+    L.outfit_b200_nbody_config_default.argtypes = [C.POINTER(NBodyConfig)]
+    L.outfit_b200_nbody_config_default.restype = None
+    L.outfit_b200_planet_gm.argtypes = [C.c_int]
+    L.outfit_b200_planet_gm.restype = C.c_double
+    L.outfit_b200_propagate_nbody.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(NBodyConfig), vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_propagate_nbody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(NBodyConfig), vp, vp, vp, vp, vp,
+                                                     vp, vp]
     _LIB = L
     return L
 
@@ -461,6 +482,25 @@ class OutfitB200:
         self._check(self._L.outfit_b200_ephemeris_request(self._h, n, _p(kind), _p(epoch), _p(elem), len(observers), _p(bf),
                                                           _p(off), _p(tt), _p(ut), out.ctypes.data, status.ctypes.data))
         return out, status
+
+    def propagate_nbody(self, kind, epoch, elem, t1, gm, perturber_pos, config=None, with_stm=True):
+        """EquinoctialElements::propagate_nbody in bulk (HOST arrays): kind (n,) int32, epoch (n,), elem (6, n), t1 (n,),
+        gm (P,), perturber_pos (P, 3, n) heliocentric ecliptic J2000 at each orbit's epoch
+        -> state (6, n) ecliptic, stm (36, n) column-major or None, status (n,), steps (n,)."""
+        n, P = int(kind.shape[0]), int(len(gm))
+        cfg = config or NBodyConfig(n_perturbers=P)
+        cfg.n_perturbers = P
+        gm = np.ascontiguousarray(gm, dtype=np.float64)
+        pp = np.ascontiguousarray(perturber_pos, dtype=np.float64)
+        assert pp.shape == (P, 3, n)
+        out = np.empty((6, n))
+        stm = np.empty((36, n)) if with_stm else None
+        status = np.empty(n, dtype=np.int32)
+        steps = np.empty(n, dtype=np.uint32)
+        self._check(self._L.outfit_b200_propagate_nbody(self._h, n, _p(kind), _p(epoch), _p(elem), _p(t1), C.byref(cfg), _p(gm),
+                                                        _p(pp), out.ctypes.data, stm.ctypes.data if with_stm else None,
+                                                        status.ctypes.data, steps.ctypes.data))
+        return out, stm, status, steps
 
     def set_ephemeris_config(self, config):
         """EphemerisConfig of the ephemeris entries of this context (aberration order; two-body propagator only)."""

@@ -32,6 +32,7 @@ using namespace ofb;
 
 #include "k_iod.cuh"
 #include "k_bulk.cuh"
+#include "k_nbody.cuh"
 
 // =================================================================================================
 // context + C-ABI
@@ -1449,6 +1450,84 @@ extern "C" void *outfit_b200_host_alloc(size_t bytes) {
 }
 extern "C" void outfit_b200_host_free(void *p) {
   if (p) cudaFreeHost(p);
+}
+
+// ---- N-body propagation (propagator/nbody.rs, equinoctial_element.rs:908-968) ------------------------------------
+extern "C" void outfit_b200_nbody_config_default(OutfitNBodyConfig *c) {  // NBodyConfig::default(): [Sun], 1e-12, 1e-12
+  if (!c) return;
+  c->abs_tol = 1e-12; c->rel_tol = 1e-12; c->n_perturbers = 1; c->max_steps = 0;
+}
+extern "C" double outfit_b200_planet_gm(int body) {  // planet_gm.rs:10-60 (DE440 values, km^3/s^2 -> AU^3/day^2)
+  static const double km3_s2[11] = {1.32712440041e11, 2.203178e4, 3.2485857e5, 4.03503235e5, 4.28283736e4, 1.267127648e8,
+                                    3.79406252e7, 5.7945564e6, 6.8365271e6, 9.755e2, 4.902800066e3};
+  const double au_km = 1.495978707e8;
+  const double conv = (86400.0 * 86400.0) / (au_km * au_km * au_km);
+  return (body >= 0 && body < 11) ? km3_s2[body] * conv : NAN;
+}
+static int check_nbody_cfg(OutfitCtx *ctx, const OutfitNBodyConfig *cfg) {
+  if (cfg->n_perturbers == 0 || cfg->n_perturbers > (unsigned)kNbMaxPert)
+    return fail(ctx, OUTFIT_E_UNSUPPORTED, "n_perturbers must be in [1, 12]");
+  if (!(cfg->abs_tol > 0.0) || !(cfg->rel_tol > 0.0)) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "abs_tol and rel_tol must be positive");
+  return OUTFIT_OK;
+}
+extern "C" int outfit_b200_propagate_nbody_device(OutfitCtx *ctx, size_t n, const int32_t *kind, const double *epoch,
+                                                  const double *elem, const double *t1, const OutfitNBodyConfig *cfg,
+                                                  const double *gm, const double *pert_pos, double *out, double *stm,
+                                                  int32_t *status, uint32_t *steps, void *cuda_stream) {
+  if (!ctx || !cfg || (n && (!kind || !epoch || !elem || !t1 || !gm || !pert_pos || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int rc = check_nbody_cfg(ctx, cfg);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return OUTFIT_OK;
+  CK(cudaFuncSetAttribute(propagate_nbody_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNbSmemBytes));
+  const NbCfgDev c{cfg->abs_tol, cfg->rel_tol, cfg->n_perturbers, cfg->max_steps ? cfg->max_steps : 100000u};
+  const size_t threads = n * 8;
+  propagate_nbody_kernel<<<(unsigned)((threads + kNbThreads - 1) / kNbThreads), kNbThreads, kNbSmemBytes, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      n, kind, epoch, elem, t1, c, gm, pert_pos, out, stm, status, steps);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+extern "C" int outfit_b200_propagate_nbody(OutfitCtx *ctx, size_t n, const int32_t *kind, const double *epoch, const double *elem,
+                                           const double *t1, const OutfitNBodyConfig *cfg, const double *gm, const double *pert_pos,
+                                           double *out, double *stm, int32_t *status, uint32_t *steps) {
+  if (!ctx || !cfg || (n && (!kind || !epoch || !elem || !t1 || !gm || !pert_pos || !out || !status))) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  int rc = check_nbody_cfg(ctx, cfg);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return OUTFIT_OK;
+  rc = ensure_host_streams(ctx);
+  if (rc) return rc;
+  const size_t P = cfg->n_perturbers;
+  const size_t bytes = n * 4 + n * 8 * (1 + 6 + 1 + 3 * P + 6 + 36) + P * 8 + n * 8 + 16 * 256;
+  rc = ensure_arena(ctx, bytes);
+  if (rc) return rc;
+  cudaStream_t stream = ctx->compute_stream;
+  ArenaPut A{ctx->arena, 0, stream};
+  const int32_t *d_kind = (const int32_t *)A.put(kind, n * 4);
+  const double *d_epoch = (const double *)A.put(epoch, n * 8);
+  const double *d_elem = (const double *)A.put(elem, 6 * n * 8);
+  const double *d_t1 = (const double *)A.put(t1, n * 8);
+  const double *d_gm = (const double *)A.put(gm, P * 8);
+  const double *d_pp = (const double *)A.put(pert_pos, 3 * P * n * 8);
+  double *d_out = (double *)A.raw(6 * n * 8);
+  double *d_stm = stm ? (double *)A.raw(36 * n * 8) : nullptr;
+  int32_t *d_st = (int32_t *)A.raw(n * 4);
+  uint32_t *d_steps = steps ? (uint32_t *)A.raw(n * 4) : nullptr;
+  if (A.err != cudaSuccess) { cudaStreamSynchronize(stream); return fail(ctx, OUTFIT_E_CUDA, "propagate_nbody: H2D", A.err); }
+  rc = outfit_b200_propagate_nbody_device(ctx, n, d_kind, d_epoch, d_elem, d_t1, cfg, d_gm, d_pp, d_out, d_stm, d_st, d_steps, stream);
+  if (rc == OUTFIT_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, 6 * n * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && stm) e = cudaMemcpyAsync(stm, d_stm, 36 * n * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && steps) e = cudaMemcpyAsync(steps, d_steps, n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_nbody: copy back / kernel", e);
+  } else {
+    cudaStreamSynchronize(stream);
+  }
+  return rc;
 }
 
 extern "C" int outfit_b200_selftest_arith(OutfitCtx *ctx, unsigned long long n, unsigned long long seed, int exp_range,
