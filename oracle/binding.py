@@ -386,6 +386,35 @@ def propagate_nbody(kind, epoch, elem, t1, gm, pert_pos, atol=1e-12, rtol=1e-12)
     return state, stm, status, steps
 
 
+def ephemeris_nbody_batch(table, kind, epoch, elem, mjd_tt, mjd_ut1, body_fixed, gm, pert_pos, atol=1e-12, rtol=1e-12,
+                          aberration_order=1):
+    """PropagatorKind::NBody flavour of ephemeris_twobody_batch (one observer): out (9, E, n), status (E, n)."""
+    L = lib()
+    L.oo_ephemeris_nbody.argtypes = [C.POINTER(EphemTable), C.POINTER(Elements), C.c_size_t, C.c_void_p, C.c_void_p, D3,
+                                     C.POINTER(Perturber), C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.oo_ephemeris_nbody.restype = None
+    n, E = len(kind), len(mjd_tt)
+    out = np.empty((9, E, n))
+    status = np.empty((E, n), dtype=np.int32)
+    tt = np.ascontiguousarray(mjd_tt, dtype=np.float64)
+    ut = np.ascontiguousarray(mjd_ut1, dtype=np.float64)
+    L.oo_set_aberration_order(int(aberration_order))
+    try:
+        for i in range(n):
+            el = Elements()
+            el.kind, el.epoch = int(kind[i]), float(epoch[i])
+            for q in range(6):
+                el.e[q] = float(elem[q, i])
+            o = np.empty((9, E))
+            st = np.empty(E, dtype=np.int32)
+            L.oo_ephemeris_nbody(C.byref(table), C.byref(el), E, tt.ctypes.data, ut.ctypes.data, d3(body_fixed),
+                                 _perturbers(gm, pert_pos[:, :, i]), len(gm), atol, rtol, o.ctypes.data, st.ctypes.data)
+            out[:, :, i], status[:, i] = o, st
+    finally:
+        L.oo_set_aberration_order(1)
+    return out, status
+
+
 def draw_noise(seeds, per_traj):
     """Deviates of SmallRng::seed_from_u64(seed) + StandardNormal for every seed: (len(seeds), per_traj)."""
     out = np.empty((len(seeds), per_traj), dtype=np.float64)

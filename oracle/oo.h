@@ -319,6 +319,9 @@ int oo_ephemeris_observer_pv(const oo_ephem_table *tab, double mjd_tt, double mj
 int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const double obs_pos[3],
                        const double obs_vel[3], const double earth_pos[3], double out[9]);
 /* OrbitalElements::compute::<Combined>, one orbit x one observer x n_epochs; out [9][n_epochs] */
+void oo_ephemeris_nbody(const oo_ephem_table *tab, const oo_elements *orbit, size_t n_epochs, const double *mjd_tt,
+                        const double *mjd_ut1, const double r_bf[3], const oo_perturber *pert, size_t n_pert, double atol,
+                        double rtol, double *out, int32_t *status);
 void oo_ephemeris_twobody(const oo_ephem_table *tab, const oo_elements *orbit, size_t n_epochs,
                           const double *mjd_tt, const double *mjd_ut1, const double r_bf[3],
                           double *out, int32_t *status);

@@ -59,17 +59,10 @@ static int retropropagate(const oo_elements *equi, double obs_time_mjd, double s
   return OO_OK;
 }
 
-/* One (orbit, epoch) entry given the observer state: out[9] = ra, dec, geocentric_dist,
- * heliocentric_dist, phase_angle, solar_elongation, radial_velocity, d_ra_dt, d_dec_dt. */
-int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const double obs_pos[3],
-                       const double obs_vel[3], const double earth_pos[3], double out[9]) {
-  /* propagator/mod.rs:84-91 : dt from the reference epoch, propagate_twobody(0.0, dt, false) */
-  double dt = obs_time_mjd - equi->epoch;
-  double pe[3], ve[3], ap[3], av[3];
-  int rc = oo_propagate_twobody(equi, 0.0, dt, pe, ve);
-  if (rc != OO_OK) return rc;
-  oo_matvec(ROT_ECL2EQU, pe, ap);
-  oo_matvec(ROT_ECL2EQU, ve, av);
+/* assemble_apparent_position + compute_geometry from the propagated heliocentric state (equatorial J2000) */
+static int entry_from_state(const oo_elements *equi, double obs_time_mjd, const double ap[3], const double av[3],
+                            const double obs_pos[3], const double obs_vel[3], const double earth_pos[3], double out[9]) {
+  int rc;
   /* assemble_apparent_position */
   double helio = oo_norm3(ap);
   double dgeo[3], topo_raw[3];
@@ -77,7 +70,8 @@ int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const doubl
   double geo = oo_norm3(dgeo);
   double topo[3];
   if (g_aberration_order == 2) {
-    /* correct_aberration_second_order (aberration.rs:195-209): two back-propagations by the light time */
+    /* correct_aberration_second_order (aberration.rs:195-209): two back-propagations by the light time; the two-body
+     * propagator is used for both passes whatever the main propagator is */
     double r1[3], d1[3], r2[3];
     rc = retropropagate(equi, obs_time_mjd, oo_norm3(topo_raw), r1);
     if (rc != OO_OK) return rc;
@@ -112,6 +106,60 @@ int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const doubl
     out[8] = (-dz * dx * vt[0] - dz * dy * vt[1] + dxy2 * vt[2]) / (rho * rho * dxy);
   }
   return OO_OK;
+}
+
+/* One (orbit, epoch) entry given the observer state: out[9] = ra, dec, geocentric_dist,
+ * heliocentric_dist, phase_angle, solar_elongation, radial_velocity, d_ra_dt, d_dec_dt. */
+int oo_ephemeris_entry(const oo_elements *equi, double obs_time_mjd, const double obs_pos[3],
+                       const double obs_vel[3], const double earth_pos[3], double out[9]) {
+  /* propagator/mod.rs:84-91 : dt from the reference epoch, propagate_twobody(0.0, dt, false) */
+  double dt = obs_time_mjd - equi->epoch;
+  double pe[3], ve[3], ap[3], av[3];
+  int rc = oo_propagate_twobody(equi, 0.0, dt, pe, ve);
+  if (rc != OO_OK) return rc;
+  oo_matvec(ROT_ECL2EQU, pe, ap);
+  oo_matvec(ROT_ECL2EQU, ve, av);
+  return entry_from_state(equi, obs_time_mjd, ap, av, obs_pos, obs_vel, earth_pos, out);
+}
+
+/* The same entry with PropagatorKind::NBody (propagator/mod.rs:93-101: propagate_nbody, then the same rotation) */
+int oo_ephemeris_entry_nbody(const oo_elements *equi, double obs_time_mjd, const oo_perturber *pert, size_t n_pert,
+                             double atol, double rtol, const double obs_pos[3], const double obs_vel[3],
+                             const double earth_pos[3], double out[9]) {
+  double pe[3], ve[3], ap[3], av[3];
+  int rc = oo_propagate_nbody(equi, obs_time_mjd, pert, n_pert, atol, rtol, pe, ve, NULL, NULL);
+  if (rc != OO_OK) return rc;
+  oo_matvec(ROT_ECL2EQU, pe, ap);
+  oo_matvec(ROT_ECL2EQU, ve, av);
+  return entry_from_state(equi, obs_time_mjd, ap, av, obs_pos, obs_vel, earth_pos, out);
+}
+
+/* OrbitalElements::compute::<Combined> with PropagatorKind::NBody for one orbit, one observer, n_epochs epochs */
+void oo_ephemeris_nbody(const oo_ephem_table *tab, const oo_elements *orbit, size_t n_epochs, const double *mjd_tt,
+                        const double *mjd_ut1, const double r_bf[3], const oo_perturber *pert, size_t n_pert, double atol,
+                        double rtol, double *out, int32_t *status) {
+  oo_elements equi;
+  int rc = oo_to_equinoctial(orbit, &equi);
+  if (rc == OO_OK) {
+    double h = equi.e[1], k = equi.e[2];
+    if (sqrt(h * h + k * k) >= 1.0) rc = OO_ERR_INVALID_CONVERSION;
+  } else {
+    rc = OO_ERR_INVALID_CONVERSION;
+  }
+  for (size_t e = 0; e < n_epochs; e++) {
+    double o[9];
+    for (int q = 0; q < 9; q++) o[q] = NAN;
+    int st = rc;
+    if (st == OO_OK) {
+      double op[3], ov[3], ep[3];
+      st = oo_ephemeris_observer_pv(tab, mjd_tt[e], mjd_ut1[e], r_bf, op, ov, ep);
+      if (st == OO_OK) st = oo_ephemeris_entry_nbody(&equi, mjd_tt[e], pert, n_pert, atol, rtol, op, ov, ep, o);
+      if (st != OO_OK)
+        for (int q = 0; q < 9; q++) o[q] = NAN;
+    }
+    for (int q = 0; q < 9; q++) out[(size_t)q * n_epochs + e] = o[q];
+    status[e] = st;
+  }
 }
 
 /* OrbitalElements::compute::<Combined> for one orbit, one observer, n_epochs epochs.

@@ -185,6 +185,7 @@ ABI_SYMBOLS = [
     "outfit_b200_host_alloc", "outfit_b200_host_free",
     "outfit_b200_ephemeris_config_default", "outfit_b200_set_ephemeris_config", "outfit_b200_group_set_ephemeris_config",
     "outfit_b200_nbody_config_default", "outfit_b200_planet_gm", "outfit_b200_propagate_nbody", "outfit_b200_propagate_nbody_device",
+    "outfit_b200_ephemeris_nbody", "outfit_b200_ephemeris_nbody_device",
 ]
 
 
@@ -268,6 +269,10 @@ def load_library():
     L.outfit_b200_planet_gm.argtypes = [C.c_int]
     L.outfit_b200_planet_gm.restype = C.c_double
     L.outfit_b200_propagate_nbody.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(NBodyConfig), vp, vp, vp, vp, vp, vp]
+    L.outfit_b200_ephemeris_nbody.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(NBodyConfig), vp, vp,
+                                              vp, vp]
+    L.outfit_b200_ephemeris_nbody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, C.POINTER(NBodyConfig), vp,
+                                                     vp, vp, vp, vp]
     L.outfit_b200_propagate_nbody_device.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(NBodyConfig), vp, vp, vp, vp, vp,
                                                      vp, vp]
     _LIB = L
@@ -501,6 +506,24 @@ class OutfitB200:
                                                         _p(pp), out.ctypes.data, stm.ctypes.data if with_stm else None,
                                                         status.ctypes.data, steps.ctypes.data))
         return out, stm, status, steps
+
+    def ephemeris_nbody(self, kind, epoch, elem, observers, gm, perturber_pos, config=None):
+        """OrbitalElements::compute::<Combined> with PropagatorKind::NBody (HOST arrays): observers as in ephemeris_request,
+        gm / perturber_pos as in propagate_nbody -> out (9, E_total, n), status (E_total, n)."""
+        n, P = int(kind.shape[0]), int(len(gm))
+        cfg = config or NBodyConfig(n_perturbers=P)
+        cfg.n_perturbers = P
+        bf, off, tt, ut = _flatten_request(observers)
+        E = int(off[-1])
+        gm = np.ascontiguousarray(gm, dtype=np.float64)
+        pp = np.ascontiguousarray(perturber_pos, dtype=np.float64)
+        assert pp.shape == (P, 3, n)
+        out = np.empty((9, E, n), dtype=np.float64)
+        status = np.empty((E, n), dtype=np.int32)
+        self._check(self._L.outfit_b200_ephemeris_nbody(self._h, n, _p(kind), _p(epoch), _p(elem), len(observers), _p(bf), _p(off),
+                                                        _p(tt), _p(ut), C.byref(cfg), _p(gm), _p(pp), out.ctypes.data,
+                                                        status.ctypes.data))
+        return out, status
 
     def set_ephemeris_config(self, config):
         """EphemerisConfig of the ephemeris entries of this context (aberration order; two-body propagator only)."""

@@ -190,12 +190,16 @@ constexpr int kEphTile = 128;  // epochs per shared-memory tile: 9 rows x 128 x 
 #endif
 // SECOND = AberrationOrder::Second (aberration.rs:195-209): the line of sight comes from two back-propagations by the
 // light time instead of the linear shift; a separate instantiation, the first-order kernel is untouched by it.
-template <bool SECOND>
+// NBODY = PropagatorKind::NBody (propagator/mod.rs:93-101): the heliocentric state of every (epoch, orbit) entry comes
+// from the DOP853 integration of k_nbody.cuh (state_in [6][n_epochs][n_orbits], equatorial J2000; state_status
+// [n_epochs][n_orbits]) instead of the Kepler solve; everything after the state is the same code.
+template <bool SECOND, bool NBODY = false>
 __global__ void __launch_bounds__(kEphThreads, OUTFIT_EPH_BPS)
 ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const double *__restrict__ epoch,
                          const double *__restrict__ elem, size_t n_epochs, size_t e_stride,
                          const double *__restrict__ mjd_tt, const double *__restrict__ table,
-                         const int *__restrict__ obs_status, double *__restrict__ out, int *__restrict__ status) {
+                         const int *__restrict__ obs_status, double *__restrict__ out, int *__restrict__ status,
+                         const double *__restrict__ state_in = nullptr, const int *__restrict__ state_status = nullptr) {
   __shared__ __align__(16) double tile[9 * kEphTile];
   __shared__ __align__(8) unsigned long long bar;
   const size_t i = (size_t)blockIdx.x * kEphThreads + threadIdx.x;
@@ -271,8 +275,8 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
       const double eps = kEps * 1e2;
       double x = kPi + lon_peri, sF = sx0, cF = cx0;
       int iter = 0;
-      bool run = st == 0, last = false, ok = true, have = true;  // the first evaluation point is per orbit (hoisted above)
-      while (__any_sync(0xffffffffu, run)) {
+      bool run = st == 0 && !NBODY, last = false, ok = true, have = true;  // the first evaluation point is per orbit (hoisted above)
+      while (!NBODY && __any_sync(0xffffffffu, run)) {
         if (run) {
           if (!have) sincos_angle(x, &sF, &cF);
           have = false;
@@ -302,8 +306,15 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
       const double vc = bf_div(n_mot * (a * a), bf_sqrt(xe * xe + ye * ye));
       const double vxe = vc * (bhk * cF - ch * sF);
       const double vye = vc * (ck * cF - bhk * sF);
-      const V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
-      const V3 av = ecl_to_equ(vxe * fv + vye * gv);
+      V3 ap = ecl_to_equ(xe * fv + ye * gv);   // ROT_ECLMJ2000_TO_EQUMJ2000 * pos_ecl
+      V3 av = ecl_to_equ(vxe * fv + vye * gv);
+      if (NBODY) {
+        const size_t ii = i < n_orbits ? i : n_orbits - 1;
+        const size_t at = e * n_orbits + ii, pl = n_epochs * n_orbits;
+        ap = V3{state_in[at], state_in[pl + at], state_in[2 * pl + at]};
+        av = V3{state_in[3 * pl + at], state_in[4 * pl + at], state_in[5 * pl + at]};
+        if (st == 0) st = state_status[at];
+      }
       const V3 op = V3{tile[j], tile[kEphTile + j], tile[2 * kEphTile + j]};
       const V3 ov = V3{tile[3 * kEphTile + j], tile[4 * kEphTile + j], tile[5 * kEphTile + j]};
       const V3 ep = V3{tile[6 * kEphTile + j], tile[7 * kEphTile + j], tile[8 * kEphTile + j]};

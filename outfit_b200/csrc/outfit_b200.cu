@@ -71,6 +71,8 @@ struct OutfitCtx {
   bool phase_valid = false;
   bool count_work = true;  // work counters on (outfit_b200_set_work_counters)
   int aberration_order = 1;  // EphemerisConfig::aberration (outfit_b200_set_ephemeris_config)
+  void *nbody_state = nullptr;  // propagated states of the N-body ephemeris [6][E][n] + status
+  size_t nbody_state_bytes = 0;
 };
 
 static int fail(OutfitCtx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -203,6 +205,7 @@ extern "C" void outfit_b200_destroy(OutfitCtx *ctx) {
   if (ctx->d_zig) cudaFree(ctx->d_zig);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->iod_scratch) cudaFree(ctx->iod_scratch);
+  if (ctx->nbody_state) cudaFree(ctx->nbody_state);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   for (cudaEvent_t e : ctx->phase_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->copy_ev) cudaEventDestroy(e);
@@ -1083,7 +1086,7 @@ extern "C" int outfit_b200_set_ephemeris_config(OutfitCtx *ctx, const OutfitEphe
   if (!ctx || !c) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (c->propagator != OUTFIT_PROPAGATOR_TWOBODY)
-    return fail(ctx, OUTFIT_E_UNSUPPORTED, "PropagatorKind::NBody (DOP853 with planetary perturbations) is not implemented on the device");
+    return fail(ctx, OUTFIT_E_UNSUPPORTED, "PropagatorKind::NBody needs the perturber snapshots: call outfit_b200_ephemeris_nbody, which takes them");
   if (c->aberration != OUTFIT_ABERRATION_FIRST && c->aberration != OUTFIT_ABERRATION_SECOND)
     return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "aberration must be OUTFIT_ABERRATION_FIRST or _SECOND");
   ctx->aberration_order = c->aberration == OUTFIT_ABERRATION_SECOND ? 2 : 1;
@@ -1524,6 +1527,100 @@ extern "C" int outfit_b200_propagate_nbody(OutfitCtx *ctx, size_t n, const int32
     if (e == cudaSuccess && steps) e = cudaMemcpyAsync(steps, d_steps, n * 4, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "propagate_nbody: copy back / kernel", e);
+  } else {
+    cudaStreamSynchronize(stream);
+  }
+  return rc;
+}
+
+// OrbitalElements::compute::<Combined> with PropagatorKind::NBody (ephemeris/mod.rs:189-292, propagator/mod.rs:93-101):
+// DEVICE buffers.  d_bf = [3][n_epochs] per-epoch body-fixed observer positions.
+extern "C" int outfit_b200_ephemeris_nbody_device(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                                  const double *elem, size_t n_epochs, const double *mjd_tt,
+                                                  const double *mjd_ut1, const double *epoch_body_fixed,
+                                                  const OutfitNBodyConfig *cfg, const double *gm, const double *pert_pos,
+                                                  double *out, int32_t *status, void *cuda_stream) {
+  if (!ctx || !cfg) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (n_orbits && n_epochs && (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !epoch_body_fixed || !gm || !pert_pos || !out || !status))
+    return OUTFIT_E_INVALID_ARGUMENT;
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  int rc = check_nbody_cfg(ctx, cfg);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n_orbits == 0 || n_epochs == 0) return OUTFIT_OK;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const size_t n_ent = n_orbits * n_epochs;
+  // propagated states [6][E][n] + their status: a separate slab (the observer table lives in ctx->scratch)
+  if (ctx->nbody_state_bytes < 6 * n_ent * 8 + n_ent * 4 + 256) {
+    if (ctx->nbody_state) { cudaFree(ctx->nbody_state); ctx->nbody_state = nullptr; ctx->nbody_state_bytes = 0; }
+    if (cudaMalloc(&ctx->nbody_state, 6 * n_ent * 8 + n_ent * 4 + 256) != cudaSuccess) return fail(ctx, OUTFIT_E_ALLOC, "cudaMalloc(N-body states)");
+    ctx->nbody_state_bytes = 6 * n_ent * 8 + n_ent * 4 + 256;
+  }
+  double *d_state = reinterpret_cast<double *>(ctx->nbody_state);
+  int *d_sst = reinterpret_cast<int *>(d_state + 6 * n_ent);
+  CK(cudaFuncSetAttribute(ephemeris_nbody_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNbSmemBytes));
+  const NbCfgDev c{cfg->abs_tol, cfg->rel_tol, cfg->n_perturbers, cfg->max_steps ? cfg->max_steps : 100000u};
+  ephemeris_nbody_state_kernel<<<(unsigned)((n_ent * 8 + kNbThreads - 1) / kNbThreads), kNbThreads, kNbSmemBytes, stream>>>(
+      n_orbits, kind, epoch, elem, n_epochs, mjd_tt, c, gm, pert_pos, d_state, d_sst);
+  size_t e_stride;
+  double *d_table;
+  int *d_ost;
+  rc = ephemeris_observer_table(ctx, n_epochs, mjd_tt, mjd_ut1, epoch_body_fixed, nullptr, stream, &e_stride, &d_table, &d_ost);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((n_orbits + kEphThreads - 1) / kEphThreads);
+  if (ctx->aberration_order == 2)
+    ephemeris_twobody_kernel<true, true><<<blocks, kEphThreads, 0, stream>>>(n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table,
+                                                                            d_ost, out, status, d_state, d_sst);
+  else
+    ephemeris_twobody_kernel<false, true><<<blocks, kEphThreads, 0, stream>>>(n_orbits, kind, epoch, elem, n_epochs, e_stride, mjd_tt, d_table,
+                                                                             d_ost, out, status, d_state, d_sst);
+  CK(cudaGetLastError());
+  return OUTFIT_OK;
+}
+
+// HOST buffers: an EphemerisRequest with several observers (as outfit_b200_ephemeris_request) under PropagatorKind::NBody
+extern "C" int outfit_b200_ephemeris_nbody(OutfitCtx *ctx, size_t n_orbits, const int32_t *kind, const double *epoch,
+                                           const double *elem, size_t n_observers, const double *observer_body_fixed,
+                                           const uint64_t *epoch_offset, const double *mjd_tt, const double *mjd_ut1,
+                                           const OutfitNBodyConfig *cfg, const double *gm, const double *pert_pos, double *out,
+                                           int32_t *status) {
+  if (!ctx || !cfg) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (n_observers == 0 || n_orbits == 0) return OUTFIT_OK;
+  std::vector<double> bfp;
+  size_t E = 0;
+  int rc = expand_request(ctx, n_observers, observer_body_fixed, epoch_offset, bfp, &E);
+  if (rc) return rc;
+  if (E == 0) return OUTFIT_OK;
+  if (!kind || !epoch || !elem || !mjd_tt || !mjd_ut1 || !gm || !pert_pos || !out || !status) return OUTFIT_E_INVALID_ARGUMENT;
+  rc = check_nbody_cfg(ctx, cfg);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_host_streams(ctx);
+  if (rc) return rc;
+  const size_t P = cfg->n_perturbers, n = n_orbits, n_ent = n * E;
+  rc = ensure_arena(ctx, n * 4 + n * 8 * (1 + 6 + 3 * P) + 5 * E * 8 + P * 8 + 9 * n_ent * 8 + n_ent * 4 + 16 * 256);
+  if (rc) return rc;
+  cudaStream_t stream = ctx->compute_stream;
+  ArenaPut A{ctx->arena, 0, stream};
+  const int32_t *d_kind = (const int32_t *)A.put(kind, n * 4);
+  const double *d_epoch = (const double *)A.put(epoch, n * 8);
+  const double *d_elem = (const double *)A.put(elem, 6 * n * 8);
+  const double *d_tt = (const double *)A.put(mjd_tt, E * 8);
+  const double *d_ut = (const double *)A.put(mjd_ut1, E * 8);
+  const double *d_bf = (const double *)A.put(bfp.data(), 3 * E * 8);
+  const double *d_gm = (const double *)A.put(gm, P * 8);
+  const double *d_pp = (const double *)A.put(pert_pos, 3 * P * n * 8);
+  double *d_out = (double *)A.raw(9 * n_ent * 8);
+  int32_t *d_st = (int32_t *)A.raw(n_ent * 4);
+  if (A.err != cudaSuccess) { cudaStreamSynchronize(stream); return fail(ctx, OUTFIT_E_CUDA, "ephemeris_nbody: H2D", A.err); }
+  rc = outfit_b200_ephemeris_nbody_device(ctx, n, d_kind, d_epoch, d_elem, E, d_tt, d_ut, d_bf, cfg, d_gm, d_pp, d_out, d_st, stream);
+  if (rc == OUTFIT_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, 9 * n_ent * 8, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_st, n_ent * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = fail(ctx, OUTFIT_E_CUDA, "ephemeris_nbody: copy back / kernel", e);
   } else {
     cudaStreamSynchronize(stream);
   }

@@ -149,7 +149,7 @@ def test_gpu_nbody_matches_oracle(oracle):
     kind, epoch, elem = synth.make_ephemeris_orbits(n, seed=31, mixed_kinds=True)
     rng = np.random.default_rng(32)
     t1 = epoch + rng.uniform(-80.0, 150.0, n)
-    t1[5] = epoch[5]                      # zero span: the initial state, Phi = I
+    t1[:8] = epoch[:8]                    # zero span: the initial state, Phi = I
     gm, pos = _perturbers(oracle, n, seed=33, bodies=(0, 5, 6, 3, 2))
     assert [planet_gm(b) for b in (0, 5, 6, 3, 2)] == list(gm)
     got, gstm, gst, gsteps = ctx.propagate_nbody(kind, epoch, elem, t1, gm, pos)
@@ -161,7 +161,8 @@ def test_gpu_nbody_matches_oracle(oracle):
     scale = np.maximum(1.0, np.abs(wstm[:, ok]).max(axis=0))
     assert (np.abs(gstm[:, ok] - wstm[:, ok]).max(axis=0) / scale).max() < 1e-8
     assert np.abs(gsteps[ok].astype(int) - wsteps[ok].astype(int)).max() <= 3
-    assert gsteps[5] == 0 and np.array_equal(gstm[:, 5].reshape(6, 6), np.eye(6))
+    z = np.flatnonzero(ok[:8])
+    assert len(z) > 0 and (gsteps[z] == 0).all() and all(np.array_equal(gstm[:, i].reshape(6, 6), np.eye(6)) for i in z)
     # NBodyConfig::default(): the Sun alone == the analytic two-body propagation at the tolerance level
     sun, _, sst, _ = ctx.propagate_nbody(kind, epoch, elem, t1, gm[:1], pos[:1], with_stm=False)
     osun, _, _, _ = oracle.propagate_nbody(kind, epoch, elem, t1, gm[:1], pos[:1])
@@ -173,3 +174,43 @@ def test_gpu_nbody_matches_oracle(oracle):
     _, _, bst, _ = ctx.propagate_nbody(kind[:200], epoch[:200], np.ascontiguousarray(elem[:, :200]), t1[:200], gm,
                                        np.ascontiguousarray(pos[:, :, :200]), NBodyConfig(max_steps=2))
     assert (bst[ok[:200] & (gsteps[:200] > 2)] == 21).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aberration", [1, 2])
+def test_gpu_nbody_ephemeris_matches_oracle(oracle, aberration):
+    """OrbitalElements::compute::<Combined> with PropagatorKind::NBody: every (orbit, epoch) entry integrated on its own
+    from the orbit's epoch, then the same observer / aberration / geometry code as the two-body entries."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from outfit_b200 import EphemerisConfig, OutfitB200, synth
+    table = synth.make_ephemeris_table()
+    et = oracle.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    ctx = OutfitB200(0)
+    ctx.load_ephemeris(table)
+    n, E = 400, 9
+    kind, epoch, elem = synth.make_ephemeris_orbits(n, seed=41, mixed_kinds=True)
+    tt, ut1, bf = synth.make_ephemeris_epochs(E, step=7.0, site_idx=2)
+    gm, pos = _perturbers(oracle, n, seed=42, bodies=(0, 5, 3))
+    ctx.set_ephemeris_config(EphemerisConfig(aberration=aberration))
+    got, gst = ctx.ephemeris_nbody(kind, epoch, elem, [(bf, tt, ut1)], gm, pos)
+    want, wst = oracle.ephemeris_nbody_batch(et, kind, epoch, elem, tt, ut1, bf, gm, pos, aberration_order=aberration)
+    assert np.array_equal(gst, wst)
+    ok = wst == 0
+    assert ok.mean() > 0.9 and np.isnan(got[:, ~ok]).all()
+    dang = np.abs((got[0][ok] - want[0][ok] + np.pi) % (2 * np.pi) - np.pi)
+    assert dang.max() < 1e-10
+    for q in (1, 4, 5):
+        assert np.abs(got[q][ok] - want[q][ok]).max() < 1e-10, FIELDS[q]
+    for q in (2, 3):
+        assert (np.abs(got[q][ok] - want[q][ok]) / np.abs(want[q][ok])).max() < 1e-10, FIELDS[q]
+    for q in (6, 7, 8):
+        assert np.abs(got[q][ok] - want[q][ok]).max() < 1e-10, FIELDS[q]
+    # the perturbers are visible: against the two-body ephemeris the sky position moves by far more than the tolerance
+    two, _ = ctx.ephemeris_twobody(kind, epoch, elem, tt, ut1, bf)
+    d = np.abs((got[0][ok] - two[0][ok] + np.pi) % (2 * np.pi) - np.pi)
+    assert d.max() > 1e-8
+
+
+FIELDS = ("ra", "dec", "geocentric_dist", "heliocentric_dist", "phase_angle", "solar_elongation", "radial_velocity", "d_ra_dt", "d_dec_dt")
