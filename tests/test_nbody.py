@@ -207,10 +207,15 @@ def test_gpu_nbody_ephemeris_matches_oracle(oracle, aberration):
         assert (np.abs(got[q][ok] - want[q][ok]) / np.abs(want[q][ok])).max() < 1e-10, FIELDS[q]
     for q in (6, 7, 8):
         assert np.abs(got[q][ok] - want[q][ok]).max() < 1e-10, FIELDS[q]
-    # the perturbers are visible: against the two-body ephemeris the sky position moves by far more than the tolerance
+    # the perturbers are visible against the two-body ephemeris, far above the tolerance: in the sky position with the
+    # first-order aberration; with the second-order one the line of sight comes from two-body back-propagations whatever
+    # the main propagator is (reference behaviour, aberration.rs:176-178), so only the distances carry the N-body state
     two, _ = ctx.ephemeris_twobody(kind, epoch, elem, tt, ut1, bf)
     d = np.abs((got[0][ok] - two[0][ok] + np.pi) % (2 * np.pi) - np.pi)
-    assert d.max() > 1e-8
+    if aberration == 1:
+        assert d.max() > 1e-8
+    else:
+        assert d.max() < 1e-11 and np.abs(got[3][ok] - two[3][ok]).max() > 1e-8
 
 
 FIELDS = ("ra", "dec", "geocentric_dist", "heliocentric_dist", "phase_angle", "solar_elongation", "radial_velocity", "d_ra_dt", "d_dec_dt")
