@@ -29,6 +29,7 @@ Further legs in the same line (each with its own device-resident and end-to-end 
   kepler     configs[1]: 10 M propagate_universal, the reference bench's 8 named scenarios, host entry e2e
   ephemeris  configs[4]: 1 M orbits x 100 epochs, host entry e2e
   lsq        differential correction of the C3 orbits
+  nbody      bulk N-body propagation (DOP853, frozen perturbers, state + STM)
   fit_iod    configs[0]: latency of the single-trajectory entry on the reference's 37-observation quick start
 """
 import argparse
@@ -647,6 +648,46 @@ def main():
             eph["cpu_sample"] = f"{ns} orbits x {n_ep} epochs, oracle (-O3 build) on all {cores} host threads (observer state re-evaluated per entry like the reference)"
         del hk, he, hl, ho, hs
 
+    # N-body leg: bulk EquinoctialElements::propagate_nbody, state + STM, DOP853 at 1e-12
+    nbody = None
+    if not args.no_kepler:
+        try:
+            from outfit_b200 import NBodyConfig, planet_gm
+            import ctypes as C
+            n_nb = 200_000
+            nk, nepoch, nelem = synth.make_ephemeris_orbits(n_nb, seed=20261018 + rank)
+            rng = np.random.default_rng(20261018 + rank)
+            nt1 = nepoch + rng.uniform(20.0, 120.0, n_nb)
+            bodies = (0, 5, 6, 3, 4)
+            radius = {0: 0.0, 3: 1.0, 4: 1.52, 5: 5.2, 6: 9.5}
+            ngm = np.array([planet_gm(b) for b in bodies])
+            npos = np.zeros((len(bodies), 3, n_nb))
+            for j, b in enumerate(bodies):
+                lon = rng.uniform(0, 2 * np.pi, n_nb)
+                npos[j, 0], npos[j, 1] = radius[b] * np.cos(lon), radius[b] * np.sin(lon)
+            dn = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (nk, nepoch, nelem, nt1, ngm, npos)]
+            d_no = torch.empty(6 * n_nb, dtype=torch.float64, device=dev)
+            d_nm = torch.empty(36 * n_nb, dtype=torch.float64, device=dev)
+            d_ns = torch.empty(n_nb, dtype=torch.int32, device=dev)
+            d_nc = torch.empty(n_nb, dtype=torch.int32, device=dev)
+            ncfg = NBodyConfig(n_perturbers=len(bodies))
+
+            def nb_run():
+                rc = ctx._L.outfit_b200_propagate_nbody_device(ctx._h, n_nb, dn[0].data_ptr(), dn[1].data_ptr(), dn[2].data_ptr(),
+                                                               dn[3].data_ptr(), C.byref(ncfg), dn[4].data_ptr(), dn[5].data_ptr(),
+                                                               d_no.data_ptr(), d_nm.data_ptr(), d_ns.data_ptr(), d_nc.data_ptr(), stream)
+                assert rc == 0, rc
+            nms = timed(nb_run, reps=3, warm=1)
+            launches += 4
+            nsteps = d_nc.cpu().numpy()
+            nbody = {"orbits_per_s": n_nb / (nms * 1e-3), "ms": nms, "n": n_nb, "perturbers": len(bodies), "mean_steps": float(nsteps.mean()),
+                     "rhs_evaluations_per_s": float(nsteps.sum()) * 13 / (nms * 1e-3), "ok_fraction": float((d_ns == 0).float().mean().item()),
+                     "workload": "200k main-belt orbits, 5 frozen perturbers (Sun, Jupiter, Saturn, Earth-Moon, Mars), spans of 20-120 days, "
+                                 "DOP853 on [r, v, Phi] at abs_tol = rel_tol = 1e-12 (NBodyConfig::default tolerances); 8 lanes per orbit"}
+            del dn, d_no, d_nm, d_ns, d_nc
+        except Exception as e:  # noqa: BLE001
+            nbody = {"error": str(e)[:300]}
+
     # FitLSQ leg: differential correction of the batch's IOD orbits
     lsq = None
     if not args.no_kepler:
@@ -789,6 +830,7 @@ def main():
                        "iod_kepler_props_per_trajectory": kepler_in_iod / T, **(kep or {})},
             "ephemeris": eph,
             "lsq": lsq,
+            "nbody": nbody,
             "fit_iod": fit_iod,
             "counters": counters,
             "selected_ok_fraction": float((res_host["status"] == 0).mean()),
