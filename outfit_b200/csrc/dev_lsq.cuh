@@ -28,6 +28,17 @@ struct LsqCfgDev {
 
 #define OFB_M6(m, r, c) ((m)[6 * (c) + (r)])
 
+// The FitLSQ kernels are bound by instruction fetch (one trip of their state machine sweeps most of the kernel):
+// the iterative fmod / remainder of the two range reductions, which garbage input alone reaches, stay out of line.
+__device__ __noinline__ double lsq_fmod_cold(double x, double m) { return fmod(x, m); }
+__device__ __noinline__ double lsq_remainder_cold(double x, double m) { return remainder(x, m); }
+__device__ __forceinline__ double lsq_rem_euclid(double x, double m) {  // rem_euclid (dev_kepler.cuh), same values
+  if (x >= 0.0 && x < m) return x;
+  if (x < 0.0 && x > -m) return x + m;
+  const double r = lsq_fmod_cold(x, m);
+  return r < 0.0 ? r + m : r;
+}
+
 // equinoctial_element.rs:258-270
 __device__ __forceinline__ bool lsq_is_bizarre(const double *e, const LsqCfgDev &c) {
   const double ecc = sqrt(e[1] * e[1] + e[2] * e[2]);
@@ -49,8 +60,8 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double n = sqrt(kMu / ((a * a) * a));
   double lam1 = el[6] + n * (t1 - t0);
   double lon_peri = 0.0;
-  if (e2 > kEps * 1e2) lon_peri = rem_euclid(atan2(h, k), kTwoPi);
-  lam1 = rem_euclid(lam1, kTwoPi);
+  if (e2 > kEps * 1e2) lon_peri = lsq_rem_euclid(atan2(h, k), kTwoPi);
+  lam1 = lsq_rem_euclid(lam1, kTwoPi);
   if (lam1 < lon_peri) lam1 += kTwoPi;
   // solve_kepler_equation (:326-348; roots 0.0.8 Newton, eps 100 ulp, 25 iterations)
   const double eps = kEps * 1e2;
@@ -127,7 +138,7 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double rho_xy = hypot(x, y);
   const double rho_xy_sq = rho_xy * rho_xy;
   dec = atan2(z, rho_xy);
-  ra = rem_euclid(atan2(y, x), kTwoPi);
+  ra = lsq_rem_euclid(atan2(y, x), kTwoPi);
   const double rho_sq = rho * rho;
   const V3 gra{-y / rho_xy_sq, x / rho_xy_sq, 0.0};
   const V3 gdec{-z * x / (rho_xy * rho_sq), -z * y / (rho_xy * rho_sq), rho_xy / rho_sq};
@@ -148,108 +159,123 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
 // ecl_to_equ above is (kCos*y - kSin*z, kSin*y + kCos*z); the reference multiplies by the full 3x3
 // matrix, (0*x + c*y) + (-s)*z: the zero products and the sign placement do not change any rounding.
 
+// S = element stride of the 6x6 matrices (1: a private array; kLsqQuads: one column of the quad kernel's shared block);
+// vectors (v, out, b) are always private
+#define OFB_MS(m, r, c) ((m)[(6 * (c) + (r)) * S])
 // nalgebra Cholesky::new: in-place lower factor; false <=> not positive definite
+template <int S = 1>
 __device__ __noinline__ bool lsq_cholesky6(double *m) {
+#pragma unroll 1
   for (int j = 0; j < 6; ++j) {
     for (int k = 0; k < j; ++k) {
-      const double factor = -OFB_M6(m, j, k);
-      for (int i = j; i < 6; ++i) OFB_M6(m, i, j) = factor * OFB_M6(m, i, k) + OFB_M6(m, i, j);
+      const double factor = -OFB_MS(m, j, k);
+      for (int i = j; i < 6; ++i) OFB_MS(m, i, j) = factor * OFB_MS(m, i, k) + OFB_MS(m, i, j);
     }
-    const double diag = OFB_M6(m, j, j);
+    const double diag = OFB_MS(m, j, j);
     if (diag == 0.0 || !(diag >= 0.0)) return false;
     const double denom = sqrt(diag);
-    OFB_M6(m, j, j) = denom;
-    for (int i = j + 1; i < 6; ++i) OFB_M6(m, i, j) = OFB_M6(m, i, j) / denom;
+    OFB_MS(m, j, j) = denom;
+    for (int i = j + 1; i < 6; ++i) OFB_MS(m, i, j) = OFB_MS(m, i, j) / denom;
   }
   return true;
 }
 // Cholesky::inverse: L then L^T substitution on the identity, column by column
-__device__ __noinline__ void lsq_cholesky6_inverse(const double *l, double *inv) {
-  for (int c = 0; c < 6; ++c) {
-    double b[6] = {0, 0, 0, 0, 0, 0};
-    b[c] = 1.0;
-    for (int i = 0; i < 5; ++i) {
-      const double coeff = b[i] / OFB_M6(l, i, i);
-      b[i] = coeff;
-      for (int r = i + 1; r < 6; ++r) b[r] = -coeff * OFB_M6(l, r, i) + b[r];
-    }
-    b[5] = b[5] / OFB_M6(l, 5, 5);
-    for (int i = 5; i >= 0; --i) {
-      double dot = 0.0;
-      for (int r = i + 1; r < 6; ++r) dot += OFB_M6(l, r, i) * b[r];
-      b[i] = (b[i] - dot) / OFB_M6(l, i, i);
-    }
-    for (int r = 0; r < 6; ++r) OFB_M6(inv, r, c) = b[r];
+template <int S = 1>
+__device__ __noinline__ void lsq_cholesky6_inverse_column(const double *l, double *inv, int c) {
+  double b[6];
+  for (int r = 0; r < 6; ++r) b[r] = r == c ? 1.0 : 0.0;
+  for (int i = 0; i < 5; ++i) {
+    const double coeff = b[i] / OFB_MS(l, i, i);
+    b[i] = coeff;
+    for (int r = i + 1; r < 6; ++r) b[r] = -coeff * OFB_MS(l, r, i) + b[r];
   }
+  b[5] = b[5] / OFB_MS(l, 5, 5);
+  for (int i = 5; i >= 0; --i) {
+    double dot = 0.0;
+    for (int r = i + 1; r < 6; ++r) dot += OFB_MS(l, r, i) * b[r];
+    b[i] = (b[i] - dot) / OFB_MS(l, i, i);
+  }
+  for (int r = 0; r < 6; ++r) OFB_MS(inv, r, c) = b[r];
+}
+template <int S = 1>
+__device__ __forceinline__ void lsq_cholesky6_inverse(const double *l, double *inv) {
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c)  // rolled: six copies of the substitution (66 divisions) are 26 KB of code
+    lsq_cholesky6_inverse_column<S>(l, inv, c);
 }
 // nalgebra QR::new + try_inverse (Householder, doubly normalised axis); `m` is destroyed
+template <int S = 1>
 __device__ __noinline__ bool lsq_qr6_inverse(double *m, double *inv) {
   double diag[6];
-  for (int ic = 0; ic < 6; ++ic) {
+#pragma unroll 1
+  for (int ic = 0; ic < 6; ++ic) {  // rolled (the matrix is in memory: dynamic indices cost nothing)
     double sq = 0.0;
-    for (int r = ic; r < 6; ++r) sq += OFB_M6(m, r, ic) * OFB_M6(m, r, ic);
+    for (int r = ic; r < 6; ++r) sq += OFB_MS(m, r, ic) * OFB_MS(m, r, ic);
     const double nrm = sqrt(sq);
-    const double x0 = OFB_M6(m, ic, ic);
+    const double x0 = OFB_MS(m, ic, ic);
     const double modulus = x0 >= 0.0 ? x0 : -x0;
     const double sgn = x0 >= 0.0 ? 1.0 : -1.0;
     const double signed_norm = sgn * nrm;
     const double factor = (sq + modulus * nrm) * 2.0;
-    OFB_M6(m, ic, ic) = x0 + signed_norm;
+    OFB_MS(m, ic, ic) = x0 + signed_norm;
     if (factor != 0.0) {
       const double sf = sqrt(factor);
-      for (int r = ic; r < 6; ++r) OFB_M6(m, r, ic) = OFB_M6(m, r, ic) / sf;
+      for (int r = ic; r < 6; ++r) OFB_MS(m, r, ic) = OFB_MS(m, r, ic) / sf;
       double n2 = 0.0;
-      for (int r = ic; r < 6; ++r) n2 += OFB_M6(m, r, ic) * OFB_M6(m, r, ic);
+      for (int r = ic; r < 6; ++r) n2 += OFB_MS(m, r, ic) * OFB_MS(m, r, ic);
       const double nn = sqrt(n2);
-      for (int r = ic; r < 6; ++r) OFB_M6(m, r, ic) = OFB_M6(m, r, ic) / nn;
+      for (int r = ic; r < 6; ++r) OFB_MS(m, r, ic) = OFB_MS(m, r, ic) / nn;
       const double rn = -signed_norm;
       diag[ic] = rn;
       const double sign = signbit(rn) ? -1.0 : 1.0;
       const double m_two = sign * -2.0;
       for (int c = ic + 1; c < 6; ++c) {
         double dot = 0.0;
-        for (int r = ic; r < 6; ++r) dot += OFB_M6(m, r, ic) * OFB_M6(m, r, c);
+        for (int r = ic; r < 6; ++r) dot += OFB_MS(m, r, ic) * OFB_MS(m, r, c);
         const double fac = (dot - 0.0) * m_two;
-        for (int r = ic; r < 6; ++r) OFB_M6(m, r, c) = fac * OFB_M6(m, r, ic) + sign * OFB_M6(m, r, c);
+        for (int r = ic; r < 6; ++r) OFB_MS(m, r, c) = fac * OFB_MS(m, r, ic) + sign * OFB_MS(m, r, c);
       }
     } else {
       diag[ic] = signed_norm;
     }
   }
+#pragma unroll 1
   for (int c = 0; c < 6; ++c) {
-    double b[6] = {0, 0, 0, 0, 0, 0};
-    b[c] = 1.0;
+    double b[6];
+    for (int r = 0; r < 6; ++r) b[r] = r == c ? 1.0 : 0.0;
     for (int i = 0; i < 6; ++i) {
       const double sign = signbit(diag[i]) ? -1.0 : 1.0;
       double dot = 0.0;
-      for (int r = i; r < 6; ++r) dot += OFB_M6(m, r, i) * b[r];
+      for (int r = i; r < 6; ++r) dot += OFB_MS(m, r, i) * b[r];
       const double fac = (dot - 0.0) * (sign * -2.0);
-      for (int r = i; r < 6; ++r) b[r] = fac * OFB_M6(m, r, i) + sign * b[r];
+      for (int r = i; r < 6; ++r) b[r] = fac * OFB_MS(m, r, i) + sign * b[r];
     }
     for (int i = 5; i >= 0; --i) {
       const double d = fabs(diag[i]);
       if (d == 0.0) return false;
       const double coeff = b[i] / d;
       b[i] = coeff;
-      for (int r = 0; r < i; ++r) b[r] = -coeff * OFB_M6(m, r, i) + b[r];
+      for (int r = 0; r < i; ++r) b[r] = -coeff * OFB_MS(m, r, i) + b[r];
     }
-    for (int r = 0; r < 6; ++r) OFB_M6(inv, r, c) = b[r];
+    for (int r = 0; r < 6; ++r) OFB_MS(inv, r, c) = b[r];
   }
   return true;
 }
 // least_square.rs:329-342 ; `work` is a 36-double temporary
+template <int S = 1>
 __device__ __forceinline__ bool lsq_invert_normal_matrix(const double *m, double *inv, double *work) {
-  for (int i = 0; i < 36; ++i) work[i] = m[i];
-  if (lsq_cholesky6(work)) { lsq_cholesky6_inverse(work, inv); return true; }
-  for (int i = 0; i < 36; ++i) work[i] = m[i];
-  if (lsq_qr6_inverse(work, inv)) return true;
-  for (int i = 0; i < 36; ++i) inv[i] = 0.0;
+  for (int i = 0; i < 36; ++i) work[i * S] = m[i * S];
+  if (lsq_cholesky6<S>(work)) { lsq_cholesky6_inverse<S>(work, inv); return true; }
+  for (int i = 0; i < 36; ++i) work[i * S] = m[i * S];
+  if (lsq_qr6_inverse<S>(work, inv)) return true;
+  for (int i = 0; i < 36; ++i) inv[i * S] = 0.0;
   return false;
 }
+template <int S = 1>
 __device__ __forceinline__ void lsq_gemv6(const double *m, const double *v, double *out) {
-  for (int r = 0; r < 6; ++r) out[r] = OFB_M6(m, r, 0) * v[0];
+  for (int r = 0; r < 6; ++r) out[r] = OFB_MS(m, r, 0) * v[0];
   for (int c = 1; c < 6; ++c)
-    for (int r = 0; r < 6; ++r) out[r] = OFB_M6(m, r, c) * v[c] + out[r];
+    for (int r = 0; r < 6; ++r) out[r] = OFB_MS(m, r, c) * v[c] + out[r];
 }
 __device__ __forceinline__ double lsq_dot6(const double *a, const double *b) {
   double res = 0.0;
@@ -262,7 +288,7 @@ __device__ __forceinline__ double lsq_angular_diff(double a, double b) {
   // the reference's subtract-until-in-range loop never ends for an infinite difference and takes |d| / 2 pi
   // trips for a huge one (garbage input: predicted and observed RA both lie in [0, 2 pi) otherwise); a kernel
   // must not hang on it
-  if (!(fabs(d) < 1e6)) return remainder(d, kTwoPi);
+  if (!(fabs(d) < 1e6)) return lsq_remainder_cold(d, kTwoPi);
   while (d > kPi) d -= kTwoPi;
   while (d < -kPi) d += kTwoPi;
   return d;

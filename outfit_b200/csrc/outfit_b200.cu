@@ -32,6 +32,7 @@ using namespace ofb;
 
 #include "k_iod.cuh"
 #include "k_bulk.cuh"
+#include "k_lsq.cuh"
 #include "k_nbody.cuh"
 
 // =================================================================================================
@@ -751,9 +752,17 @@ extern "C" int outfit_b200_fit_lsq_device(OutfitCtx *ctx, const OutfitLsqConfig 
   B.scorer = d_scorer; B.obs_status = d_status;
   unsigned long long *d_next = reinterpret_cast<unsigned long long *>(d_status + ((n + 1) & ~(size_t)1));
   CK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream));
-  const unsigned long long want = (b->n_traj + 63) / 64;
-  const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQ_BPS;  // resident blocks of 64
-  lsq_kernel<<<(unsigned)(want < cap ? want : cap), 64, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp, d_next);
+  static const bool one_lane = getenv("OUTFIT_B200_LSQ_ONE_LANE") != nullptr;  // A/B switch: the round-1 kernel
+  if (one_lane) {
+    const unsigned long long want = (b->n_traj + 63) / 64;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQ_BPS;  // resident blocks of 64
+    lsq_kernel<<<(unsigned)(want < cap ? want : cap), 64, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp, d_next);
+  } else {
+    const unsigned long long want = (b->n_traj + kLsqQuads - 1) / kLsqQuads;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQQ_BPS;  // resident blocks
+    lsq_quad_kernel<<<(unsigned)(want < cap ? want : cap), kLsqQThreads, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp,
+                                                                                      d_next);
+  }
   CK(cudaGetLastError());
   return OUTFIT_OK;
 }
