@@ -60,33 +60,43 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double n = sqrt(kMu / ((a * a) * a));
   double lam1 = el[6] + n * (t1 - t0);
   double lon_peri = 0.0;
-  if (e2 > kEps * 1e2) lon_peri = lsq_rem_euclid(atan2(h, k), kTwoPi);
+  if (e2 > kEps * 1e2) lon_peri = lsq_rem_euclid(atan2_finite(h, k), kTwoPi);
   lam1 = lsq_rem_euclid(lam1, kTwoPi);
   if (lam1 < lon_peri) lam1 += kTwoPi;
   // solve_kepler_equation (:326-348; roots 0.0.8 Newton, eps 100 ulp, 25 iterations)
   const double eps = kEps * 1e2;
   double F = kPi + lon_peri;
   int iter = 0;
+  // Every lane that entered together leaves together: a lane whose Newton iteration has ended (state != 0)
+  // idles until the slowest of its group is done.  With per-lane `break`s the lanes that left early ran ahead
+  // and the 400 flops below executed once per exit time, at 12 of 32 lanes (profiles/r2h_lsq_lines.txt).
+  int state = 0;  // 0 iterating | 1 converged | 2 failed (the reference returns Err)
   for (;;) {
-    double sx, cx;
-    sincos(F, &sx, &cx);
-    const double f = F - k * sx + h * cx - lam1;
-    const double d = 1.0 - k * cx - h * sx;
-    if (fabs(f) < eps) break;
-    if (fabs(d) < eps) {
-      if (iter == 0) { F = F + 1.0; iter = 1; continue; }
-      return false;
+    if (state == 0) {
+      double sx, cx;
+      sincos_angle(F, &sx, &cx);
+      const double f = F - k * sx + h * cx - lam1;
+      const double d = 1.0 - k * cx - h * sx;
+      if (fabs(f) < eps) {
+        state = 1;
+      } else if (fabs(d) < eps) {
+        if (iter == 0) { F = F + 1.0; iter = 1; }
+        else state = 2;
+      } else {
+        const double x1 = F - f / d;
+        if (fabs(F - x1) < eps) state = 1;
+        else if (++iter >= 25) state = 2;
+        F = x1;
+      }
     }
-    const double x1 = F - f / d;
-    if (fabs(F - x1) < eps) { F = x1; break; }
-    F = x1;
-    if (++iter >= 25) return false;
+    if (!__any_sync(__activemask(), state == 0)) break;
   }
+  if (state == 2) return false;
   // compute_cartesian_position_and_velocity (:639-759)
   const double beta = 1.0 / (1.0 + sqrt(1.0 - e2));
   const double bhk = beta * h * k;
   double sF, cF;
-  sincos(F, &sF, &cF);
+  sincos_angle(F, &sF, &cF);
   const double xe = a * ((1.0 - beta * (h * h)) * cF + bhk * sF - k);
   const double ye = a * ((1.0 - beta * (k * k)) * sF + bhk * cF - h);
   const double u = 1.0 + p * p + q * q;
@@ -137,8 +147,8 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double rho = norm(cor);
   const double rho_xy = hypot(x, y);
   const double rho_xy_sq = rho_xy * rho_xy;
-  dec = atan2(z, rho_xy);
-  ra = lsq_rem_euclid(atan2(y, x), kTwoPi);
+  dec = atan2_finite(z, rho_xy);
+  ra = lsq_rem_euclid(atan2_finite(y, x), kTwoPi);
   const double rho_sq = rho * rho;
   const V3 gra{-y / rho_xy_sq, x / rho_xy_sq, 0.0};
   const V3 gdec{-z * x / (rho_xy * rho_sq), -z * y / (rho_xy * rho_sq), rho_xy / rho_sq};

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q -k "lsq" 2>&1 | tail -3
 echo "== one lane =="; OUTFIT_B200_LSQ_ONE_LANE=1 python tools/gpu_perf_lsq.py
 echo "== quad bps7 =="; python tools/gpu_perf_lsq.py
-for b in 5 6; do echo "== quad bps$b =="; OUTFIT_B200_LIB=$PWD/outfit_b200/lib_q$b.so python tools/gpu_perf_lsq.py; done
+
 
 } > gpurun_out/lsq_ab.log 2>&1
 tail -40 gpurun_out/lsq_ab.log
