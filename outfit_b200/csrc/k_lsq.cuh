@@ -32,6 +32,32 @@ constexpr int kLsqQuads = kLsqQThreads / 4;
 constexpr int kQsNm = 0, kQsCov = 36, kQsWork = 72, kQsLastCov = 108, kQsEl = 144, kQsElLin = 151, kQsRhs = 158,
               kQsQsum = 164, kQsBv = 165, kQsSlots = kQsBv + 4 * 16;
 
+// lsq_cholesky6 (dev_lsq.cuh) on the four lanes of a quad: row i of the factor belongs to lane i mod 4.  Column j
+// needs rows j..5 of the columns before it, final since their own step; every element receives the updates of
+// the serial loop in the same order (k ascending), so the factor is the same to the bit.
+__device__ __forceinline__ bool lsq_cholesky6_quad(double *m, unsigned q, unsigned qmask) {
+#pragma unroll 1
+  for (int j = 0; j < 6; ++j) {
+    for (int i = (int)q; i < 6; i += 4)
+      if (i >= j)
+        for (int k = 0; k < j; ++k) {
+          const double factor = -OFB_M6(m, j, k);
+          OFB_M6(m, i, j) = factor * OFB_M6(m, i, k) + OFB_M6(m, i, j);
+        }
+    __syncwarp(qmask);
+    const double diag = OFB_M6(m, j, j);
+    if (diag == 0.0 || !(diag >= 0.0)) return false;  // the same value on the four lanes
+    const double denom = sqrt(diag);
+    __syncwarp(qmask);
+    for (int i = (int)q; i < 6; i += 4) {
+      if (i == j) OFB_M6(m, j, j) = denom;
+      else if (i > j) OFB_M6(m, i, j) = OFB_M6(m, i, j) / denom;
+    }
+    __syncwarp(qmask);
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kLsqQThreads, OUTFIT_LSQQ_BPS)
 lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ iod, OutfitLsqResult *__restrict__ out,
                 OutfitObsFit *__restrict__ fit, double *__restrict__ tmp, unsigned long long *__restrict__ next) {
@@ -178,18 +204,16 @@ lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ 
       double *nm = &QS(kQsNm), *cov = &QS(kQsCov), *work = &QS(kQsWork);
       // invert_normal_matrix (least_square.rs:329-342): Cholesky on the leader, then the six columns of the
       // inverse on the four lanes (column c on lane c mod 4); Householder QR on the leader if not positive definite
-      int chol = 0;
-      if (lead) {
+      if (lead)
         for (int j = 0; j < 6; ++j)
           if (!C.free_el[j]) {
             for (int k = 0; k < 6; ++k) { OFB_MS(nm, j, k) = 0.0; OFB_MS(nm, k, j) = 0.0; }
             OFB_MS(nm, j, j) = 1.0;
           }
-        for (int i = 0; i < 36; ++i) work[i] = nm[i];
-        chol = lsq_cholesky6<S>(work) ? 1 : 0;
-      }
       __syncwarp(qmask);
-      chol = __shfl_sync(qmask, chol, leader);
+      for (int i = (int)q; i < 36; i += 4) work[i] = nm[i];
+      __syncwarp(qmask);
+      const int chol = lsq_cholesky6_quad(work, q, qmask) ? 1 : 0;
       if (chol) {
         lsq_cholesky6_inverse_column<S>(work, cov, (int)q);
         if (q < 2) lsq_cholesky6_inverse_column<S>(work, cov, (int)q + 4);
@@ -234,10 +258,6 @@ lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ 
           } else {  // advance the state
             for (int j = 0; j < 7; ++j) QS(kQsElLin + j) = el[j];
             have_lin = true;
-            for (int i = 0; i < 36; ++i) {
-              res->normal_matrix[i] = QS(kQsNm + i);  // unscaled until the trajectory finishes
-              QS(kQsLastCov + i) = QS(kQsCov + i);
-            }
             last_rms = new_rms;
             last_nmeas = nmeas;
             for (int j = 0; j < 6; ++j) QS(kQsEl + 1 + j) = corrected[j];
@@ -247,8 +267,13 @@ lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ 
           }
         }
       }
-      if (__shfl_sync(qmask, advance, leader))
+      if (__shfl_sync(qmask, advance, leader)) {
         for (unsigned i = q; i < n_obs; i += 4) { F[i].residual_ra = t_rra[i]; F[i].residual_dec = t_rdec[i]; F[i].chi = t_chi[i]; }
+        for (int i = (int)q; i < 36; i += 4) {
+          res->normal_matrix[i] = QS(kQsNm + i);  // unscaled until the trajectory finishes
+          QS(kQsLastCov + i) = QS(kQsCov + i);
+        }
+      }
       __syncwarp(qmask);
     }
     // ---- the inner loop has ended (diff_cor.rs:400-428) --------------------------------------------------
@@ -316,6 +341,7 @@ lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ 
       const int failed = __shfl_sync(qmask, fail_code, leader);
       if (failed)  // Err(_) => Ok(initial_orbit) (mod.rs:113)
         for (unsigned i = q; i < n_obs; i += 4) { F[i].residual_ra = 0.0; F[i].residual_dec = 0.0; F[i].chi = 0.0; F[i].selection = 0; }
+      double mu2 = 1.0;
       if (lead) {
         res->status = OUTFIT_ST_OK;
         res->total_newton_iterations = total_it;
@@ -325,27 +351,31 @@ lsq_quad_kernel(LsqBatchDev B, LsqCfgDev C, const OutfitIodResult *__restrict__ 
           res->epoch = iod[tr].epoch;
           for (int j = 0; j < 6; ++j) res->elem[j] = iod[tr].elem[j];
           res->normalised_rms = iod[tr].rms;
-          for (int i = 0; i < 36; ++i) res->normal_matrix[i] = 0.0;
         } else {  // rescale_covariance (least_square.rs:371-394)
           double mu = 1.0;
           if (num_free < last_nmeas) {
             const double factor = sqrt((double)last_nmeas / (double)(last_nmeas - num_free));
             mu = last_rms > 1.0 ? last_rms * factor : factor;
           }
-          const double mu2 = mu * mu;
+          mu2 = mu * mu;
           res->kind = OUTFIT_LSQ_CORRECTED;
           res->epoch = QS(kQsEl);
           for (int j = 0; j < 6; ++j) res->elem[j] = QS(kQsEl + 1 + j);
-#pragma unroll 1
-          for (int i = 0; i < 36; ++i) {
-            res->covariance[i] = QS(kQsLastCov + i) * mu2;
-            res->normal_matrix[i] = res->normal_matrix[i] / mu2;
-          }
-#pragma unroll 1
-          for (int j = 0; j < 6; ++j) res->sigma[j] = sqrt(QS(kQsLastCov + 7 * j) * mu2);
           res->normalised_rms = last_rms;
           res->num_measurements = last_nmeas;
         }
+      }
+      mu2 = __shfl_sync(qmask, mu2, leader);
+      if (failed) {
+        for (int i = (int)q; i < 36; i += 4) res->normal_matrix[i] = 0.0;
+      } else {
+#pragma unroll 1
+        for (int i = (int)q; i < 36; i += 4) {
+          res->covariance[i] = QS(kQsLastCov + i) * mu2;
+          res->normal_matrix[i] = res->normal_matrix[i] / mu2;
+        }
+#pragma unroll 1
+        for (int j = (int)q; j < 6; j += 4) res->sigma[j] = sqrt(QS(kQsLastCov + 7 * j) * mu2);
       }
       busy = false;
       __syncwarp(qmask);

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 {
 python -m pytest tests -m gpu -x -q -k "lsq" 2>&1 | tail -3
 echo "== one lane =="; OUTFIT_B200_LSQ_ONE_LANE=1 python tools/gpu_perf_lsq.py
-echo "== quad bps7 =="; python tools/gpu_perf_lsq.py
+echo "== four lanes =="; python tools/gpu_perf_lsq.py
 
 
 } > gpurun_out/lsq_ab.log 2>&1
