@@ -720,7 +720,7 @@ def main():
                "host_entry_bytes": {"h2d": int(n_all * 64 + T * (8 + 128)), "d2h": int(T * 776 + n_all * 32)},
                "corrected_fraction": float((lres["kind"] == 1).mean()), "iod_fallback_fraction": float((lres["kind"] == 2).mean()),
                "newton_iterations": n_it, "observation_equations_per_s": n_it * (n_all / T) / (lms * 1e-3),
-               "workload": "differential correction (two-body, default DifferentialCorrectionConfig) of the same batch from its IOD orbits; one thread per trajectory"}
+               "workload": "differential correction (two-body, default DifferentialCorrectionConfig) of the same batch from its IOD orbits; four lanes per trajectory"}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import binding as O
             et_ = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])

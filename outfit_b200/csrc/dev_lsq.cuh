@@ -1,5 +1,5 @@
 // dev_lsq.cuh -- differential orbit correction (weighted least-squares Newton-Raphson on equinoctial
-// elements with outlier rejection), one thread per trajectory.
+// elements with outlier rejection), four lanes per trajectory (k_lsq.cuh).
 //
 // Reference: differential_orbit_correction/{mod.rs:60-115, diff_cor.rs:282-442,
 // single_iteration.rs:140-317, least_square.rs:188-405, outlier_rejection.rs:118-235},

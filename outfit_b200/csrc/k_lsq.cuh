@@ -1,25 +1,42 @@
-// k_lsq.cuh -- differential orbit correction (FitLSQ) with FOUR lanes per trajectory.
+// k_lsq.cuh -- differential orbit correction (FitLSQ) with FOUR lanes per trajectory (algorithm, reference files
+// and arithmetic: dev_lsq.cuh).
 //
-// Same algorithm, same arithmetic and the same operation order per output number as lsq_kernel (k_bulk.cuh;
-// reference files in dev_lsq.cuh): what changes is who computes what.
-//
-//   * lane 0 of a quad (the leader) owns the control flow of the trajectory: Newton / rejection state machine,
-//     the 6x6 inversion, the convergence tests and the result record;
+//   * lane 0 of a quad (the leader) owns the control flow of the trajectory: the Newton / rejection state
+//     machine, the convergence tests and the scalars of the result record;
 //   * the observation loops -- predicted position + 12 partials per observation (an equinoctial Kepler solve
-//     and ~400 flops each) in the Newton step, and the same partials + two 6x6 products in the rejection pass
-//     -- run four observations at a time, observation i on lane i mod 4;
+//     and ~400 flops each) in the Newton step, the same partials + two 6x6 products in the rejection pass -- run
+//     four observations at a time, observation i on lane i mod 4;
 //   * the normal matrix is accumulated by all four lanes, each owning 9 of its 36 entries (entry e on lane
 //     e mod 4), every entry summed over the observations IN OBSERVATION ORDER, so each entry sees exactly the
-//     additions of the serial loop;
-//   * the matrices (normal matrix, covariance, factorisation work space, last accepted covariance) and the two
-//     element vectors live in shared memory, one column of `kLsqQuads` doubles per number (a quad's numbers
-//     are `kLsqQuads` apart, so the eight leaders of a warp touch eight consecutive doubles: no bank conflict).
-//     lsq_kernel kept them (5 x 36 doubles) in local memory at 255 registers.
+//     additions of a serial loop over the observations;
+//   * the Cholesky factor is built row-parallel (row i on lane i mod 4), the six columns of the inverse
+//     column-parallel, the covariance / normal-matrix rescaling entry-parallel -- each number by the serial
+//     algorithm's operations in the serial order;
+//   * the matrices (normal matrix, covariance, factorisation work space, last accepted covariance), the two
+//     element vectors and the per-round partials live in shared memory, one contiguous block of kQsSlots (odd)
+//     doubles per quad, so the eight leaders of a warp fall in eight different banks.
 //
 // A persistent grid: quads fetch trajectories from a work counter and advance them one Newton step (or one
-// rejection pass) per loop trip, as lsq_kernel's lanes did.
+// rejection pass) per loop trip, so a quad whose trajectory is done (2 steps for a diverging start, 3-8 for a
+// converging one) takes the next one instead of idling.
+//
+// Round 1 ran one lane per trajectory with the five 6x6 matrices in local memory (255 registers, 1.5 KB of
+// spills, 3.3-3.4 ms on 100k x 12).  On the way here, with the records bit-identical at every step
+// (profiles/r2h_lsq_ab*.log): four lanes alone 4.2 ms (slower: instruction fetch, `no_instruction` at 10 stalled
+// warps per issue -- one trip of the state machine swept 187 KB of code); 6x6 loops rolled 3.3 ms; contiguous
+// blocks + parallel inverse columns 2.95 ms; lanes leaving the Kepler iteration of the partials together (they
+// ran its 400-flop tail at 12 of 32 lanes) + transcribed sincos / atan2 1.99 ms; parallel Cholesky rows and
+// result scaling 1.76 ms.
 #pragma once
 #include "dev_lsq.cuh"
+
+struct LsqBatchDev {
+  unsigned long long n_traj, n_obs;
+  const unsigned long long *traj_offset;
+  const double *mjd_tt, *ra, *dec, *sigma_ra, *sigma_dec;
+  const double *scorer;  // [3][n_obs] observer position, equatorial J2000 (scorer_observer_kernel)
+  const int *obs_status; // [n_obs] 0 | OUTFIT_ST_EPHEM_OUT_OF_RANGE
+};
 
 namespace ofb {
 

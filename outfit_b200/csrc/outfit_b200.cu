@@ -6,7 +6,8 @@
 //                     for selection + fold, one lane per (triplet, realization))
 //   dev_geometry.cuh  scorer_observer_kernel, observer_cache_kernel: Chebyshev Earth position + frame rotations
 //   dev_ephemeris.cuh two-body Combined ephemeris (first / second-order aberration)
-//   k_bulk.cuh        propagate_universal_kernel, lsq_kernel, arithmetic self-test, fp64_peak_kernel
+//   k_bulk.cuh        propagate_universal_kernel, arithmetic self-test, fp64_peak_kernel
+//   k_lsq.cuh         lsq_quad_kernel (FitLSQ, four lanes per trajectory)
 // There is no CPU fallback anywhere in this library.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -752,17 +753,10 @@ extern "C" int outfit_b200_fit_lsq_device(OutfitCtx *ctx, const OutfitLsqConfig 
   B.scorer = d_scorer; B.obs_status = d_status;
   unsigned long long *d_next = reinterpret_cast<unsigned long long *>(d_status + ((n + 1) & ~(size_t)1));
   CK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream));
-  static const bool one_lane = getenv("OUTFIT_B200_LSQ_ONE_LANE") != nullptr;  // A/B switch: the round-1 kernel
-  if (one_lane) {
-    const unsigned long long want = (b->n_traj + 63) / 64;
-    const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQ_BPS;  // resident blocks of 64
-    lsq_kernel<<<(unsigned)(want < cap ? want : cap), 64, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp, d_next);
-  } else {
-    const unsigned long long want = (b->n_traj + kLsqQuads - 1) / kLsqQuads;
-    const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQQ_BPS;  // resident blocks
-    lsq_quad_kernel<<<(unsigned)(want < cap ? want : cap), kLsqQThreads, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp,
-                                                                                      d_next);
-  }
+  const unsigned long long want = (b->n_traj + kLsqQuads - 1) / kLsqQuads;
+  const unsigned long long cap = (unsigned long long)ctx->sm_count * OUTFIT_LSQQ_BPS;  // resident blocks
+  lsq_quad_kernel<<<(unsigned)(want < cap ? want : cap), kLsqQThreads, 0, stream>>>(B, to_lsq_dev(*cfg), iod, out, fit, d_tmp,
+                                                                                    d_next);
   CK(cudaGetLastError());
   return OUTFIT_OK;
 }

@@ -14,6 +14,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     --launch-skip 3 -c 3 -o gpurun_out/${TAG}_phases -f python tools/gpu_perf.py > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-ncu --set full --clock-control none --import-source on -k regex:'lsq_kernel' --launch-skip 1 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:'lsq_quad_kernel' --launch-skip 1 -c 1 \
     -o gpurun_out/${TAG}_lsq -f python tools/gpu_perf_lsq.py 30000 > gpurun_out/${TAG}_ncu_lsq.log 2>&1; echo "ncu lsq rc=$?"
 fi
