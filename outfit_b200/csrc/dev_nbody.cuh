@@ -12,9 +12,9 @@
 // dPhi/dt = A(r) Phi couple the columns of Phi only through r, so lane 0 of a group integrates (r, v), lanes 1..6 one
 // column of Phi each (6 doubles per lane), lane 7 idles.  Per stage lane 0 broadcasts the stage position (3 shuffles),
 // every lane rebuilds the 3x3 gravity gradient from the frozen perturbers, and the error norm of the step-size
-// controller is reduced over the group (3 xor-shuffles), so all lanes of a group take the same steps.  The 13 stage
-// derivatives (78 doubles per lane) live in shared memory [slot][thread].  The four groups of a warp run a
-// warp-uniform number of step attempts (finished groups ride along with h = 0).
+// controller is reduced over the group (3 xor-shuffles), so all lanes of a group take the same steps.  The stage
+// derivatives (10 live slots x 6 doubles per lane) live in shared memory [slot][thread].  The four groups of a warp
+// run a warp-uniform number of step attempts (finished groups ride along with h = 0).
 #pragma once
 #include "dev_elements.cuh"
 
@@ -22,8 +22,20 @@ namespace ofb {
 
 #include "dop853_coeffs.inc"
 
-constexpr int kNbThreads = 128;             // 16 orbits per block
-constexpr int kNbSlots = 13 * 6;            // stage derivatives per lane
+#ifndef OUTFIT_NB_THREADS
+#define OUTFIT_NB_THREADS 64
+#endif
+#ifndef OUTFIT_NB_BPS
+#define OUTFIT_NB_BPS 7
+#endif
+constexpr int kNbThreads = OUTFIT_NB_THREADS;  // 8 orbits per block
+// Stage derivatives per lane.  Of the 12 stages k2 feeds only stage 3 and k3 only stages 4 and 5 (the zeros of
+// Hairer's a-matrix), so k11 and k12 take their places: 10 live slots instead of 12 -- with 64-thread blocks 30 KB
+// per block, 7 blocks (14 warps) per SM where 13 slots x 128 threads allowed 2 blocks (8 warps) of a kernel that
+// waits on FP64 latency (warps_active 9 %, profiles/r2h_ncu_bulk.txt).
+constexpr int kNbStageSlots = 10;
+constexpr int kNbSlots = kNbStageSlots * 6;
+__device__ __forceinline__ int nb_stage_slot(int s) { return s == 0 ? 0 : (s == 1 ? 9 : (s == 2 ? 8 : s - 2)); }
 constexpr size_t kNbSmemBytes = (size_t)kNbSlots * kNbThreads * sizeof(double);
 constexpr int kNbMaxPert = 12;
 
@@ -142,7 +154,7 @@ __device__ __forceinline__ int nb_dop853(const NbPert &P, int role, double (&y)[
   const double interval = fabs(span);
   const bool dummy = role == 7;
   const double n_comp = 42.0;
-  auto K = [&](int s, int c) -> double & { return ksm[(size_t)(s * 6 + c) * kNbThreads]; };
+  auto K = [&](int s, int c) -> double & { return ksm[(size_t)(nb_stage_slot(s) * 6 + c) * kNbThreads]; };
   double f[6], w[6], ynew[6];
   unsigned nst = 0;
   int rc = 0;
@@ -199,7 +211,8 @@ __device__ __forceinline__ int nb_dop853(const NbPert &P, int role, double (&y)[
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         double acc = 0.0;
-        for (int j = 0; j < s; ++j) acc += K(j, c) * a[j];
+        for (int j = 0; j < s; ++j)
+          if (j == 0 || j >= (s <= 2 ? 1 : (s <= 4 ? 2 : 3))) acc += K(j, c) * a[j];  // the a-matrix's zeros: exact +0
         w[c] = y[c] + acc * h;
       }
       double dw[6];
@@ -210,7 +223,8 @@ __device__ __forceinline__ int nb_dop853(const NbPert &P, int role, double (&y)[
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       double acc = 0.0;
-      for (int j = 0; j < DOP853_STAGES; ++j) acc += K(j, c) * DOP853_B[j];
+      for (int j = 0; j < DOP853_STAGES; ++j)
+        if (j == 0 || j >= 5) acc += K(j, c) * DOP853_B[j];
       ynew[c] = y[c] + h * acc;
     }
     double fnew[6];
@@ -221,7 +235,8 @@ __device__ __forceinline__ int nb_dop853(const NbPert &P, int role, double (&y)[
       const double scl = atol + fmax(fabs(y[c]), fabs(ynew[c])) * rtol;
       double a5 = fnew[c] * DOP853_E5[DOP853_STAGES], a3 = fnew[c] * DOP853_E3[DOP853_STAGES];
       double b5 = 0.0, b3 = 0.0;
-      for (int j = 0; j < DOP853_STAGES; ++j) { b5 += K(j, c) * DOP853_E5[j]; b3 += K(j, c) * DOP853_E3[j]; }
+      for (int j = 0; j < DOP853_STAGES; ++j)
+        if (j == 0 || j >= 5) { b5 += K(j, c) * DOP853_E5[j]; b3 += K(j, c) * DOP853_E3[j]; }
       a5 = (b5 + a5) / scl; a3 = (b3 + a3) / scl;
       if (!dummy) { e5 += a5 * a5; e3 += a3 * a3; }
     }

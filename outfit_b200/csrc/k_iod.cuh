@@ -193,6 +193,9 @@ roots_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__
 #ifndef OUTFIT_CORRECT_BPS
 #define OUTFIT_CORRECT_BPS 5  // 96 registers, 20 warps per SM: 42.3 ms against 44.5 at 4 blocks / 126 registers (round 2, r2a)
 #endif
+#ifdef OUTFIT_DEBUG_FGHIST
+__device__ unsigned long long g_fghist[3][128];
+#endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kCorrectThreads, OUTFIT_CORRECT_BPS)
 correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *__restrict__ work_counters) {
@@ -282,6 +285,17 @@ correct_kernel(IodBatchDev B, IodDevParams P, IodScratch S, unsigned long long *
     atomicAdd(work_counters + 24, dc >> 8);
 #endif
   }
+#ifdef OUTFIT_DEBUG_FGHIST
+  if (COUNT) {  // distribution of the executed Kepler Newton steps per candidate, and of the maximum over each warp
+    const unsigned mine = w.newton_steps;
+    const unsigned mx = __reduce_max_sync(0xffffffffu, mine), sm = __reduce_add_sync(0xffffffffu, mine);
+    atomicAdd(&g_fghist[0][min(mine / 8u, 127u)], 1ull);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&g_fghist[1][min(mx / 8u, 127u)], 1ull);
+      atomicAdd(&g_fghist[2][0], (unsigned long long)sm); atomicAdd(&g_fghist[2][1], (unsigned long long)mx); atomicAdd(&g_fghist[2][2], 1ull);
+    }
+  }
+#endif
   if (COUNT) {
     Work wk;
     memset(&wk, 0, sizeof wk);

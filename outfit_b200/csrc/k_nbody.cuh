@@ -15,7 +15,7 @@ struct NbCfgDev {
 // position (ecliptic J2000, AU) of every perturber at each orbit's reference epoch (build_perturber_snapshots,
 // nbody.rs:453-476).  out [6][n] = position, velocity at t1 (ecliptic J2000); stm [36][n] column-major or null;
 // status [n]; steps [n] or null.
-__global__ void __launch_bounds__(kNbThreads)
+__global__ void __launch_bounds__(kNbThreads, OUTFIT_NB_BPS)
 propagate_nbody_kernel(size_t n, const int *__restrict__ kind, const double *__restrict__ epoch,
                        const double *__restrict__ elem, const double *__restrict__ t1, NbCfgDev cfg,
                        const double *__restrict__ gm, const double *__restrict__ pert_pos, double *__restrict__ out,
@@ -82,7 +82,7 @@ propagate_nbody_kernel(size_t n, const int *__restrict__ kind, const double *__r
 // integration from the orbit's reference epoch to mjd_tt[e] -- what the reference does, entry by entry -- by one group
 // of eight lanes; the state is rotated to the equatorial frame (ecl_state_to_equ) and written to
 // state [6][n_epochs][n_orbits], status [n_epochs][n_orbits] for ephemeris_twobody_kernel<.., NBODY = true>.
-__global__ void __launch_bounds__(kNbThreads)
+__global__ void __launch_bounds__(kNbThreads, OUTFIT_NB_BPS)
 ephemeris_nbody_state_kernel(size_t n_orbits, const int *__restrict__ kind, const double *__restrict__ epoch,
                              const double *__restrict__ elem, size_t n_epochs, const double *__restrict__ mjd_tt,
                              NbCfgDev cfg, const double *__restrict__ gm, const double *__restrict__ pert_pos,

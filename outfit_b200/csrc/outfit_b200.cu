@@ -903,6 +903,20 @@ extern "C" int outfit_b200_debug_counters(OutfitCtx *ctx, unsigned long long *ou
   return OUTFIT_OK;
 }
 
+#ifdef OUTFIT_DEBUG_FGHIST
+extern "C" int outfit_b200_debug_fghist(OutfitCtx *ctx, unsigned long long *out384, int reset) {
+  if (!ctx || !out384) return OUTFIT_E_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out384, g_fghist, 3 * 128 * sizeof(unsigned long long)));
+  if (reset) {
+    static const unsigned long long zero[3 * 128] = {0};
+    CK(cudaMemcpyToSymbol(g_fghist, zero, sizeof zero));
+  }
+  return OUTFIT_OK;
+}
+#endif
+
 extern "C" int outfit_b200_set_work_counters(OutfitCtx *ctx, int enabled) {
   if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
