@@ -19,6 +19,8 @@ PERF_N=1000000 PERF_E=100 ncu --set full --clock-control none --import-source on
     -o gpurun_out/${TAG}_eph -f python tools/gpu_perf_eph.py > gpurun_out/${TAG}_ncu_eph.log 2>&1; echo "ncu eph rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'lsq_quad_kernel' --launch-skip 1 -c 1 \
     -o gpurun_out/${TAG}_lsq -f python tools/gpu_perf_lsq.py 100000 > gpurun_out/${TAG}_ncu_lsq.log 2>&1; echo "ncu lsq rc=$?"
+PERF_N=500000 ncu --set full --clock-control none --import-source on -k regex:'propagate_nbody_kernel' --launch-skip 1 -c 1 \
+    -o gpurun_out/${TAG}_nbody -f python tools/gpu_perf_nbody.py > gpurun_out/${TAG}_ncu_nbody.log 2>&1; echo "ncu nbody rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c4 > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
 fi
