@@ -281,6 +281,19 @@ def from_soa_batch(batch):
     return out
 
 
+def traj_view(batch, t):
+    """oo_traj_view of trajectory t of a from_soa_batch() batch (the arrays must outlive the view)."""
+    o, e = int(batch["traj_offset"][t]), int(batch["traj_offset"][t + 1])
+    tv = TrajView()
+    tv.n = e - o
+    for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec"):
+        setattr(tv, k, C.cast(batch[k].ctypes.data + 8 * o, c_double_p))
+    tv.helio_equ = C.cast(batch["helio_equ"].ctypes.data + 24 * o, c_double_p)
+    tv.geo_ecl = C.cast(batch["geo_ecl"].ctypes.data + 24 * o, c_double_p)
+    tv.scorer_obs_equ = None
+    return tv
+
+
 def fit_full_iod(batch, table, params, n_threads=0, dedup_earth=False):
     """batch: dict of contiguous float64/uint64 numpy arrays (see outfit_b200.synth)."""
     T = len(batch["traj_offset"]) - 1
@@ -493,4 +506,25 @@ def fit_lsq(batch, table, cfg, iod, n_threads=0):
     lib().oo_fit_lsq(C.c_size_t(T), ptr(batch["traj_offset"]), ptr(batch["mjd_tt"]), ptr(batch["ra"]),
                      ptr(batch["dec"]), ptr(batch["sigma_ra"]), ptr(batch["sigma_dec"]), ptr(batch["geo_ecl"]),
                      C.byref(table), C.byref(cfg), ptr(iod), ptr(out), ptr(fit), n_threads)
+    return out, fit
+
+
+def fit_lsq_nbody(batch, table, cfg, iod, gm, pert_pos, atol=1e-12, rtol=1e-12, n_threads=0):
+    """fit_lsq with PropagatorKind::NBody: gm (P,), pert_pos (P, 3, T) = the perturbers frozen at each trajectory's IOD
+    epoch (heliocentric, ecliptic J2000, AU)."""
+    T = len(batch["traj_offset"]) - 1
+    gm = np.asarray(gm, dtype=np.float64)
+    pert_pos = np.asarray(pert_pos, dtype=np.float64).reshape(len(gm), 3, T)
+    pert = np.zeros((T, len(gm)), dtype=np.dtype([("gm", "<f8"), ("pos", "<f8", (3,))]))
+    pert["gm"] = gm[None, :]
+    pert["pos"] = np.transpose(pert_pos, (2, 0, 1))
+    out = np.zeros(T, dtype=LSQ_RESULT_DTYPE)
+    fit = np.zeros(len(batch["mjd_tt"]), dtype=OBS_FIT_DTYPE)
+    iod = np.ascontiguousarray(iod)
+    L = lib()
+    L.oo_fit_lsq_nbody.restype = None
+    L.oo_fit_lsq_nbody(C.c_size_t(T), ptr(batch["traj_offset"]), ptr(batch["mjd_tt"]), ptr(batch["ra"]), ptr(batch["dec"]),
+                       ptr(batch["sigma_ra"]), ptr(batch["sigma_dec"]), ptr(batch["geo_ecl"]), C.byref(table), C.byref(cfg),
+                       ptr(iod), ptr(pert), C.c_size_t(len(gm)), C.c_double(atol), C.c_double(rtol), ptr(out), ptr(fit),
+                       C.c_int(n_threads))
     return out, fit

@@ -383,6 +383,10 @@ int oo_propagate_twobody_partials(const oo_elements *eq, double t0, double t1, d
 int oo_obs_and_partials(const oo_traj_view *tv, size_t i, const oo_ephem_table *tab,
                         const oo_elements *equi, double *ra, double *dec, double d_ra[6],
                         double d_dec[6]);
+void oo_lsq_set_nbody(const oo_perturber *pert, size_t n_pert, double atol, double rtol);  /* thread-local; n_pert = 0: two-body */
+int oo_obs_and_partials_nbody(const oo_traj_view *tv, size_t i, const oo_ephem_table *tab, const oo_elements *equi,
+                              const oo_perturber *pert, size_t n_pert, double atol, double rtol, double *ra,
+                              double *dec, double d_ra[6], double d_dec[6]);   /* observation_ephemeris.rs:452-486 */
 double oo_angular_diff(double a, double b);
 int oo_invert_normal_matrix(const double m[36], double inv[36]);
 void oo_solve_weighted_least_squares(size_t n, const oo_obs_equation *eqs, const int32_t free_elements[6],
@@ -406,6 +410,14 @@ void oo_fit_lsq(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt
                 const double *dec, const double *sigma_ra, const double *sigma_dec,
                 const double *geo_ecl, const oo_ephem_table *tab, const oo_lsq_config *cfg,
                 const oo_iod_result *iod, oo_lsq_result *out, oo_obs_fit_data *fit, int n_threads);
+
+/* The same with DifferentialCorrectionConfig::propagator = PropagatorKind::NBody: pert[n_traj][n_pert] = the perturbers
+   frozen at each trajectory's IOD epoch. */
+void oo_fit_lsq_nbody(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,
+                      const double *dec, const double *sigma_ra, const double *sigma_dec, const double *geo_ecl,
+                      const oo_ephem_table *tab, const oo_lsq_config *cfg, const oo_iod_result *iod,
+                      const oo_perturber *pert, size_t n_pert, double atol, double rtol, oo_lsq_result *out,
+                      oo_obs_fit_data *fit, int n_threads);
 
 #ifdef __cplusplus
 }

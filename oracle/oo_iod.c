@@ -478,6 +478,9 @@ typedef struct {
   const oo_iod_result *iod;
   oo_lsq_result *out;
   oo_obs_fit_data *fit;
+  const oo_perturber *pert;  /* [n_traj][n_pert] or NULL (two-body) */
+  size_t n_pert;
+  double atol, rtol;
 } lsq_ctx;
 static void lsq_task(long long lo, long long hi, void *vctx) {
   lsq_ctx *c = (lsq_ctx *)vctx;
@@ -489,13 +492,23 @@ static void lsq_task(long long lo, long long hi, void *vctx) {
     tv.sigma_ra = c->sigma_ra + o; tv.sigma_dec = c->sigma_dec + o;
     tv.helio_equ = NULL; tv.geo_ecl = c->geo_ecl + 3 * o;
     tv.scorer_obs_equ = NULL;
+    if (c->pert) oo_lsq_set_nbody(c->pert + (size_t)t * c->n_pert, c->n_pert, c->atol, c->rtol);
     oo_differential_correction(&tv, c->tab, &c->iod[t], c->cfg, &c->out[t], c->fit + o);
+    if (c->pert) oo_lsq_set_nbody(NULL, 0, 0.0, 0.0);
   }
 }
 void oo_fit_lsq(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,
                 const double *dec, const double *sigma_ra, const double *sigma_dec,
                 const double *geo_ecl, const oo_ephem_table *tab, const oo_lsq_config *cfg,
                 const oo_iod_result *iod, oo_lsq_result *out, oo_obs_fit_data *fit, int n_threads) {
-  lsq_ctx c = {traj_offset, mjd_tt, ra, dec, sigma_ra, sigma_dec, geo_ecl, tab, cfg, iod, out, fit};
+  lsq_ctx c = {traj_offset, mjd_tt, ra, dec, sigma_ra, sigma_dec, geo_ecl, tab, cfg, iod, out, fit, NULL, 0, 0.0, 0.0};
+  parallel_for((long long)n_traj, 1, n_threads, lsq_task, &c);
+}
+void oo_fit_lsq_nbody(size_t n_traj, const uint64_t *traj_offset, const double *mjd_tt, const double *ra,
+                      const double *dec, const double *sigma_ra, const double *sigma_dec, const double *geo_ecl,
+                      const oo_ephem_table *tab, const oo_lsq_config *cfg, const oo_iod_result *iod,
+                      const oo_perturber *pert, size_t n_pert, double atol, double rtol, oo_lsq_result *out,
+                      oo_obs_fit_data *fit, int n_threads) {
+  lsq_ctx c = {traj_offset, mjd_tt, ra, dec, sigma_ra, sigma_dec, geo_ecl, tab, cfg, iod, out, fit, pert, n_pert, atol, rtol};
   parallel_for((long long)n_traj, 1, n_threads, lsq_task, &c);
 }

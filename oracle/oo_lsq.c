@@ -151,11 +151,12 @@ int oo_propagate_twobody_partials(const oo_elements *eq, double t0, double t1, d
   return OO_OK;
 }
 
+static void topocentric_partials(const double pe[3], const double ve[3], const double dpos[18], const double obs[3],
+                                 double *ra, double *dec, double d_ra[6], double d_dec[6]);
 /* observation_ephemeris.rs:418-450 (compute_obs_and_partials_2body), :204-258, :322-342 */
 int oo_obs_and_partials(const oo_traj_view *tv, size_t i, const oo_ephem_table *tab,
                         const oo_elements *equi, double *ra, double *dec, double d_ra[6],
                         double d_dec[6]) {
-  const double vlight_au = 2.99792458e5 / OO_AU * 86400.0;
   double h = equi->e[1], k = equi->e[2];
   if (sqrt(h * h + k * k) >= 1.0) return OO_ERR_INVALID_ORBIT;
   double dt = tv->mjd_tt[i] - equi->epoch;
@@ -169,6 +170,14 @@ int oo_obs_and_partials(const oo_traj_view *tv, size_t i, const oo_ephem_table *
     rc = oo_scorer_observer_position(tab, tv->mjd_tt[i], &tv->geo_ecl[3 * i], obs);
     if (rc != OO_OK) return rc;
   }
+  topocentric_partials(pe, ve, dpos, obs, ra, dec, d_ra, d_dec);
+  return OO_OK;
+}
+
+/* topocentric_radec_and_partials + element_partials_from_position_partials (observation_ephemeris.rs:204-258, :322-342) */
+static void topocentric_partials(const double pe[3], const double ve[3], const double dpos[18], const double obs[3],
+                                 double *ra, double *dec, double d_ra[6], double d_dec[6]) {
+  const double vlight_au = 2.99792458e5 / OO_AU * 86400.0;
   double ap[3], av[3], rel[3], cor[3];
   oo_matvec(ROT_ECL2EQU_L, pe, ap);
   oo_matvec(ROT_ECL2EQU_L, ve, av);
@@ -198,6 +207,58 @@ int oo_obs_and_partials(const oo_traj_view *tv, size_t i, const oo_ephem_table *
     d_ra[j] = oo_dot3(drp, dq);
     d_dec[j] = oo_dot3(ddp, dq);
   }
+}
+
+/* PropagatorKind::NBody inside the differential correction (single_iteration.rs:186-191): the frozen perturbers of the
+ * trajectory in hand (PerturberSnapshot at the elements' reference epoch, nbody.rs:453-476) and the integrator
+ * tolerances.  Thread-local: oo_fit_lsq_nbody sets it per trajectory; n_pert == 0 <=> PropagatorKind::TwoBody. */
+static __thread struct { const oo_perturber *pert; size_t n_pert; double atol, rtol; } nb_ctx = {NULL, 0, 0.0, 0.0};
+void oo_lsq_set_nbody(const oo_perturber *pert, size_t n_pert, double atol, double rtol) {
+  nb_ctx.pert = pert; nb_ctx.n_pert = n_pert; nb_ctx.atol = atol; nb_ctx.rtol = rtol;
+}
+
+/* compute_obs_and_partials_nbody (observation_ephemeris.rs:452-486) on EquinoctialElements::propagate_nbody
+ * (equinoctial_element.rs:908-968): state and element Jacobian J0 at the reference epoch, DOP853 on [r, v, Phi], then
+ * d pos(t1) / d elements = the top three rows of Phi(t1) J0 (nbody.rs:552-604). */
+int oo_obs_and_partials_nbody(const oo_traj_view *tv, size_t i, const oo_ephem_table *tab, const oo_elements *equi,
+                              const oo_perturber *pert, size_t n_pert, double atol, double rtol, double *ra,
+                              double *dec, double d_ra[6], double d_dec[6]) {
+  double h = equi->e[1], k = equi->e[2];
+  if (sqrt(h * h + k * k) >= 1.0) return OO_ERR_INVALID_ORBIT;
+  double p0[3], v0[3], dpos0[18], dvel0[18];
+  int rc = oo_propagate_twobody_partials(equi, 0.0, 0.0, p0, v0, dpos0, dvel0);
+  if (rc != OO_OK) return rc;
+  double span = tv->mjd_tt[i] - equi->epoch;
+  double pe[3], ve[3], dpos[18];
+  if (fabs(span) < 1e-14) {
+    memcpy(pe, p0, sizeof pe); memcpy(ve, v0, sizeof ve); memcpy(dpos, dpos0, sizeof dpos);
+  } else {
+    double y[42];
+    memset(y, 0, sizeof y);
+    for (int c = 0; c < 3; c++) { y[c] = p0[c]; y[3 + c] = v0[c]; }
+    for (int c = 0; c < 6; c++) y[6 + 7 * c] = 1.0;
+    rc = oo_dop853_nbody(y, span, pert, n_pert, atol, rtol, 100000u, NULL, NULL);
+    if (rc != OO_OK) return rc;
+    for (int c = 0; c < 3; c++) { pe[c] = y[c]; ve[c] = y[3 + c]; }
+    /* (Phi J0)[c][j] = sum_k Phi[c][k] J0[k][j], Phi column-major at y[6 + 6 k + c]; J0[k][j] = d state_k / d element j */
+    for (int c = 0; c < 3; c++)
+      for (int j = 0; j < 6; j++) {
+        double acc = y[6 + c] * dpos0[j];
+        for (int kk = 1; kk < 6; kk++) {
+          double jk = kk < 3 ? dpos0[6 * kk + j] : dvel0[6 * (kk - 3) + j];
+          acc = y[6 + 6 * kk + c] * jk + acc;
+        }
+        dpos[6 * c + j] = acc;
+      }
+  }
+  double obs[3];
+  if (tv->scorer_obs_equ) {
+    memcpy(obs, &tv->scorer_obs_equ[3 * i], sizeof obs);
+  } else {
+    rc = oo_scorer_observer_position(tab, tv->mjd_tt[i], &tv->geo_ecl[3 * i], obs);
+    if (rc != OO_OK) return rc;
+  }
+  topocentric_partials(pe, ve, dpos, obs, ra, dec, d_ra, d_dec);
   return OO_OK;
 }
 
@@ -407,7 +468,7 @@ size_t oo_update_observation_selection(size_t n, oo_obs_fit_data *fit, const oo_
   return changes;
 }
 
-/* single_iteration.rs:140-317 (apply_correction = true, PropagatorKind::TwoBody) */
+/* single_iteration.rs:140-317 (apply_correction = true; PropagatorKind::TwoBody, or NBody when oo_lsq_set_nbody is on) */
 static void single_iteration(const oo_traj_view *tv, const oo_ephem_table *tab, const oo_obs_fit_data *fit,
                              const oo_elements *el, const int32_t free_elements[6], oo_obs_equation *eqs,
                              oo_obs_fit_data *fit_out, oo_lsq_solution *sol, oo_elements *corrected,
@@ -416,7 +477,10 @@ static void single_iteration(const oo_traj_view *tv, const oo_ephem_table *tab, 
     oo_obs_equation *e = &eqs[i];
     fit_out[i] = fit[i];
     double ra, dec;
-    int ok = fit[i].selection == 0 && oo_obs_and_partials(tv, i, tab, el, &ra, &dec, e->d_ra, e->d_dec) == OO_OK;
+    int ok = fit[i].selection == 0 &&
+             (nb_ctx.n_pert ? oo_obs_and_partials_nbody(tv, i, tab, el, nb_ctx.pert, nb_ctx.n_pert, nb_ctx.atol, nb_ctx.rtol, &ra,
+                                                        &dec, e->d_ra, e->d_dec)
+                            : oo_obs_and_partials(tv, i, tab, el, &ra, &dec, e->d_ra, e->d_dec)) == OO_OK;
     if (!ok) {
       memset(e, 0, sizeof *e);
       e->weight_ra = 1.0 / (1.0 * 1.0);

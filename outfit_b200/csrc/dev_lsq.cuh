@@ -47,16 +47,17 @@ __device__ __forceinline__ bool lsq_is_bizarre(const double *e, const LsqCfgDev 
   return ecc > c.ecc_limit || e[0] < c.min_a || e[0] > c.max_a || peri < c.min_q || apo > c.max_Q;
 }
 
-// compute_obs_and_partials_2body (observation_ephemeris.rs:418-450): predicted (ra, dec) of the orbit
-// `el` = (epoch, a, h, k, p, q, lambda) at one observation and d(ra, dec)/d(elements).
+// propagate_twobody(0.0, dt, true) (equinoctial_element.rs:809-867, 639-759) + compute_derivative (:442-637) of the
+// orbit `el` = (epoch, a, h, k, p, q, lambda): heliocentric position and velocity (ecliptic J2000) at epoch + t1 and the
+// columns col[j] = d pos / d element j (and, with VEL, colv[j] = d vel / d element j).
 // false <=> the reference returns Err (e >= 1, Kepler equation not converged).
-__device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs, V3 obs_equ, double &ra,
-                                                  double &dec, double *d_ra, double *d_dec) {
-  const double epoch = el[0], a = el[1], h = el[2], k = el[3], p = el[4], q = el[5];
+template <bool VEL>
+__device__ __forceinline__ bool lsq_state_and_columns(const double *el, double t1, V3 &pos_out, V3 &vel_out, V3 (&col)[6],
+                                                      V3 (&colv)[6]) {
+  const double a = el[1], h = el[2], k = el[3], p = el[4], q = el[5];
   const double e2 = h * h + k * k;
   if (sqrt(e2) >= 1.0) return false;  // check_elliptical_orbit
-  // propagate_twobody(0.0, dt, true) (equinoctial_element.rs:809-867)
-  const double t0 = 0.0, t1 = t_obs - epoch;
+  const double t0 = 0.0;
   const double n = sqrt(kMu / ((a * a) * a));
   double lam1 = el[6] + n * (t1 - t0);
   double lon_peri = 0.0;
@@ -109,7 +110,7 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double vxe = vconst * (bhk * cF - (1.0 - beta * (h * h)) * sF);
   const double vye = vconst * ((1.0 - beta * (k * k)) * cF - bhk * sF);
   const V3 vel = vxe * fv + vye * gv;
-  // compute_derivative (:442-637), position block only (the velocity block is unused on this path)
+  // compute_derivative (:442-637); the velocity block only where the N-body Jacobian J0 needs it
   const V3 wv{2.0 * p * inv_u, -2.0 * q * inv_u, (1.0 - p * p - q * q) * inv_u};
   const double r = sqrt(xe * xe + ye * ye);
   const double inv_r = 1.0 / r;
@@ -122,7 +123,6 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
   const double tmp5 = beta * k - cF;
   const double tmp6 = beta + (k * k) * b3 * inv_1_beta;
   const double dt = t1 - t0;
-  V3 col[6];
   col[0] = V3{(pos.x - 3.0 * vel.x * dt / 2.0) / a, (pos.y - 3.0 * vel.y * dt / 2.0) / a,
               (pos.z - 3.0 * vel.z * dt / 2.0) / a};
   const double dx1de2 = -a * (tmp1 * tmp2 + a * cF * tmp4 * inv_r);
@@ -138,7 +138,39 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
     col[4] = V3{2.0 * s.x * inv_u, 2.0 * s.y * inv_u, 2.0 * s.z * inv_u};
   }
   col[5] = V3{vel.x / n, vel.y / n, vel.z / n};
-  // topocentric_radec_and_partials (observation_ephemeris.rs:204-258)
+  if (VEL) {
+    const double tmp7 = 1.0 - r / a;
+    const double tmp8 = sF - h;
+    const double tmp9 = cF - k;
+    const double tmp10 = a * cF * inv_r;
+    const double tmp11 = a * sF * inv_r;
+    const double tmp12 = n * (a * a) * inv_r;
+    const double r3 = (r * r) * r;
+    colv[0] = V3{-(vel.x - 3.0 * kMu * pos.x * dt / r3) / (2.0 * a), -(vel.y - 3.0 * kMu * pos.y * dt / r3) / (2.0 * a),
+                 -(vel.z - 3.0 * kMu * pos.z * dt / r3) / (2.0 * a)};
+    const double ir2 = inv_r * inv_r, a2 = a * a;
+    const double dx4de2 = tmp12 * (tmp7 * tmp2 + a2 * tmp8 * tmp4 * ir2 + tmp10 * cF);
+    const double dx5de2 = -tmp12 * (tmp7 * tmp3 + a2 * tmp8 * tmp5 * ir2 - tmp10 * sF);
+    colv[1] = dx4de2 * fv + dx5de2 * gv;
+    const double dx4de3 = tmp12 * (tmp7 * tmp3 + a2 * tmp9 * tmp4 * ir2 - tmp11 * cF);
+    const double dx5de3 = -tmp12 * (tmp7 * tmp6 + a2 * tmp9 * tmp5 * ir2 + tmp11 * sF);
+    colv[2] = dx4de3 * fv + dx5de3 * gv;
+    const V3 t = q * (vye * fv - vxe * gv) - vxe * wv;
+    colv[3] = V3{2.0 * t.x * inv_u, 2.0 * t.y * inv_u, 2.0 * t.z * inv_u};
+    const V3 sv = p * ((-vye) * fv + vxe * gv) + vye * wv;
+    colv[4] = V3{2.0 * sv.x * inv_u, 2.0 * sv.y * inv_u, 2.0 * sv.z * inv_u};
+    const double ir3 = (inv_r * inv_r) * inv_r, a3 = (a * a) * a;
+    colv[5] = V3{-n * a3 * pos.x * ir3, -n * a3 * pos.y * ir3, -n * a3 * pos.z * ir3};
+  }
+  pos_out = pos;
+  vel_out = vel;
+  return true;
+}
+
+// topocentric_radec_and_partials (observation_ephemeris.rs:204-258) + element_partials_from_position_partials: predicted
+// (ra, dec) of the heliocentric state (ecliptic J2000) seen from obs_equ, and d(ra, dec)/d(elements) through col[j]
+__device__ __forceinline__ void lsq_topocentric(V3 pos, V3 vel, const V3 (&col)[6], V3 obs_equ, double &ra, double &dec,
+                                                double *d_ra, double *d_dec) {
   const V3 ap = ecl_to_equ(pos), av = ecl_to_equ(vel);
   const V3 rel = ap - obs_equ;
   const double ltt = norm(rel) / kVlightAu;
@@ -163,6 +195,15 @@ __device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs
     d_ra[j] = dot(drp, dq);
     d_dec[j] = dot(ddp, dq);
   }
+}
+
+// compute_obs_and_partials_2body (observation_ephemeris.rs:418-450): predicted (ra, dec) of the orbit `el` at one
+// observation and d(ra, dec)/d(elements).  false <=> the reference returns Err.
+__device__ __noinline__ bool lsq_obs_and_partials(const double *el, double t_obs, V3 obs_equ, double &ra,
+                                                  double &dec, double *d_ra, double *d_dec) {
+  V3 pos, vel, col[6], colv[6];
+  if (!lsq_state_and_columns<false>(el, t_obs - el[0], pos, vel, col, colv)) return false;
+  lsq_topocentric(pos, vel, col, obs_equ, ra, dec, d_ra, d_dec);
   return true;
 }
 

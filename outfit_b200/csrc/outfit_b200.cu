@@ -8,6 +8,7 @@
 //   dev_ephemeris.cuh two-body Combined ephemeris (first / second-order aberration)
 //   k_bulk.cuh        propagate_universal_kernel, arithmetic self-test, fp64_peak_kernel
 //   k_lsq.cuh         lsq_quad_kernel (FitLSQ, four lanes per trajectory)
+//   k_lsq_nbody.cuh   FitLSQ with PropagatorKind::NBody: init / partials / step kernels driven trip by trip
 // There is no CPU fallback anywhere in this library.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,6 +36,7 @@ using namespace ofb;
 #include "k_bulk.cuh"
 #include "k_lsq.cuh"
 #include "k_nbody.cuh"
+#include "k_lsq_nbody.cuh"
 
 // =================================================================================================
 // context + C-ABI
@@ -1657,6 +1659,142 @@ extern "C" int outfit_b200_selftest_arith(OutfitCtx *ctx, unsigned long long n, 
   // zero / special values: bf_sqrt(0) must be exactly 0
   cudaFree(d);
   if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "selftest_arith", e);
+  return OUTFIT_OK;
+}
+
+// ---- FitLSQ with PropagatorKind::NBody (k_lsq_nbody.cuh) --------------------------------------------------------------
+// DEVICE buffers.  Unlike the two-body entry this one SYNCHRONISES `cuda_stream`: the host drives the state machine
+// trip by trip and reads the number of active trajectories (8 bytes) after every trip.
+extern "C" int outfit_b200_fit_lsq_nbody_device(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb,
+                                                const double *gm, const double *pert_pos, const OutfitObsBatch *b,
+                                                const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit,
+                                                void *cuda_stream) {
+  if (!ctx || !cfg || !nb || !b) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (b->n_traj && (!iod || !out || !fit || !gm || !pert_pos))
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq_nbody: iod, out, fit, gm and perturber_pos are required");
+  if (!ctx->have_eph) return fail(ctx, OUTFIT_E_NO_EPHEMERIS, "outfit_b200_load_ephemeris must be called first");
+  int rc = check_nbody_cfg(ctx, nb);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const size_t n = b->n_obs, T = b->n_traj;
+  if (T == 0) return OUTFIT_OK;
+  if (T > 0xffffffffull) return fail(ctx, OUTFIT_E_UNSUPPORTED, "fit_lsq_nbody: more than 2^32 trajectories in one call");
+  const bool have_geo = b->obs_geo_ecl != nullptr;
+  const bool have_bf = b->observer_body_fixed && b->mjd_ut1;
+  if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  // scratch: scorer[3][n] + tentative residuals[3][n] (+ geo[3][n] + helio[3][n] from pvobs) | records[n] | states[T] |
+  //          status[n] | obs -> trajectory[n] | active counter
+  const size_t planes = have_geo ? 6 : 12;
+  const size_t off_rec = planes * n * sizeof(double);
+  const size_t off_state = off_rec + n * sizeof(LsqNbRec);
+  const size_t off_status = off_state + T * sizeof(LsqNbState);
+  const size_t off_map = off_status + ((n + 1) & ~(size_t)1) * sizeof(int);
+  const size_t off_cnt = off_map + ((n + 1) & ~(size_t)1) * sizeof(unsigned);
+  rc = ensure_scratch(ctx, off_cnt + 256);
+  if (rc) return rc;
+  unsigned char *base = reinterpret_cast<unsigned char *>(ctx->scratch);
+  double *d_scorer = reinterpret_cast<double *>(base);
+  double *d_tmp = d_scorer + 3 * n;
+  LsqNbRec *d_rec = reinterpret_cast<LsqNbRec *>(base + off_rec);
+  LsqNbState *d_state = reinterpret_cast<LsqNbState *>(base + off_state);
+  int *d_status = reinterpret_cast<int *>(base + off_status);
+  unsigned *d_map = reinterpret_cast<unsigned *>(base + off_map);
+  unsigned long long *d_active = reinterpret_cast<unsigned long long *>(base + off_cnt);
+  const double *d_geo = b->obs_geo_ecl;
+  const int tpb = 128;
+  const unsigned gblocks = (unsigned)((n + tpb - 1) / tpb);
+  if (!have_geo) {
+    double *geo = d_scorer + 6 * n, *helio = d_scorer + 9 * n;
+    if (n) observer_cache_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, b->mjd_ut1, b->observer_body_fixed, geo, helio, d_status);
+    d_geo = geo;
+  }
+  if (n) scorer_observer_kernel<<<gblocks, tpb, 0, stream>>>(ctx->eph, n, b->mjd_tt, d_geo, d_scorer, d_status);
+  LsqBatchDev B;
+  B.n_traj = T; B.n_obs = n; B.traj_offset = (const unsigned long long *)b->traj_offset;
+  B.mjd_tt = b->mjd_tt; B.ra = b->ra; B.dec = b->dec; B.sigma_ra = b->sigma_ra; B.sigma_dec = b->sigma_dec;
+  B.scorer = d_scorer; B.obs_status = d_status;
+  const LsqCfgDev C = to_lsq_dev(*cfg);
+  const NbCfgDev nc{nb->abs_tol, nb->rel_tol, nb->n_perturbers, nb->max_steps ? nb->max_steps : 100000u};
+  CK(cudaFuncSetAttribute(lsqnb_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNbSmemBytes));
+  CK(cudaMemsetAsync(d_active, 0, sizeof(unsigned long long), stream));
+  lsqnb_init_kernel<<<(unsigned)((T + 127) / 128), 128, 0, stream>>>(B, C, iod, out, fit, d_state, d_map, d_active);
+  unsigned long long active = 0;
+  CK(cudaMemcpyAsync(&active, d_active, sizeof active, cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  // every trip either ends a trajectory or advances its (outer, inner) counters: bounded by the configuration
+  const unsigned long long max_trips = (cfg->max_newton_iterations + 2) * (cfg->max_outlier_rejection_passes + 2) + 2;
+  const size_t pthreads = n * 8;
+  for (unsigned long long trip = 0; active != 0 && trip < max_trips; ++trip) {
+    CK(cudaMemsetAsync(d_active, 0, sizeof(unsigned long long), stream));
+    lsqnb_partials_kernel<<<(unsigned)((pthreads + kNbThreads - 1) / kNbThreads), kNbThreads, kNbSmemBytes, stream>>>(
+        B, nc, gm, pert_pos, d_state, fit, d_map, d_rec);
+    lsqnb_step_kernel<<<(unsigned)((T + 63) / 64), 64, 0, stream>>>(B, C, iod, out, fit, d_tmp, d_state, d_rec, d_active);
+    CK(cudaMemcpyAsync(&active, d_active, sizeof active, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  CK(cudaGetLastError());
+  if (active != 0) return fail(ctx, OUTFIT_E_CUDA, "fit_lsq_nbody: the state machine did not end within its trip bound");
+  return OUTFIT_OK;
+}
+
+// HOST buffers: the batch, the IOD records and the perturbers go up, the device entry runs, the results come back.
+extern "C" int outfit_b200_fit_lsq_nbody(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb,
+                                         const double *gm, const double *pert_pos, const OutfitObsBatch *hb,
+                                         const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit) {
+  if (!ctx || !cfg || !nb || !hb) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  const size_t T = hb->n_traj, n = hb->n_obs;
+  if (T == 0) return OUTFIT_OK;
+  if (!iod || !out || !gm || !pert_pos) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq_nbody: iod, out, gm and perturber_pos are required");
+  if (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec)
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  int rc = check_nbody_cfg(ctx, nb);
+  if (rc) return rc;
+  rc = check_offsets(ctx, hb, 0, T, nullptr);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const bool have_geo = hb->obs_geo_ecl != nullptr;
+  const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
+  if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  rc = ensure_host_streams(ctx);
+  if (rc) return rc;
+  cudaStream_t stream = ctx->compute_stream;
+  const size_t P = nb->n_perturbers;
+  const size_t bytes = (T + 1) * 8 + 5 * n * 8 + (have_geo ? 3 : 4) * n * 8 + T * sizeof(OutfitIodResult) + T * sizeof(OutfitLsqResult) +
+                       n * sizeof(OutfitObsFit) + P * 8 + P * 3 * T * 8 + 20 * 256;
+  rc = ensure_arena(ctx, bytes);
+  if (rc) return rc;
+  ArenaPut A{ctx->arena, 0, stream};
+  OutfitObsBatch db = *hb;
+  db.traj_offset = (const uint64_t *)A.put(hb->traj_offset, (T + 1) * 8);
+  db.mjd_tt = (const double *)A.put(hb->mjd_tt, n * 8);
+  db.ra = (const double *)A.put(hb->ra, n * 8);
+  db.dec = (const double *)A.put(hb->dec, n * 8);
+  db.sigma_ra = (const double *)A.put(hb->sigma_ra, n * 8);
+  db.sigma_dec = (const double *)A.put(hb->sigma_dec, n * 8);
+  db.obs_helio_equ = nullptr; db.noise_z = nullptr; db.traj_seed = nullptr;
+  if (have_geo) {
+    db.obs_geo_ecl = (const double *)A.put(hb->obs_geo_ecl, 3 * n * 8);
+    db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
+  } else {
+    db.obs_geo_ecl = nullptr;
+    db.observer_body_fixed = (const double *)A.put(hb->observer_body_fixed, 3 * n * 8);
+    db.mjd_ut1 = (const double *)A.put(hb->mjd_ut1, n * 8);
+  }
+  const OutfitIodResult *d_iod = (const OutfitIodResult *)A.put(iod, T * sizeof(OutfitIodResult));
+  const double *d_gm = (const double *)A.put(gm, P * 8);
+  const double *d_pos = (const double *)A.put(pert_pos, P * 3 * T * 8);
+  OutfitLsqResult *d_out = (OutfitLsqResult *)A.raw(T * sizeof(OutfitLsqResult));
+  OutfitObsFit *d_fit = (OutfitObsFit *)A.raw(n * sizeof(OutfitObsFit));
+  if (A.err != cudaSuccess) { cudaStreamSynchronize(stream); return fail(ctx, OUTFIT_E_CUDA, "fit_lsq_nbody: H2D", A.err); }
+  rc = outfit_b200_fit_lsq_nbody_device(ctx, cfg, nb, d_gm, d_pos, &db, d_iod, d_out, d_fit, stream);
+  if (rc != OUTFIT_OK) { cudaStreamSynchronize(stream); return rc; }
+  cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitLsqResult), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && fit) e = cudaMemcpyAsync(fit, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "fit_lsq_nbody: copy back / kernel", e);
   return OUTFIT_OK;
 }
 

@@ -51,7 +51,7 @@ def test_c_abi_exports_every_declared_symbol(lib):
     assert sorted(ABI_SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.outfit_b200_abi_version() == 5  # v4: + OutfitGroup (multi-GPU), fit_iod, ephemeris_request; v5: + propagate_nbody
+    assert lib.outfit_b200_abi_version() == 6  # v4: + OutfitGroup (multi-GPU), fit_iod, ephemeris_request; v5: + propagate_nbody; v6: + fit_lsq_nbody
 
 
 def test_struct_layouts_match_the_oracle_and_numpy_views(lib, oracle):
