@@ -730,6 +730,42 @@ def main():
             O.fit_lsq(ob_, et_, O.default_lsq_config(), io_, n_threads=0)
             lsq["cpu_trajectories_per_s"] = T / (time.perf_counter() - t0)
             lsq["cpu_sample"] = f"the whole batch ({T} trajectories), oracle (-O3 build) on all {cores} host threads"
+        # the same correction with PropagatorKind::NBody on the first 20k trajectories (host entry: the loop is host-driven)
+        if rank == 0:
+            try:
+                Tn = min(T, 20000)
+                sub = {k: (v[:Tn + 1] if k == "traj_offset" else v) for k, v in host_batch.items()}
+                n_sub = int(host_batch["traj_offset"][Tn])
+                for k in ("mjd_tt", "ra", "dec", "sigma_ra", "sigma_dec"):
+                    sub[k] = np.ascontiguousarray(host_batch[k][:n_sub])
+                for k in ("helio_equ", "geo_ecl"):
+                    sub[k] = np.ascontiguousarray(host_batch[k][:, :n_sub])
+                sub["noise_z"] = None
+                bodies = (0, 5, 6, 3, 4)
+                from outfit_b200 import planet_gm
+                gmn = np.array([planet_gm(b) for b in bodies])
+                rngn = np.random.default_rng(11)
+                posn = np.zeros((len(bodies), 3, Tn))
+                for j, rad in enumerate((0.0, 5.2, 9.5, 1.0, 1.52)):
+                    lon = rngn.uniform(0, 2 * np.pi, Tn)
+                    posn[j, 0], posn[j, 1] = rad * np.cos(lon), rad * np.sin(lon)
+                from outfit_b200 import NBodyConfig
+                # accepted-step budget 1000 per integration (a 60-day arc takes ~10): with the library default (100 000) the
+                # few orbits a diverging Newton step throws close to the Sun set the duration of every trip
+                nbc = NBodyConfig(n_perturbers=len(bodies), max_steps=1000)
+                ctx.fit_lsq_nbody(sub, io_host[:Tn], gmn, posn, lcfg, nbc)
+                t0 = time.perf_counter()
+                nres, _ = ctx.fit_lsq_nbody(sub, io_host[:Tn], gmn, posn, lcfg, nbc)
+                nb_s = time.perf_counter() - t0
+                trips = int(nres["total_newton_iterations"].max()) + 2
+                launches += 2 * (2 * trips + 3)
+                lsq["nbody"] = {"trajectories_per_s": Tn / nb_s, "ms": nb_s * 1e3, "n": Tn, "perturbers": len(bodies),
+                                "corrected_fraction": float((nres["kind"] == 1).mean()),
+                                "integrations_per_s": float(nres["total_newton_iterations"].sum()) * (n_sub / Tn) / nb_s,
+                                "api": "outfit_b200_fit_lsq_nbody (host buffers; PropagatorKind::NBody: one DOP853 integration of "
+                                       "[r, v, Phi] per observation and Newton step, 8 lanes each; host-driven trips; max_steps = 1000)"}
+            except Exception as e:  # noqa: BLE001
+                lsq["nbody"] = {"error": str(e)[:300]}
         del d_lo, d_lf, lo_p, lf_p
 
     # configs[0]: latency of the single-trajectory entry (FitIOD::fit_iod) on the reference's quick start

@@ -207,6 +207,21 @@ class Context {
     std::vector<OutfitLsqResult> raw(batch.n_traj);
     if (fit) fit->resize(batch.n_obs);
     check(outfit_b200_fit_lsq(h_, &params, &cfg, &batch, initial_orbits, raw.data(), fit ? fit->data() : nullptr));
+    return lsq_records(raw);
+  }
+  // The same with DifferentialCorrectionConfig::propagator = PropagatorKind::NBody(nbody) (diff_cor.rs:160-173):
+  // gm[n_perturbers], perturber_pos[n_perturbers][3][n_traj] = the perturbers at the epochs of `initial_orbits`
+  // (build_perturber_snapshots, propagator/nbody.rs:453-476).
+  std::vector<LsqOrbitResult> fit_lsq_nbody(const OutfitObsBatch &batch, const OutfitLsqConfig &cfg, const OutfitNBodyConfig &nbody,
+                                            const double *gm, const double *perturber_pos, const OutfitIodResult *initial_orbits,
+                                            std::vector<OutfitObsFit> *fit = nullptr) {
+    std::vector<OutfitLsqResult> raw(batch.n_traj);
+    if (fit) fit->resize(batch.n_obs);
+    check(outfit_b200_fit_lsq_nbody(h_, &cfg, &nbody, gm, perturber_pos, &batch, initial_orbits, raw.data(),
+                                    fit ? fit->data() : nullptr));
+    return lsq_records(raw);
+  }
+  static std::vector<LsqOrbitResult> lsq_records(const std::vector<OutfitLsqResult> &raw) {
     std::vector<LsqOrbitResult> out(raw.size());
     for (size_t t = 0; t < raw.size(); ++t) {
       const OutfitLsqResult &r = raw[t];
