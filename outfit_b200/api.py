@@ -186,7 +186,7 @@ ABI_SYMBOLS = [
     "outfit_b200_ephemeris_config_default", "outfit_b200_set_ephemeris_config", "outfit_b200_group_set_ephemeris_config",
     "outfit_b200_nbody_config_default", "outfit_b200_planet_gm", "outfit_b200_propagate_nbody", "outfit_b200_propagate_nbody_device",
     "outfit_b200_ephemeris_nbody", "outfit_b200_ephemeris_nbody_device",
-    "outfit_b200_fit_lsq_nbody", "outfit_b200_fit_lsq_nbody_device",
+    "outfit_b200_fit_lsq_nbody", "outfit_b200_fit_lsq_nbody_device", "outfit_b200_group_fit_lsq_nbody",
 ]
 
 
@@ -253,6 +253,8 @@ def load_library():
     L.outfit_b200_group_fit_full_iod.argtypes = [vp, C.POINTER(IODParams), C.POINTER(ObsBatch), vp]
     L.outfit_b200_group_fit_lsq.argtypes = [vp, C.POINTER(IODParams), C.POINTER(DifferentialCorrectionConfig),
                                             C.POINTER(ObsBatch), vp, vp, vp]
+    L.outfit_b200_group_fit_lsq_nbody.argtypes = [vp, C.POINTER(DifferentialCorrectionConfig), C.POINTER(NBodyConfig), vp, vp,
+                                                  C.POINTER(ObsBatch), vp, vp, vp]
     L.outfit_b200_group_propagate_universal.argtypes = [vp, C.c_size_t, vp, vp, vp, vp, C.POINTER(SolverType), vp, vp]
     L.outfit_b200_group_ephemeris_request.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
     L.outfit_b200_group_last_shards.argtypes = [vp, vp, vp]
@@ -672,6 +674,23 @@ class OutfitGroup:
         self._check(self._L.outfit_b200_group_fit_lsq(self._h, C.byref(iod_params) if iod_params is not None else None,
                                                       C.byref(cfg), C.byref(b), io.ctypes.data if io is not None else None,
                                                       out.ctypes.data, fit.ctypes.data))
+        return out, fit
+
+    def fit_lsq_nbody(self, batch, initial_orbits, gm, perturber_pos, cfg=None, nbody=None, use_body_fixed=False):
+        cfg = cfg or DifferentialCorrectionConfig.default()
+        b = OutfitB200._batch_struct(batch, use_body_fixed)
+        b.noise_z = None
+        T, P = int(b.n_traj), int(len(gm))
+        nb = nbody or NBodyConfig(n_perturbers=P)
+        nb.n_perturbers = P
+        gm = np.ascontiguousarray(gm, dtype=np.float64)
+        pp = np.ascontiguousarray(perturber_pos, dtype=np.float64)
+        assert pp.shape == (P, 3, T)
+        io = np.ascontiguousarray(initial_orbits, dtype=RESULT_DTYPE)
+        out = np.zeros(T, dtype=LSQ_RESULT_DTYPE)
+        fit = np.zeros(int(b.n_obs), dtype=OBS_FIT_DTYPE)
+        self._check(self._L.outfit_b200_group_fit_lsq_nbody(self._h, C.byref(cfg), C.byref(nb), _p(gm), _p(pp), C.byref(b),
+                                                            io.ctypes.data, out.ctypes.data, fit.ctypes.data))
         return out, fit
 
     def propagate_universal(self, rv, t0, t1, solver=None, psi_guess=None, out=None, status=None):

@@ -1739,26 +1739,16 @@ extern "C" int outfit_b200_fit_lsq_nbody_device(OutfitCtx *ctx, const OutfitLsqC
   return OUTFIT_OK;
 }
 
-// HOST buffers: the batch, the IOD records and the perturbers go up, the device entry runs, the results come back.
-extern "C" int outfit_b200_fit_lsq_nbody(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb,
-                                         const double *gm, const double *pert_pos, const OutfitObsBatch *hb,
-                                         const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit) {
-  if (!ctx || !cfg || !nb || !hb) return OUTFIT_E_INVALID_ARGUMENT;
-  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-  const size_t T = hb->n_traj, n = hb->n_obs;
+// HOST buffers, trajectories [tb, te) of the batch: their observations, IOD records and perturbers go up, the device
+// entry runs, the results come back (iod / out = &records[tb], fit = &fit[0], pert_pos [P][3][hb->n_traj]).
+static int fit_lsq_nbody_range(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb, const double *gm,
+                               const double *pert_pos, const OutfitObsBatch *hb, size_t tb, size_t te,
+                               const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit) {
+  const size_t T = te - tb;
   if (T == 0) return OUTFIT_OK;
-  if (!iod || !out || !gm || !pert_pos) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq_nbody: iod, out, gm and perturber_pos are required");
-  if (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec)
-    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
-  int rc = check_nbody_cfg(ctx, nb);
-  if (rc) return rc;
-  rc = check_offsets(ctx, hb, 0, T, nullptr);
-  if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+  const size_t o0 = hb->traj_offset[tb], n = hb->traj_offset[te] - o0, n_all = hb->n_obs, T_all = hb->n_traj;
   const bool have_geo = hb->obs_geo_ecl != nullptr;
-  const bool have_bf = hb->observer_body_fixed && hb->mjd_ut1;
-  if (!have_geo && !have_bf) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
-  rc = ensure_host_streams(ctx);
+  int rc = ensure_host_streams(ctx);
   if (rc) return rc;
   cudaStream_t stream = ctx->compute_stream;
   const size_t P = nb->n_perturbers;
@@ -1768,34 +1758,84 @@ extern "C" int outfit_b200_fit_lsq_nbody(OutfitCtx *ctx, const OutfitLsqConfig *
   if (rc) return rc;
   ArenaPut A{ctx->arena, 0, stream};
   OutfitObsBatch db = *hb;
-  db.traj_offset = (const uint64_t *)A.put(hb->traj_offset, (T + 1) * 8);
-  db.mjd_tt = (const double *)A.put(hb->mjd_tt, n * 8);
-  db.ra = (const double *)A.put(hb->ra, n * 8);
-  db.dec = (const double *)A.put(hb->dec, n * 8);
-  db.sigma_ra = (const double *)A.put(hb->sigma_ra, n * 8);
-  db.sigma_dec = (const double *)A.put(hb->sigma_dec, n * 8);
+  db.n_traj = T; db.n_obs = n;
+  if (o0 == 0) {
+    db.traj_offset = (const uint64_t *)A.put(hb->traj_offset + tb, (T + 1) * 8);
+  } else {
+    rc = ensure_host_staging(ctx, (T + 1) * 8);
+    if (rc) return rc;
+    uint64_t *h = reinterpret_cast<uint64_t *>(ctx->h_scratch);
+    for (size_t t = 0; t <= T; ++t) h[t] = hb->traj_offset[tb + t] - o0;
+    db.traj_offset = (const uint64_t *)A.put(h, (T + 1) * 8);
+  }
+  db.mjd_tt = (const double *)A.put(hb->mjd_tt + o0, n * 8);
+  db.ra = (const double *)A.put(hb->ra + o0, n * 8);
+  db.dec = (const double *)A.put(hb->dec + o0, n * 8);
+  db.sigma_ra = (const double *)A.put(hb->sigma_ra + o0, n * 8);
+  db.sigma_dec = (const double *)A.put(hb->sigma_dec + o0, n * 8);
   db.obs_helio_equ = nullptr; db.noise_z = nullptr; db.traj_seed = nullptr;
   if (have_geo) {
-    db.obs_geo_ecl = (const double *)A.put(hb->obs_geo_ecl, 3 * n * 8);
+    db.obs_geo_ecl = (const double *)A.put_planes(hb->obs_geo_ecl, n_all, o0, n);
     db.observer_body_fixed = nullptr; db.mjd_ut1 = nullptr;
   } else {
     db.obs_geo_ecl = nullptr;
-    db.observer_body_fixed = (const double *)A.put(hb->observer_body_fixed, 3 * n * 8);
-    db.mjd_ut1 = (const double *)A.put(hb->mjd_ut1, n * 8);
+    db.observer_body_fixed = (const double *)A.put_planes(hb->observer_body_fixed, n_all, o0, n);
+    db.mjd_ut1 = (const double *)A.put(hb->mjd_ut1 + o0, n * 8);
   }
   const OutfitIodResult *d_iod = (const OutfitIodResult *)A.put(iod, T * sizeof(OutfitIodResult));
   const double *d_gm = (const double *)A.put(gm, P * 8);
-  const double *d_pos = (const double *)A.put(pert_pos, P * 3 * T * 8);
+  const double *d_pos = (const double *)A.put_planes(pert_pos, T_all, tb, T, (int)(3 * P));
   OutfitLsqResult *d_out = (OutfitLsqResult *)A.raw(T * sizeof(OutfitLsqResult));
   OutfitObsFit *d_fit = (OutfitObsFit *)A.raw(n * sizeof(OutfitObsFit));
   if (A.err != cudaSuccess) { cudaStreamSynchronize(stream); return fail(ctx, OUTFIT_E_CUDA, "fit_lsq_nbody: H2D", A.err); }
   rc = outfit_b200_fit_lsq_nbody_device(ctx, cfg, nb, d_gm, d_pos, &db, d_iod, d_out, d_fit, stream);
   if (rc != OUTFIT_OK) { cudaStreamSynchronize(stream); return rc; }
   cudaError_t e = cudaMemcpyAsync(out, d_out, T * sizeof(OutfitLsqResult), cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess && fit) e = cudaMemcpyAsync(fit, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && fit) e = cudaMemcpyAsync(fit + o0, d_fit, n * sizeof(OutfitObsFit), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) return fail(ctx, OUTFIT_E_CUDA, "fit_lsq_nbody: copy back / kernel", e);
   return OUTFIT_OK;
+}
+
+static int check_lsq_nbody_host_args(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb, const double *gm,
+                                     const double *pert_pos, const OutfitObsBatch *hb, const OutfitIodResult *iod, const void *out) {
+  if (!ctx || !cfg || !nb || !hb) return OUTFIT_E_INVALID_ARGUMENT;
+  if (hb->n_traj == 0) return OUTFIT_OK;
+  if (!iod || !out || !gm || !pert_pos) return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "fit_lsq_nbody: iod, out, gm and perturber_pos are required");
+  if (!hb->traj_offset || !hb->mjd_tt || !hb->ra || !hb->dec || !hb->sigma_ra || !hb->sigma_dec)
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "NULL observation array");
+  if (!hb->obs_geo_ecl && !(hb->observer_body_fixed && hb->mjd_ut1))
+    return fail(ctx, OUTFIT_E_INVALID_ARGUMENT, "need obs_geo_ecl or observer_body_fixed+mjd_ut1");
+  const int rc = check_nbody_cfg(ctx, nb);
+  if (rc) return rc;
+  return check_offsets(ctx, hb, 0, hb->n_traj, nullptr);
+}
+
+extern "C" int outfit_b200_fit_lsq_nbody(OutfitCtx *ctx, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb,
+                                         const double *gm, const double *pert_pos, const OutfitObsBatch *hb,
+                                         const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit) {
+  if (!ctx) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  const int rc = check_lsq_nbody_host_args(ctx, cfg, nb, gm, pert_pos, hb, iod, out);
+  if (rc || hb->n_traj == 0) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return fit_lsq_nbody_range(ctx, cfg, nb, gm, pert_pos, hb, 0, hb->n_traj, iod, out, fit);
+}
+
+// one call, every GPU of the group: trajectory ranges of equal observation counts (the integrations dominate)
+extern "C" int outfit_b200_group_fit_lsq_nbody(OutfitGroup *g, const OutfitLsqConfig *cfg, const OutfitNBodyConfig *nb,
+                                               const double *gm, const double *pert_pos, const OutfitObsBatch *hb,
+                                               const OutfitIodResult *iod, OutfitLsqResult *out, OutfitObsFit *fit) {
+  if (!g || g->ctx.empty()) return OUTFIT_E_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g->mu);
+  const int rc = check_lsq_nbody_host_args(g->ctx[0], cfg, nb, gm, pert_pos, hb, iod, out);
+  if (rc) { g->last_error = g->ctx[0]->last_error; return rc; }
+  if (hb->n_traj == 0) return OUTFIT_OK;
+  std::vector<unsigned long long> cuts(g->ctx.size() + 1, 0ull);
+  outfit_b200_shard_ranges(hb->n_traj, hb->traj_offset, 1u, 0ull, (int)g->ctx.size(), reinterpret_cast<uint64_t *>(cuts.data()));
+  return group_run(g, cuts, [&](size_t, OutfitCtx *c, unsigned long long tb, unsigned long long te) {
+    return fit_lsq_nbody_range(c, cfg, nb, gm, pert_pos, hb, tb, te, iod + tb, out + tb, fit);
+  });
 }
 
 extern "C" int outfit_b200_measure_fp64_peak(OutfitCtx *ctx, double *flops_per_s) {

@@ -301,6 +301,16 @@ class Group {
     check(outfit_b200_group_fit_full_iod(g_, &params, &batch, raw.data()));
     return Context::from_raw(raw);
   }
+  // FitLSQ::fit_lsq with PropagatorKind::NBody over every GPU of the group (raw records, batch order)
+  std::vector<OutfitLsqResult> fit_lsq_nbody(const OutfitObsBatch &batch, const OutfitLsqConfig &cfg, const OutfitNBodyConfig &nbody,
+                                             const double *gm, const double *perturber_pos, const OutfitIodResult *initial_orbits,
+                                             std::vector<OutfitObsFit> *fit = nullptr) {
+    std::vector<OutfitLsqResult> raw(batch.n_traj);
+    if (fit) fit->resize(batch.n_obs);
+    check(outfit_b200_group_fit_lsq_nbody(g_, &cfg, &nbody, gm, perturber_pos, &batch, initial_orbits, raw.data(),
+                                          fit ? fit->data() : nullptr));
+    return raw;
+  }
   void propagate_universal(size_t n, const double *rv, const double *t0, const double *t1, const OutfitSolverType &solver,
                            double *out, int32_t *status, const double *psi_guess = nullptr) {
     check(outfit_b200_group_propagate_universal(g_, n, rv, t0, t1, psi_guess, &solver, out, status));

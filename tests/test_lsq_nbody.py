@@ -152,3 +152,30 @@ def test_gpu_nbody_lsq_with_the_sun_alone_is_the_twobody_lsq(oracle):
     # the failed-IOD trajectories pass through untouched in both
     bad = a["kind"] == 0
     assert np.array_equal(a[bad], b[bad])
+
+
+@pytest.mark.gpu
+def test_group_nbody_lsq_equals_one_context(oracle):
+    """outfit_b200_group_fit_lsq_nbody over several contexts (all GPUs of the box, or three contexts on one GPU): the
+    records at their global indices, bit-identical to the single-context call."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from outfit_b200 import DifferentialCorrectionConfig, NBodyConfig, OutfitB200, OutfitGroup, RESULT_DTYPE, synth
+    T = 150
+    table = synth.make_ephemeris_table()
+    batch = synth.make_trajectories(T, (8, 20), seed=403, table=table, max_triplets=10, n_noise=1)
+    ctx = OutfitB200(0)
+    ctx.load_ephemeris(table)
+    from outfit_b200 import IODParams
+    iod = ctx.fit_full_iod(batch, IODParams.builder(n_noise_realizations=0, max_triplets=10))
+    gm, pos = _perturbers(oracle, T, 4, (0, 5, 3))
+    cfg, nb = DifferentialCorrectionConfig.default(), NBodyConfig(n_perturbers=3, max_steps=2000)
+    one, ofit = ctx.fit_lsq_nbody(batch, iod, gm, pos, cfg, nb)
+    n_dev = torch.cuda.device_count()
+    grp = OutfitGroup(list(range(n_dev)) if n_dev > 1 else [0, 0, 0])
+    grp.load_ephemeris(table)
+    many, mfit = grp.fit_lsq_nbody(batch, iod, gm, pos, cfg, nb)
+    assert (one["kind"] == 1).sum() > 30
+    assert one.tobytes() == many.tobytes() and ofit.tobytes() == mfit.tobytes()
+    grp.close()
