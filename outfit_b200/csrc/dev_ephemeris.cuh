@@ -341,8 +341,8 @@ ephemeris_twobody_kernel(size_t n_orbits, const int *__restrict__ kind, const do
       o[3] = helio;
       const double rho = bf_sqrt(dot(topo, topo));
       const double r_obs = bf_sqrt(dot(op, op));
-      o[4] = acos(clampd(bf_div(dot(ap, topo), helio * rho), -1.0, 1.0));
-      o[5] = acos(clampd(bf_div(-dot(op, topo), r_obs * rho), -1.0, 1.0));
+      o[4] = acos_unit(clampd(bf_div(dot(ap, topo), helio * rho), -1.0, 1.0));
+      o[5] = acos_unit(clampd(bf_div(-dot(op, topo), r_obs * rho), -1.0, 1.0));
       const V3 vt = av - ov;
       o[6] = bf_div(dot(topo, vt), rho);
       const double dxy2 = topo.x * topo.x + topo.y * topo.y;
