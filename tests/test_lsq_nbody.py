@@ -179,3 +179,34 @@ def test_group_nbody_lsq_equals_one_context(oracle):
     assert (one["kind"] == 1).sum() > 30
     assert one.tobytes() == many.tobytes() and ofit.tobytes() == mfit.tobytes()
     grp.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nbody_lsq_with_on_device_observer_geometry(oracle):
+    """Body-fixed observer coordinates + UT1 (pvobs on the device) instead of a precomputed cache: parity with the oracle
+    fed by the oracle's own pvobs / Earth positions, from the same initial orbits."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from outfit_b200 import DifferentialCorrectionConfig, IODParams, NBodyConfig, OutfitB200, synth
+    from parity_util import oracle_observer_cache
+    T = 120
+    table = synth.make_ephemeris_table()
+    et = oracle.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
+    batch = synth.make_trajectories(T, 12, seed=404, table=table, max_triplets=10, n_noise=1)
+    ctx = OutfitB200(0)
+    ctx.load_ephemeris(table)
+    iod = ctx.fit_full_iod(batch, IODParams.builder(n_noise_realizations=0, max_triplets=10), use_body_fixed=True)
+    gm, pos = _perturbers(oracle, T, 6, (0, 5))
+    got, gfit = ctx.fit_lsq_nbody(batch, iod, gm, pos, DifferentialCorrectionConfig.default(), NBodyConfig(n_perturbers=2),
+                                  use_body_fixed=True)
+    hel, geo = oracle_observer_cache(oracle, et, batch)
+    ob = oracle.from_soa_batch(batch)
+    ob["helio_equ"], ob["geo_ecl"] = hel, geo
+    oiod = np.ascontiguousarray(iod.view(oracle.IOD_RESULT_DTYPE))
+    want, wfit = oracle.fit_lsq_nbody(ob, et, oracle.default_lsq_config(), oiod, gm, pos, n_threads=0)
+    assert np.array_equal(got["status"], want["status"]) and (got["kind"] == want["kind"]).mean() > 0.97
+    ok = (got["kind"] == 1) & (want["kind"] == 1)
+    assert ok.sum() > 40
+    d = np.abs(got["elem"][ok] - want["elem"][ok]).max(axis=1)
+    assert np.median(d) < 1e-9 and np.quantile(d, 0.95) < 1e-6, (np.median(d), d.max())
