@@ -113,8 +113,8 @@ RESULT_DTYPE = np.dtype([
 assert RESULT_DTYPE.itemsize == C.sizeof(IodResult)
 
 class EphemerisConfig(C.Structure):
-    """EphemerisConfig (ephemeris/mod.rs:124-142): propagator 0 TwoBody | 1 NBody (unsupported on the device);
-    aberration 1 First (default) | 2 Second."""
+    """EphemerisConfig (ephemeris/mod.rs:124-142): propagator 0 TwoBody | 1 NBody (rejected here: the N-body ephemeris needs the
+    perturber snapshots and has its own entry, OutfitB200.ephemeris_nbody); aberration 1 First (default) | 2 Second."""
     _fields_ = [("propagator", C.c_int32), ("aberration", C.c_int32)]
 
     def __init__(self, propagator=0, aberration=1):
