@@ -1724,7 +1724,10 @@ extern "C" int outfit_b200_fit_lsq_nbody_device(OutfitCtx *ctx, const OutfitLsqC
   CK(cudaMemcpyAsync(&active, d_active, sizeof active, cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   // every trip either ends a trajectory or advances its (outer, inner) counters: bounded by the configuration
-  const unsigned long long max_trips = (cfg->max_newton_iterations + 2) * (cfg->max_outlier_rejection_passes + 2) + 2;
+  const unsigned long long lim = 1ull << 31;  // saturating: absurd iteration caps must not wrap the bound
+  const unsigned long long a_ = cfg->max_newton_iterations < lim ? cfg->max_newton_iterations + 2 : lim;
+  const unsigned long long b_ = cfg->max_outlier_rejection_passes < lim ? cfg->max_outlier_rejection_passes + 2 : lim;
+  const unsigned long long max_trips = a_ * b_ + 2;
   const size_t pthreads = n * 8;
   for (unsigned long long trip = 0; active != 0 && trip < max_trips; ++trip) {
     CK(cudaMemsetAsync(d_active, 0, sizeof(unsigned long long), stream));
