@@ -516,6 +516,11 @@ class OutfitB200:
                                                           _p(off), _p(tt), _p(ut), out.ctypes.data, status.ctypes.data))
         return out, status
 
+    def compute_ephemerides(self, results, observers, iod_results=None):
+        """FullOrbitResultExt::compute_ephemerides (ephemeris/batch.rs:134-183): the ephemeris request for every orbit of
+        a fit result array (IOD or LSQ records); failed fits give status 9 (InvalidConversion) entries."""
+        return _compute_ephemerides(self, results, observers, iod_results)
+
     def propagate_nbody(self, kind, epoch, elem, t1, gm, perturber_pos, config=None, with_stm=True):
         """EquinoctialElements::propagate_nbody in bulk (HOST arrays): kind (n,) int32, epoch (n,), elem (6, n), t1 (n,),
         gm (P,), perturber_pos (P, 3, n) heliocentric ecliptic J2000 at each orbit's epoch
@@ -598,6 +603,40 @@ def pinned_empty(shape, dtype):
     buf = (C.c_char * max(n, 1)).from_address(ptr)
     buf._owner = _Owner(ptr)
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+
+def orbits_of_results(results, iod_results=None):
+    """(kind (n,) int32, epoch (n,), elem (6, n), ok (n,) bool) of fit records, for the ephemeris entries: RESULT_DTYPE
+    records give the IOD orbit; LSQ_RESULT_DTYPE records give the corrected equinoctial orbit, or -- for an IOD fallback
+    (kind 2) -- the IOD orbit, whose element type is in `iod_results`."""
+    r = np.asarray(results)
+    n = len(r)
+    kind = np.zeros(n, dtype=np.int32)
+    if "element_kind" in r.dtype.names:
+        ok = r["status"] == 0
+        kind[:] = r["element_kind"]
+    else:
+        ok = r["kind"] != 0
+        kind[r["kind"] == 1] = 1  # equinoctial
+        fb = r["kind"] == 2
+        if fb.any():
+            if iod_results is None:
+                raise ValueError("LSQ records with IOD fallbacks need iod_results for the element type")
+            kind[fb] = np.asarray(iod_results)["element_kind"][fb]
+    epoch = np.where(ok, r["epoch"], 0.0)
+    elem = np.ascontiguousarray(np.where(ok[:, None], r["elem"], 0.0).T)
+    return kind, np.ascontiguousarray(epoch), elem, ok
+
+
+def _compute_ephemerides(engine, results, observers, iod_results=None):
+    kind, epoch, elem, ok = orbits_of_results(results, iod_results)
+    # a failed fit is Err(InvalidConversion) in the reference's map (ephemeris/batch.rs:141-147): its entries carry
+    # status 9 and NaN, whatever the kernel made of the zeroed elements
+    out, status = engine.ephemeris_request(kind, epoch, elem, observers)
+    out[:, :, ~ok] = np.nan
+    status[:, ~ok] = 9
+    return out, status
 
 
 class OutfitGroup:
@@ -712,6 +751,10 @@ class OutfitGroup:
                                                                 _p(bf), _p(off), _p(tt), _p(ut), out.ctypes.data,
                                                                 status.ctypes.data))
         return out, status
+
+    def compute_ephemerides(self, results, observers, iod_results=None):
+        """FullOrbitResultExt::compute_ephemerides_parallel (ephemeris/batch.rs:149-183) over every GPU of the group."""
+        return _compute_ephemerides(self, results, observers, iod_results)
 
     def last_shards(self):
         """(cuts [n+1], wall ms per shard [n]) of the last group call."""

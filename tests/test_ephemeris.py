@@ -108,6 +108,43 @@ def test_gpu_ephemeris_from_iod_results(eph_env):
 
 
 @pytest.mark.gpu
+def test_compute_ephemerides_over_fit_results(eph_env):
+    """FullOrbitResultExt::compute_ephemerides (ephemeris/batch.rs:134-183): one call over the whole result array of
+    fit_full_iod / fit_lsq; failed fits are InvalidConversion entries, the others equal the per-orbit entry."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from outfit_b200 import DifferentialCorrectionConfig, IODParams, OutfitB200
+    synth = eph_env["synth"]
+    ctx = OutfitB200(0)
+    ctx.load_ephemeris(eph_env["table"])
+    batch = synth.make_trajectories(300, (3, 14), seed=33, table=eph_env["table"], max_triplets=10, n_noise=1)
+    p = IODParams.builder(n_noise_realizations=0, max_triplets=10)
+    res = ctx.fit_full_iod(batch, p)
+    assert (res["status"] != 0).any() and (res["status"] == 0).sum() > 100
+    tt, ut1, bf = synth.make_ephemeris_epochs(6, mjd0=float(np.median(batch["mjd_tt"])))
+    observers = [(bf, tt, ut1), (np.zeros(3), tt[:2].copy(), ut1[:2].copy())]
+    out, st = ctx.compute_ephemerides(res, observers)
+    assert out.shape == (9, 8, 300) and st.shape == (8, 300)
+    bad = res["status"] != 0
+    assert (st[:, bad] == 9).all() and np.isnan(out[:, :, bad]).all()
+    ok = ~bad
+    kind = np.ascontiguousarray(res["element_kind"][ok].astype(np.int32))
+    ref, rst = ctx.ephemeris_request(kind, np.ascontiguousarray(res["epoch"][ok]), np.ascontiguousarray(res["elem"][ok].T), observers)
+    assert np.array_equal(st[:, ok], rst) and np.array_equal(out[:, :, ok], ref, equal_nan=True)
+    # the LSQ records: corrected orbits are equinoctial, fallbacks take the IOD orbit and its element type
+    lsq, _ = ctx.fit_lsq(batch, p, DifferentialCorrectionConfig.default(), initial_orbits=res)
+    out2, st2 = ctx.compute_ephemerides(lsq, observers, iod_results=res)
+    fb = lsq["kind"] == 2
+    assert fb.any() and np.array_equal(out2[:, :, fb], out[:, :, fb], equal_nan=True) and np.array_equal(st2[:, fb], st[:, fb])
+    cor = lsq["kind"] == 1
+    good = (st2[:, cor] == 0) & (st[:, cor] == 0)
+    d = np.abs((out2[0][:, cor][good] - out[0][:, cor][good] + np.pi) % (2 * np.pi) - np.pi)
+    # the corrected orbit is another orbit through the same observations: close on the sky at the arc's epochs, not equal
+    assert cor.sum() > 50 and good.mean() > 0.9 and 0.0 < np.median(d) < 0.05
+
+
+@pytest.mark.gpu
 def test_gpu_second_order_aberration_matches_oracle(eph_env):
     """EphemerisConfig::aberration = AberrationOrder::Second (ephemeris/aberration.rs:60-75, 195-234): the line of sight
     from two Keplerian back-propagations by the light time.  GPU == oracle at the first-order tolerances; the two
