@@ -8,5 +8,5 @@ needs the compiled library AND a CUDA device and fails loudly otherwise.
 from .api import (  # noqa: F401
     IODParams, IodResult, OutfitB200, OutfitError, SolverType, library_path, load_library,
     RESULT_DTYPE, STATUS_NAMES, DifferentialCorrectionConfig, LSQ_RESULT_DTYPE, OBS_FIT_DTYPE,
-    OutfitGroup, pinned_empty, shard_ranges, EphemerisConfig, NBodyConfig, planet_gm, orbits_of_results,
+    OutfitGroup, pinned_empty, shard_ranges, EphemerisConfig, NBodyConfig, planet_gm, orbits_of_results, ephemeris_mode_epochs,
 )

@@ -574,6 +574,26 @@ class OutfitB200:
         return v.value
 
 
+def ephemeris_mode_epochs(mode):
+    """EphemerisMode::epochs() (ephemeris/request.rs:246-267) as MJD days: ("single", t) | ("at", [t, ...]) |
+    ("range", start, end, step_seconds): start, start + step, ... while <= end; a non-positive step or start > end gives
+    no epochs.  The reference steps hifitime Epochs, i.e. exact integer nanoseconds: so does this (no drift of a float sum)."""
+    kind = mode[0]
+    if kind == "single":
+        return np.array([float(mode[1])])
+    if kind == "at":
+        return np.asarray(mode[1], dtype=np.float64).copy()
+    if kind != "range":
+        raise ValueError("mode must be ('single', t), ('at', [...]) or ('range', start, end, step_seconds)")
+    start, end, step_s = float(mode[1]), float(mode[2]), float(mode[3])
+    ns_day = 86400 * 10 ** 9
+    a, b, h = round(start * ns_day), round(end * ns_day), round(step_s * 10 ** 9)
+    if h <= 0 or a > b:
+        return np.zeros(0)
+    k = np.arange((b - a) // h + 1, dtype=np.int64)
+    return (a + k * h) / ns_day
+
+
 def _flatten_request(observers):
     bf = np.ascontiguousarray([np.asarray(o[0], dtype=np.float64) for o in observers]).reshape(-1)
     off = np.concatenate([[0], np.cumsum([len(o[1]) for o in observers])]).astype(np.uint64)

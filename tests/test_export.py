@@ -61,3 +61,18 @@ def test_ephemeris_columns_and_display():
     assert c["ra"][4] == out[0, 1, 1] and c["d_dec_dt"][5] == out[8, 1, 2] and c["error"][5] == "InvalidOrbit"
     txt = export.display(0, 59000.5, [2.5, 0.1, 0.2, 1.0, 2.0, 3.0])
     assert "Keplerian" in txt and "semi_major_axis" in txt and "deg" in txt
+
+
+def test_ephemeris_mode_epochs_follow_the_reference_expansion():
+    """EphemerisMode::epochs (ephemeris/request.rs:246-267 and its tests :400-470): inclusive end when reachable,
+    nothing for a non-positive step or start > end, integer-nanosecond stepping."""
+    from outfit_b200 import ephemeris_mode_epochs as ep
+    assert list(ep(("single", 60000.5))) == [60000.5]
+    assert list(ep(("at", [60001.0, 60000.0, 60001.0]))) == [60001.0, 60000.0, 60001.0]
+    r = ep(("range", 60000.0, 60002.0, 86400.0))
+    assert list(r) == [60000.0, 60001.0, 60002.0]
+    assert len(ep(("range", 60000.0, 60002.0, 86400.0 * 0.75))) == 3        # 0, 0.75, 1.5 (2.25 > 2)
+    assert len(ep(("range", 60000.0, 59999.0, 60.0))) == 0 and len(ep(("range", 60000.0, 60001.0, 0.0))) == 0
+    assert len(ep(("range", 60000.0, 60001.0, -5.0))) == 0
+    long = ep(("range", 60000.0, 60100.0, 0.1))                             # 86.4 M steps would drift as a float sum
+    assert len(long) == 100 * 864000 + 1 and long[-1] == 60100.0
