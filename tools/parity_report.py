@@ -309,7 +309,7 @@ def c5_report(ctx, O, synth, et, n_orb, n_ep, log=print):
             "tolerance_note": "angles absolute (rad), distances relative, rates absolute (AU/day, rad/day) below 1e-2 per day and relative to |rate| / 1e-2 above"}
 
 
-def run(scale=1.0, out_path=None, log=print):
+def run(scale=1.0, out_path=None, log=print, seed_offset=0):
     from oracle import binding as O
     from outfit_b200 import OutfitB200, synth
     table = synth.make_ephemeris_table()
@@ -317,18 +317,18 @@ def run(scale=1.0, out_path=None, log=print):
     ctx.load_ephemeris(table)
     et = O.make_ephem_table(table["cheb"], table["jd_start"], table["block_days"], table["ipt"], table["emrat"])
     sz = lambda n, lo: max(lo, int(n * scale))
-    report = {"what": "GPU (C-ABI, liboutfit_b200.so) vs CPU oracle, full-configuration sweep", "scale": scale,
+    report = {"what": "GPU (C-ABI, liboutfit_b200.so) vs CPU oracle, full-configuration sweep", "scale": scale, "seed_offset": seed_offset,
               "host_threads": os.cpu_count()}
     try:
         report["git"] = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
     except Exception:
         report["git"] = None
     t0 = time.perf_counter()
-    c3, b3, g3, _ = iod_config_report(ctx, O, synth, table, et, "C3 100k x 12", sz(100_000, 500), 12, seed=20261018, log=log)
+    c3, b3, g3, _ = iod_config_report(ctx, O, synth, table, et, "C3 100k x 12", sz(100_000, 500), 12, seed=20261018 + seed_offset, log=log)
     report["c3"] = c3
-    report["c4"], _, _, _ = iod_config_report(ctx, O, synth, table, et, "C4 ragged 8-30", sz(20_000, 200), (8, 30), seed=20261019, log=log)
+    report["c4"], _, _, _ = iod_config_report(ctx, O, synth, table, et, "C4 ragged 8-30", sz(20_000, 200), (8, 30), seed=20261019 + seed_offset, log=log)
     report["c3_strict_no_noise"], _, _, _ = iod_config_report(ctx, O, synth, table, et, "C3 x12, n_noise_realizations = 0, K = 10",
-                                                              sz(50_000, 300), 12, seed=20261020, K=10, nn=0, log=log)
+                                                              sz(50_000, 300), 12, seed=20261020 + seed_offset, K=10, nn=0, log=log)
     report["lsq"] = lsq_report(ctx, O, et, b3, g3, min(len(g3), sz(20_000, 300)), log=log)
     report["c2"] = c2_report(ctx, O, synth, sz(10_000_000, 20_000), log=log)
     report["c5"] = c5_report(ctx, O, synth, et, sz(100_000, 500), 100, log=log)
@@ -345,6 +345,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "parity_r02.json"))
+    ap.add_argument("--seed-offset", type=int, default=0, help="shift the seeds of the IOD batches (an independent second sweep)")
     a = ap.parse_args()
-    r = run(a.scale, a.out)
+    r = run(a.scale, a.out, seed_offset=a.seed_offset)
     print(json.dumps({k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items() if kk not in ("flips",)}) for k, v in r.items()}, indent=1)[:6000])
