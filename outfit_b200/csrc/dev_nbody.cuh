@@ -42,8 +42,21 @@ constexpr int kNbMaxPert = 12;
 struct NbPert {                              // PerturberSnapshot (nbody.rs:17-32), per orbit
   double gm[kNbMaxPert];
   V3 pos[kNbMaxPert];
+  V3 aind[kNbMaxPert];                       // nb_prepare: the indirect acceleration of each perturber
   int n;
 };
+// the indirect acceleration of perturber p (the Sun's own fall towards it, nbody.rs:150-175): a constant of the orbit
+__device__ __forceinline__ V3 nb_indirect(const NbPert &P, int p) {
+  const double pd = sqrt(dot(P.pos[p], P.pos[p]));
+  if (!(pd > 1e-10)) return V3{0.0, 0.0, 0.0};
+  const double c = P.gm[p] / (pd * pd * pd);
+  return V3{c * P.pos[p].x, c * P.pos[p].y, c * P.pos[p].z};
+}
+// once per orbit, after gm / pos are filled: the right-hand side then reads the constant instead of recomputing a
+// square root and a division per perturber and evaluation (same values)
+__device__ __forceinline__ void nb_prepare(NbPert &P) {
+  for (int p = 0; p < kNbMaxPert; ++p) P.aind[p] = p < P.n ? nb_indirect(P, p) : V3{0.0, 0.0, 0.0};
+}
 
 // acceleration (lane 0 only needs it) and gravity gradient at heliocentric position r (nbody.rs:127-270)
 __device__ __forceinline__ void nb_field(const NbPert &P, V3 r, V3 &acc, double (&G)[9]) {
@@ -54,18 +67,13 @@ __device__ __forceinline__ void nb_field(const NbPert &P, V3 r, V3 &acc, double 
   for (int p = 0; p < P.n; ++p) {
     const double gm = P.gm[p];
     const V3 d = r - P.pos[p];
-    const double dist = sqrt(dot(d, d));
+    const double dist = bf_sqrt(dot(d, d));  // branch-free forms (dev_kepler.cuh): the same bits for normal operands
     const double dist3 = dist * dist * dist;
-    const double cdir = -gm / dist3;
-    V3 aind = V3{0.0, 0.0, 0.0};
-    const double pd = sqrt(dot(P.pos[p], P.pos[p]));
-    if (pd > 1e-10) {
-      const double c = gm / (pd * pd * pd);
-      aind = V3{c * P.pos[p].x, c * P.pos[p].y, c * P.pos[p].z};
-    }
+    const double cdir = bf_div(-gm, dist3);
+    const V3 aind = P.aind[p];
     acc = V3{acc.x + cdir * d.x + aind.x, acc.y + cdir * d.y + aind.y, acc.z + cdir * d.z + aind.z};
     const double dist5 = dist * dist * dist * dist * dist;
-    const double a = 1.0 / dist3, b = 3.0 / dist5;
+    const double a = bf_rcp(dist3), b = bf_div(3.0, dist5);
     const double dv[3] = {d.x, d.y, d.z};
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)

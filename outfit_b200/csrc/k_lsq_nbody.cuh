@@ -159,6 +159,7 @@ lsqnb_partials_kernel(LsqBatchDev B, NbCfgDev cfg, const double *__restrict__ gm
       P.pos[p] = V3{0.0, 0.0, 0.0};
     }
   }
+  nb_prepare(P);
   bool ok = need;
   double y[6] = {0, 0, 0, 0, 0, 0};
   if (role >= 1 && role < 7) y[role - 1] = 1.0;

@@ -37,6 +37,7 @@ propagate_nbody_kernel(size_t n, const int *__restrict__ kind, const double *__r
       P.pos[p] = V3{0.0, 0.0, 0.0};
     }
   }
+  nb_prepare(P);
   int st = OUTFIT_ST_OK;
   Equinoctial eq;
   {
@@ -107,6 +108,7 @@ ephemeris_nbody_state_kernel(size_t n_orbits, const int *__restrict__ kind, cons
       P.pos[p] = V3{0.0, 0.0, 0.0};
     }
   }
+  nb_prepare(P);
   int st = OUTFIT_ST_OK;
   Equinoctial eq;
   {
