@@ -63,14 +63,18 @@ __device__ __forceinline__ void nb_field(const NbPert &P, V3 r, V3 &acc, double 
   acc = V3{0.0, 0.0, 0.0};
 #pragma unroll
   for (int q = 0; q < 9; ++q) G[q] = 0.0;
+  // the perturber of the NEXT trip is fetched (local memory: dynamic index) before the arithmetic of this one
+  double gm_n = P.gm[0];
+  V3 pos_n = P.pos[0], aind_n = P.aind[0];
 #pragma unroll 1
   for (int p = 0; p < P.n; ++p) {
-    const double gm = P.gm[p];
-    const V3 d = r - P.pos[p];
+    const double gm = gm_n;
+    const V3 pos = pos_n, aind = aind_n;
+    if (p + 1 < P.n) { gm_n = P.gm[p + 1]; pos_n = P.pos[p + 1]; aind_n = P.aind[p + 1]; }
+    const V3 d = r - pos;
     const double dist = bf_sqrt(dot(d, d));  // branch-free forms (dev_kepler.cuh): the same bits for normal operands
     const double dist3 = dist * dist * dist;
     const double cdir = bf_div(-gm, dist3);
-    const V3 aind = P.aind[p];
     acc = V3{acc.x + cdir * d.x + aind.x, acc.y + cdir * d.y + aind.y, acc.z + cdir * d.z + aind.z};
     const double dist5 = dist * dist * dist * dist * dist;
     const double a = bf_rcp(dist3), b = bf_div(3.0, dist5);
@@ -216,13 +220,17 @@ __device__ __forceinline__ int nb_dop853(const NbPert &P, int role, double (&y)[
 #pragma unroll 1
     for (int s = 1; s < DOP853_STAGES; ++s) {
       const double *a = DOP853_A + (s * (s - 1)) / 2;
+      // y + h sum_j a_sj k_j over the non-zero a_sj (j = 0, then first(s) .. s - 1; a zero coefficient contributes an
+      // exact +0): stage-major, the six components of a stage together -- each component still sums in j order
+      double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int j = 0; j < s; j = (j == 0 ? (s <= 2 ? 1 : (s <= 4 ? 2 : 3)) : j + 1)) {
+        const double aj = a[j];
+        const double *kj = ksm + (size_t)(nb_stage_slot(j) * 6) * kNbThreads;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double acc = 0.0;
-        for (int j = 0; j < s; ++j)
-          if (j == 0 || j >= (s <= 2 ? 1 : (s <= 4 ? 2 : 3))) acc += K(j, c) * a[j];  // the a-matrix's zeros: exact +0
-        w[c] = y[c] + acc * h;
+        for (int c = 0; c < 6; ++c) acc[c] += kj[(size_t)c * kNbThreads] * aj;
       }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) w[c] = y[c] + acc[c] * h;
       double dw[6];
       nb_rhs_lane(P, role, w, nb_group_pos(w, lane), dw);
 #pragma unroll
