@@ -19,7 +19,7 @@ for j, rad in enumerate((0.0, 5.2, 9.5, 1.0, 1.52)):
     pos[j, 0], pos[j, 1] = rad * np.cos(lon), rad * np.sin(lon)
 cfg = DifferentialCorrectionConfig.default()
 two, _ = ctx.fit_lsq(batch, p, cfg, initial_orbits=iod)
-for ms in (0, 5000, 500):
+for ms in [int(x) for x in os.environ.get("PERF_BUDGETS", "0,5000,500").split(",")]:
     nb = NBodyConfig(n_perturbers=len(bodies), max_steps=ms)
     ctx.fit_lsq_nbody(batch, iod, gm, pos, cfg, nb)
     t0 = time.perf_counter()
