@@ -79,11 +79,14 @@ __device__ __forceinline__ void nb_field(const NbPert &P, V3 r, V3 &acc, double 
     const double dist5 = dist * dist * dist * dist * dist;
     const double a = bf_rcp(dist3), b = bf_div(3.0, dist5);
     const double dv[3] = {d.x, d.y, d.z};
+    // the gradient is symmetric to the bit (dv[r] * dv[c] == dv[c] * dv[r], the same formula either side of the
+    // diagonal): six entries per perturber, mirrored after the loop
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) G[3 * rr + cc] = G[3 * rr + cc] + (-gm) * ((rr == cc ? 1.0 : 0.0) * a - (dv[rr] * dv[cc]) * b);
+      for (int cc = rr; cc < 3; ++cc) G[3 * rr + cc] = G[3 * rr + cc] + (-gm) * ((rr == cc ? 1.0 : 0.0) * a - (dv[rr] * dv[cc]) * b);
   }
+  G[3] = G[1]; G[6] = G[2]; G[7] = G[5];
 }
 
 // derivative of this lane's 6 components at stage state w (its own 6 values) and stage position rs (from lane 0)
