@@ -145,6 +145,7 @@ lsqnb_partials_kernel(LsqBatchDev B, NbCfgDev cfg, const double *__restrict__ gm
   const LsqNbState *st = state + tr;
   const int phase = live && st->busy ? st->phase : 0;
   const bool need = phase != 0 && fit[gI].selection == 0;
+  if (!__any_sync(0xffffffffu, need)) return;  // a warp whose four observations all belong to finished trajectories
   double el[7];
   for (int j = 0; j < 7; ++j) el[j] = phase == 2 ? st->el_lin[j] : st->el[j];
   NbPert P;
