@@ -9,7 +9,7 @@ n = int(os.environ.get("PERF_N", "500000"))
 ctx = OutfitB200(0)
 kind, epoch, elem = synth.make_ephemeris_orbits(n, seed=1)
 rng = np.random.default_rng(2)
-t1 = epoch + rng.uniform(20.0, 120.0, n)
+t1 = epoch + rng.uniform(20.0, 120.0, n) * float(os.environ.get("PERF_SPAN_SCALE", "1"))
 bodies = (0, 5, 6, 3, 4)
 gm = np.array([planet_gm(b) for b in bodies])
 radius = {0: 0.0, 3: 1.0, 4: 1.52, 5: 5.2, 6: 9.5}
